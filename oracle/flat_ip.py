@@ -1,0 +1,219 @@
+"""CPU ORACLE (test infrastructure, NOT product code) — exact inner-product top-K.
+
+Restates, in numpy, what the reference delegates to ``faiss.IndexFlatIP`` behind
+``FaissIndex`` (reference ``src/serving/retrieval.py:70-136`` build, ``:141-197`` search,
+``:199-226`` add) and the in-repo exact twin ``scripts/evaluate_model.py:217-232`` /
+``src/evaluation/metrics.py:381-396`` (``np.dot`` + ``-inf`` mask + ``argsort[::-1][:k]``).
+
+PARITY UNPINNED at the Faiss boundary: ``faiss-cpu==1.7.4`` (reference ``requirements.txt:13``)
+is a third-party wheel that is neither vendored under /root/reference nor installable offline,
+and no reference test touches ``src/serving/retrieval.py``.  What is restated here is the
+published IndexFlatIP algorithm:
+  * scores are fp32 inner products (sgemm in query/database blocks),
+  * the result is the k largest, sorted by descending score,
+  * labels are int64 insertion-order row numbers,
+  * a candidate replaces the current k-th only if STRICTLY greater, so at the k boundary the
+    lower row id survives; we make the whole order deterministic: (score desc, row id asc),
+  * unfilled slots (k > ntotal) carry label -1 and score -FLT_MAX (``CMin<float>::neutral()``),
+  * ``normalize_L2``: x *= 1/sqrt(sum x^2) in fp32, zero rows untouched.
+It is pinned instead against the reference's own exact twin (np.dot + argsort) in
+``tests/test_oracle.py`` on tie-free data.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+leg may import this module.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+FLT_MAX = np.finfo(np.float32).max
+
+
+def normalize_L2(x: np.ndarray) -> np.ndarray:
+    """faiss.normalize_L2 (in place, fp32).  reference call sites retrieval.py:86,167,214."""
+    assert x.dtype == np.float32 and x.ndim == 2
+    nrm2 = np.einsum("ij,ij->i", x, x, dtype=np.float32)
+    inv = np.ones_like(nrm2)
+    nz = nrm2 > 0
+    inv[nz] = (1.0 / np.sqrt(nrm2[nz])).astype(np.float32)
+    x *= inv[:, None]
+    return x
+
+
+def _select_sorted(scores: np.ndarray, ids: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Top-k of one block under the total order (score desc, id asc).  scores [nq, m]."""
+    nq, m = scores.shape
+    kk = min(k, m)
+    if kk < m:
+        # argpartition is not tie-stable; widen to every element >= the k-th score, then sort.
+        part = np.argpartition(-scores, kk - 1, axis=1)[:, :kk]
+        kth = np.take_along_axis(scores, part, axis=1).min(axis=1)
+    out_s = np.full((nq, k), -FLT_MAX, dtype=np.float32)
+    out_i = np.full((nq, k), -1, dtype=np.int64)
+    for q in range(nq):
+        if kk < m:
+            cand = np.nonzero(scores[q] >= kth[q])[0]
+        else:
+            cand = np.arange(m)
+        order = np.lexsort((ids[cand], -scores[q, cand].astype(np.float64)))[:kk]
+        sel = cand[order]
+        out_s[q, :kk] = scores[q, sel]
+        out_i[q, :kk] = ids[sel]
+    return out_s, out_i
+
+
+def merge_topk(parts_s: Sequence[np.ndarray], parts_i: Sequence[np.ndarray], k: int):
+    """k-way merge of per-shard (scores [nq,k'], ids [nq,k']) lists; id -1 entries are padding."""
+    s = np.concatenate(parts_s, axis=1)
+    i = np.concatenate(parts_i, axis=1)
+    nq = s.shape[0]
+    out_s = np.full((nq, k), -FLT_MAX, dtype=np.float32)
+    out_i = np.full((nq, k), -1, dtype=np.int64)
+    for q in range(nq):
+        valid = i[q] >= 0
+        sq, iq = s[q, valid], i[q, valid]
+        order = np.lexsort((iq, -sq.astype(np.float64)))[:k]
+        out_s[q, : len(order)] = sq[order]
+        out_i[q, : len(order)] = iq[order]
+    return out_s, out_i
+
+
+class IndexFlatIP:
+    """faiss.IndexFlatIP restated (reference retrieval.py:98 ctor, :122/:217 add, :171 search)."""
+
+    def __init__(self, d: int, db_block: int = 65536, q_block: int = 1024):
+        self.d = int(d)
+        self.xb = np.zeros((0, self.d), dtype=np.float32)
+        self.db_block = db_block
+        self.q_block = q_block
+        self.is_trained = True
+
+    @property
+    def ntotal(self) -> int:
+        return self.xb.shape[0]
+
+    def add(self, x: np.ndarray) -> None:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        assert x.ndim == 2 and x.shape[1] == self.d
+        self.xb = x if self.ntotal == 0 else np.concatenate([self.xb, x], axis=0)
+
+    def search(self, q: np.ndarray, k: int, exclude: Optional[List[np.ndarray]] = None):
+        """Returns (D fp32 [nq,k] descending, I int64 [nq,k]).
+
+        ``exclude`` (optional, one int array per query) restates the eval twin's ``-inf`` masking of
+        a user's train items (scripts/evaluate_model.py:225-228): excluded rows can never be returned.
+        """
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        assert q.ndim == 2 and q.shape[1] == self.d
+        nq = q.shape[0]
+        D = np.full((nq, k), -FLT_MAX, dtype=np.float32)
+        I = np.full((nq, k), -1, dtype=np.int64)
+        for q0 in range(0, nq, self.q_block):
+            q1 = min(nq, q0 + self.q_block)
+            run_s = [np.full((q1 - q0, k), -FLT_MAX, dtype=np.float32)]
+            run_i = [np.full((q1 - q0, k), -1, dtype=np.int64)]
+            for b0 in range(0, self.ntotal, self.db_block):
+                b1 = min(self.ntotal, b0 + self.db_block)
+                s = q[q0:q1] @ self.xb[b0:b1].T  # fp32 sgemm block
+                ids = np.arange(b0, b1, dtype=np.int64)
+                if exclude is not None:
+                    for r in range(q0, q1):
+                        ex = np.asarray(exclude[r], dtype=np.int64)
+                        ex = ex[(ex >= b0) & (ex < b1)]
+                        s[r - q0, ex - b0] = -np.inf
+                bs, bi = _select_sorted(s, ids, k)
+                if exclude is not None:
+                    bi[np.isneginf(bs)] = -1
+                    bs[bi < 0] = -FLT_MAX
+                run_s.append(bs)
+                run_i.append(bi)
+            D[q0:q1], I[q0:q1] = merge_topk(run_s, run_i, k)
+        return D, I
+
+
+class FaissIndexOracle:
+    """FaissIndex Flat/cosine-or-IP wrapper semantics (reference retrieval.py:49-226)."""
+
+    def __init__(self, config: Optional[Dict] = None):
+        self.config = config or {}
+        self.dimension = self.config.get("dimension", 128)
+        self.metric = self.config.get("metric", "cosine")
+        self.index = None
+        self.id_map: Dict[int, str] = {}
+        self.reverse_id_map: Dict[str, int] = {}
+        self.current_size = 0
+
+    def build(self, embeddings: np.ndarray, ids: List[str]) -> None:  # retrieval.py:70-136
+        emb = embeddings.astype(np.float32)
+        if self.metric == "cosine":
+            normalize_L2(emb)
+        self.index = IndexFlatIP(self.dimension)
+        self.index.add(emb)
+        for i, item_id in enumerate(ids):
+            self.id_map[i] = item_id
+            self.reverse_id_map[item_id] = i
+        self.current_size = len(emb)
+
+    def add(self, embeddings: np.ndarray, ids: List[str]) -> None:  # retrieval.py:199-226
+        if self.index is None:
+            raise ValueError("Index not built yet")
+        emb = embeddings.astype(np.float32)
+        if self.metric == "cosine":
+            normalize_L2(emb)
+        self.index.add(emb)
+        for i, item_id in enumerate(ids):
+            self.id_map[self.current_size + i] = item_id
+            self.reverse_id_map[item_id] = self.current_size + i
+        self.current_size += len(emb)
+
+    def search(self, query_embeddings: np.ndarray, k: int = 10, filter_ids=None):  # retrieval.py:141-197
+        if self.index is None:
+            raise ValueError("Index not built yet")
+        q = query_embeddings.astype(np.float32)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        if self.metric == "cosine":
+            normalize_L2(q)
+        k_search = min(k * 2, self.current_size) if filter_ids else k
+        D, I = self.index.search(q, k_search)
+        out_ids, out_d = [], []
+        for r in range(len(q)):
+            ids_r, d_r = [], []
+            for j in range(k_search):
+                idx = int(I[r, j])
+                if idx >= 0 and idx in self.id_map:
+                    item_id = self.id_map[idx]
+                    if filter_ids is None or item_id in filter_ids:
+                        ids_r.append(item_id)
+                        d_r.append(float(D[r, j]))
+                        if len(ids_r) >= k:
+                            break
+            out_ids.append(ids_r)
+            out_d.append(d_r)
+        return out_ids, out_d
+
+
+def eval_twin_topk(user_emb: np.ndarray, item_emb: np.ndarray, train_items: Dict[int, list],
+                   users: Sequence[int], top_k: int) -> Dict[int, list]:
+    """The reference's own exact scorer, restated line for line in behaviour:
+    scripts/evaluate_model.py:217-232 (np.dot, -inf mask of train items, argsort[::-1][:k])."""
+    num_items = item_emb.shape[0]
+    scores = np.dot(user_emb, item_emb.T)
+    rec = {}
+    for j, u in enumerate(users):
+        s = scores[j].copy()
+        for t in train_items.get(u, []):
+            if t < num_items:
+                s[t] = -np.inf
+        rec[u] = np.argsort(s)[::-1][:top_k].tolist()
+    return rec
+
+
+def bf16_round(x: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even fp32 -> bf16 -> fp32 (the GPU catalogue storage type in BASELINE cfg 3)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    u = x.view(np.uint32).astype(np.uint64)
+    rounded = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return rounded.astype(np.uint32).view(np.float32)

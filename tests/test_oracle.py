@@ -1,0 +1,179 @@
+"""CPU tests: pin the oracle (oracle/) against the golden vectors produced by the imported reference
+(tests/golden/make_golden.py) and against the reference's own exact-retrieval twin."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import flat_ip, two_tower as tt
+
+
+def _tower(g, prefix, L, act="relu"):
+    params = {k[len(prefix) + 1:]: g[k] for k in g.files if k.startswith(prefix + ".")}
+    return tt.TowerOracle(params, L, act)
+
+
+@pytest.mark.parametrize("name", ["step_ml1m", "step_small"])
+def test_trainer_step_matches_reference(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    T = float(g["temperature"])
+    ut, it = _tower(g, "user", 2), _tower(g, "item", 2)
+    it_neg = _tower(g, "item", 2)
+    u = ut.forward(g["user_features"])
+    p = it.forward(g["pos_item_features"])
+    nf = g["neg_item_features"]
+    n = it_neg.forward(nf.reshape(-1, nf.shape[-1]))
+    np.testing.assert_allclose(u, g["user_emb"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(p, g["pos_emb"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(n, g["neg_emb"], rtol=1e-5, atol=1e-6)
+    ub, ib = float(g["user_bias"][0]), float(g["item_bias"][0])
+    le, du_e, dp_e, dn_e, db = tt.explicit_loss(u, p, n, T, ub, ib, want_grad=True)
+    li, du_i, dp_i = tt.in_batch_loss(u, p, T, want_grad=True)
+    assert abs(le - float(g["explicit_loss"])) <= 1e-5 * abs(le)
+    assert abs(li - float(g["inbatch_loss"])) <= 1e-5 * abs(li)
+    assert abs(0.7 * le + 0.3 * li - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    assert abs(tt.mixed_loss(u, p, n, T, ub, ib) - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    du = 0.7 * du_e + 0.3 * du_i
+    dp = 0.7 * dp_e + 0.3 * dp_i
+    dn = 0.7 * dn_e
+    np.testing.assert_allclose(du, g["grad.user_emb"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(dp, g["grad.pos_emb"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(dn, g["grad.neg_emb"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(0.7 * db, g["grad.user_bias"][0], rtol=1e-4, atol=1e-7)
+    gu, _ = ut.backward(du)
+    gp, _ = it.backward(dp)
+    gn, _ = it_neg.backward(dn)
+    for k, v in gu.items():
+        ref = g["grad.user." + k]
+        assert np.abs(v - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1e-6), k
+    for k in gp:
+        ref = g["grad.item." + k]
+        assert np.abs(gp[k] + gn[k] - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1e-6), k
+
+
+@pytest.mark.parametrize("name", ["step_ml1m", "step_small"])
+def test_running_stats_and_eval_forward(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    ut, it = _tower(g, "user", 2), _tower(g, "item", 2)
+    ut.forward(g["user_features"], update_running=True)
+    it.forward(g["pos_item_features"], update_running=True)
+    nf = g["neg_item_features"]
+    it.forward(nf.reshape(-1, nf.shape[-1]), update_running=True)  # second BN update in the same step
+    for k in g.files:
+        if k.startswith("after.") and "running" in k:
+            tower, key = k[len("after."):].split(".", 1)
+            got = (ut if tower == "user" else it).p[key]
+            np.testing.assert_allclose(got, g[k], rtol=1e-5, atol=1e-6, err_msg=k)
+    ue = ut.forward(g["user_features"], training=False)
+    pe = it.forward(g["pos_item_features"], training=False)
+    np.testing.assert_allclose(ue, g["user_emb_eval"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(pe, g["pos_emb_eval"], rtol=1e-5, atol=1e-6)
+    li = tt.in_batch_loss(ue, pe, float(g["temperature"]))
+    assert abs(li - float(g["inbatch_loss_eval"])) <= 1e-5 * abs(li)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "cat_*.npz"))))
+def test_categorical_towers_match_reference(path):
+    g = np.load(path)
+    act = str(g["activation"])
+    ut, it = _tower(g, "user", 2, act), _tower(g, "item", 2, act)
+    ucat = {k.split(".", 1)[1]: g[k] for k in g.files if k.startswith("user_cat.")}
+    icat = {k.split(".", 1)[1]: g[k] for k in g.files if k.startswith("item_cat.")}
+    u = ut.forward(g["user_num"], ucat)
+    i = it.forward(g["item_num"], icat)
+    np.testing.assert_allclose(u, g["user_emb"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(i, g["item_emb"], rtol=2e-5, atol=2e-6)
+    T = float(g["temperature"])
+    np.testing.assert_allclose((u * i).sum(-1) / T, g["similarity"], rtol=1e-4, atol=1e-5)
+    loss, du, di = tt.in_batch_loss(u, i, T, want_grad=True)
+    assert abs(loss - float(g["loss"])) <= 1e-5 * abs(loss)
+    gu, _ = ut.backward(du)
+    gi, _ = it.backward(di)
+    for tower, grads in (("user", gu), ("item", gi)):
+        for k, v in grads.items():
+            ref = g[f"grad.{tower}.{k}"]
+            assert np.abs(v - ref).max() <= 5e-5 * max(np.abs(ref).max(), 1e-6), (tower, k)
+            if k.startswith("embeddings."):
+                # gradient index set: exact (padding row 0 excluded)
+                field = k.split(".")[1]
+                idx = (ucat if tower == "user" else icat)[field]
+                touched = tt.embedding_touched_rows(idx)
+                assert np.array_equal(np.nonzero(np.abs(ref).sum(1))[0], touched) or \
+                    set(np.nonzero(np.abs(ref).sum(1))[0]) <= set(touched.tolist())
+                assert np.abs(v[0]).max() == 0
+
+
+def test_kat_losses(golden_dir):
+    g = np.load(os.path.join(golden_dir, "kat_losses.npz"))
+    U = np.eye(4, 8)
+    # closed forms: -ln(e^10/(e^10+3)) and friends
+    assert abs(tt.in_batch_loss(U, U, 0.1) - np.log1p(3 * np.exp(-10.0))) < 1e-9
+    assert abs(tt.in_batch_loss(U, U, 0.1) - float(g["inbatch"])) < 1e-6
+    assert abs(tt.explicit_loss(U, U, g["neg"], 0.1) - float(g["explicit"])) < 1e-6
+    assert abs(tt.explicit_loss(U, U, g["neg"], 0.1, 0.5, 0.25) - float(g["explicit_bias"])) < 1e-6
+
+
+# ---- exact inner-product top-K ------------------------------------------------------------------
+def test_flat_ip_matches_reference_eval_twin():
+    rng = np.random.default_rng(0)
+    items = rng.standard_normal((3416, 128)).astype(np.float32)
+    users = rng.standard_normal((64, 128)).astype(np.float32)
+    flat_ip.normalize_L2(items); flat_ip.normalize_L2(users)
+    train = {u: rng.choice(3416, size=rng.integers(0, 200), replace=False).tolist() for u in range(64)}
+    twin = flat_ip.eval_twin_topk(users, items, train, list(range(64)), 100)
+    idx = flat_ip.IndexFlatIP(128, db_block=1000)
+    idx.add(items)
+    D, I = idx.search(users, 100, exclude=[np.array(train[u], dtype=np.int64) for u in range(64)])
+    for u in range(64):
+        assert I[u].tolist() == twin[u]
+    assert np.all(np.diff(D, axis=1) <= 0)
+
+
+def test_flat_ip_semantics():
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((50, 16)).astype(np.float32)
+    idx = flat_ip.IndexFlatIP(16)
+    idx.add(x[:30]); idx.add(x[30:])
+    assert idx.ntotal == 50
+    q = rng.standard_normal((3, 16)).astype(np.float32)
+    D, I = idx.search(q, 60)  # k > ntotal: padded with -1 / -FLT_MAX
+    assert np.all(I[:, 50:] == -1) and np.all(D[:, 50:] == -flat_ip.FLT_MAX)
+    full = q @ x.T
+    for r in range(3):
+        assert I[r, :50].tolist() == np.lexsort((np.arange(50), -full[r].astype(np.float64))).tolist()
+    # ties: duplicated rows -> lower row id first
+    xi = rng.integers(-4, 5, size=(5, 16)).astype(np.float32)  # exactly representable -> exact ties
+    qi = rng.integers(-4, 5, size=(1, 16)).astype(np.float32)
+    xd = np.concatenate([xi, xi], 0)
+    idx2 = flat_ip.IndexFlatIP(16); idx2.add(xd)
+    D2, I2 = idx2.search(qi, 4)
+    best = int(np.lexsort((np.arange(5), -(qi[0] @ xi.T)))[0])
+    assert I2[0, 0] == best and I2[0, 1] == best + 5 and D2[0, 0] == D2[0, 1]
+
+
+def test_normalize_and_wrapper_semantics():
+    x = np.array([[3.0, 4.0], [0.0, 0.0]], dtype=np.float32)
+    flat_ip.normalize_L2(x)
+    np.testing.assert_allclose(x, [[0.6, 0.8], [0.0, 0.0]], rtol=1e-6)
+    fi = flat_ip.FaissIndexOracle({"dimension": 4})
+    with pytest.raises(ValueError, match="Index not built yet"):
+        fi.search(np.zeros((1, 4), np.float32))
+    rng = np.random.default_rng(2)
+    emb = rng.standard_normal((20, 4)).astype(np.float32)
+    ids = [f"item_{i}" for i in range(20)]
+    fi.build(emb, ids)
+    got_ids, got_d = fi.search(emb[3], k=5)  # 1-D query promoted (retrieval.py:162-163)
+    assert got_ids[0][0] == "item_3" and abs(got_d[0][0] - 1.0) < 1e-5 and len(got_ids[0]) == 5
+    allow = ["item_1", "item_2", "item_3"]
+    f_ids, _ = fi.search(emb[:2], k=2, filter_ids=allow)
+    assert all(set(r) <= set(allow) for r in f_ids)
+    fi.add(emb[:2] * 2.0, ["dup_a", "dup_b"])
+    assert fi.current_size == 22 and fi.id_map[21] == "dup_b"
+
+
+def test_bf16_round():
+    import torch
+    x = np.random.default_rng(3).standard_normal(4096).astype(np.float32)
+    ref = torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
+    assert np.array_equal(flat_ip.bf16_round(x), ref)
