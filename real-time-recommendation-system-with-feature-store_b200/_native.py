@@ -1,0 +1,76 @@
+"""ctypes binding of libb200rec.so (the C-ABI in include/b200rec.h).  No fallback: a missing library raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200rec.so")
+
+_lib = None
+
+_P = C.c_void_p
+_I64 = C.c_int64
+_I = C.c_int
+_F = C.c_float
+_SZ = C.c_size_t
+_U64 = C.c_uint64
+
+# name -> (restype, argtypes); one entry per symbol declared in include/b200rec.h
+SIGNATURES = {
+    "b200rec_last_error": (C.c_char_p, []),
+    "b200rec_version": (_I, []),
+    "b200rec_launch_count": (_I64, []),
+    "b200rec_split_bf16": (_I, [_P, _I64, _I64, _I64, _I, _P, _I64, _I, _I, _P]),
+    "b200rec_normalize_rows": (_I, [_P, _I64, _I64, _I64, _I, _I, _P, _I64, _P, _P, _I64, _I, _I, _P]),
+    "b200rec_gemm_bf16_tn": (_I, [_P, _I64, _I64, _P, _I64, _I64, _I64, _P, _I64, _P, _F, _I, _P]),
+    "b200rec_topk_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I]),
+    "b200rec_flat_ip_topk": (_I, [_P, _I64, _I64, _P, _I64, _I, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
+    "b200rec_topk_merge": (_I, [_P, _P, _I, _I64, _I, _I, _P, _P, _P]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU or PyTorch fallback for the b200rec kernels)")
+        _lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    return _lib
+
+
+def last_error() -> str:
+    return lib().b200rec_last_error().decode()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"b200rec {what} failed: {last_error()}")
+
+
+def launch_count() -> int:
+    return int(lib().b200rec_launch_count())
+
+
+def ptr(t):
+    """device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda, "b200rec kernels take CUDA tensors only"
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def pad64(n: int) -> int:
+    return (n + 63) // 64 * 64

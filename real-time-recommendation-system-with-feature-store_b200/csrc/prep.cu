@@ -1,0 +1,163 @@
+// Operand preparation: fp32 -> bf16 tensor-core operands (optionally L2-normalised, optionally transposed,
+// optionally expanded into split-bf16 terms so that a bf16 GEMM reproduces fp32 products).
+//   x = h + m + l exactly, h = bf16(x), m = bf16(x-h), l = bf16(x-h-m)
+//   terms 1: left [h]            right [h]
+//   terms 3: left [h l h]        right [h h l]          (error ~2^-17 per product)
+//   terms 6: left [h h m h l m]  right [h m h l h m]    (drops only m*l, l*m, l*l: ~2^-24, i.e. fp32 grade)
+// Each block is kpad columns wide (zero padded), so left . right^T over K = terms*kpad is the fp32 product sum.
+// HBM-bound elementwise kernels: one warp per row, coalesced loads, 2-byte stores coalesced along the row.
+#include "host_util.h"
+#include "tc_common.cuh"
+#include "../../include/b200rec.h"
+
+namespace b200 {
+
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
+  h = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(h);
+  m = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(m);
+  l = __float2bfloat16_rn(r2);
+}
+
+// which part (0=h,1=m/lo,2=l) goes into block t for (terms, side)
+__device__ __forceinline__ int part_of(int terms, int side, int t) {
+  if (terms == 1) return 0;
+  if (terms == 3) {
+    // left [h l h], right [h h l]  ("l" here is the first residual = m)
+    const int L[3] = {0, 1, 0}, R[3] = {0, 0, 1};
+    return side == 0 ? L[t] : R[t];
+  }
+  const int L6[6] = {0, 0, 1, 0, 2, 1}, R6[6] = {0, 1, 0, 2, 0, 1};
+  return side == 0 ? L6[t] : R6[t];
+}
+
+__device__ __forceinline__ void store_terms(__nv_bfloat16* drow, int64_t c, int64_t kpad, int terms, int side,
+                                            float x) {
+  __nv_bfloat16 p[3];
+  split3(x, p[0], p[1], p[2]);
+#pragma unroll
+  for (int t = 0; t < 6; ++t)
+    if (t < terms) drow[t * kpad + c] = p[part_of(terms, side, t)];
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+
+// one warp per row
+__global__ void __launch_bounds__(256)
+prep_rows_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int64_t ld_src, int normalize,
+                 int faiss_zero_rule, float* __restrict__ dst_f32, int64_t ld_dst, float* __restrict__ norms_out,
+                 __nv_bfloat16* __restrict__ dst_bf16, int64_t kpad, int terms, int side) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps_total) {
+    const float* srow = src + r * ld_src;
+    float scale = 1.0f, denom = 1.0f;
+    if (normalize) {
+      float ss = 0.f;
+      for (int64_t c = lane; c < cols; c += 32) {
+        const float x = __ldg(srow + c);
+        ss = fmaf(x, x, ss);
+      }
+      ss = warp_sum(ss);
+      float nrm = sqrtf(ss);
+      if (faiss_zero_rule) {
+        // faiss::fvec_renorm_L2: x *= 1/sqrt(sum x^2) when the norm is > 0  (retrieval.py:86,167,214)
+        scale = (ss > 0.f) ? (1.0f / nrm) : 1.0f;
+        if (norms_out && lane == 0) norms_out[r] = nrm;
+      } else {
+        // F.normalize(p=2, eps=1e-12): x / max(||x||, eps)  (two_tower.py:132,279)
+        nrm = fmaxf(nrm, 1e-12f);
+        denom = nrm;
+        if (norms_out && lane == 0) norms_out[r] = nrm;
+      }
+    }
+    __nv_bfloat16* drow = dst_bf16 ? dst_bf16 + r * terms * kpad : nullptr;
+    const int64_t cmax = dst_bf16 ? kpad : cols;
+    for (int64_t c = lane; c < cmax; c += 32) {
+      float x = 0.f;
+      if (c < cols) {
+        x = __ldg(srow + c);
+        if (normalize) x = faiss_zero_rule ? x * scale : x / denom;
+        if (dst_f32) dst_f32[r * ld_dst + c] = x;
+      }
+      if (drow) store_terms(drow, c, kpad, terms, side, x);
+    }
+  }
+}
+
+// dst[r, c] = src[c, r]   (src has `cols` rows of `rows` floats); 32x32 tiles through padded smem
+__global__ void __launch_bounds__(256)
+prep_transpose_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int64_t ld_src,
+                      __nv_bfloat16* __restrict__ dst, int64_t kpad, int terms, int side) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 32;  // dst rows   = src columns
+  const int64_t c0 = (int64_t)blockIdx.x * 32;  // dst cols   = src rows
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t sr = c0 + i, sc = r0 + tx;
+    tile[i][tx] = (sr < cols && sc < rows) ? __ldg(src + sr * ld_src + sc) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + i, c = c0 + tx;
+    if (r < rows && c < kpad) store_terms(dst + r * terms * kpad, c, kpad, terms, side, tile[tx][i]);
+  }
+}
+
+static int check_terms(int terms, int side) {
+  if (terms != 1 && terms != 3 && terms != 6) return fail("terms must be 1, 3 or 6 (got %d)", terms);
+  if (side != 0 && side != 1) return fail("side must be 0 (left) or 1 (right)");
+  return 0;
+}
+
+}  // namespace b200
+
+extern "C" int b200rec_split_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_src, int transpose,
+                                  void* dst, int64_t kpad, int terms, int side, void* stream) {
+  using namespace b200;
+  if (!src || !dst) return fail("split_bf16: null pointer");
+  if (rows <= 0 || cols <= 0) return fail("split_bf16: empty input");
+  if (kpad < cols || (kpad % 8)) return fail("split_bf16: kpad must be >= cols and a multiple of 8");
+  if (check_terms(terms, side)) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!transpose) {
+    const int64_t blocks = (rows + 7) / 8;
+    const int grid = (int)(blocks < (int64_t)num_sms() * 16 ? blocks : (int64_t)num_sms() * 16);
+    prep_rows_kernel<<<grid, 256, 0, st>>>(src, rows, cols, ld_src, 0, 0, nullptr, 0, nullptr,
+                                           reinterpret_cast<__nv_bfloat16*>(dst), kpad, terms, side);
+    B200_LAUNCH_OK("prep_rows_kernel");
+  } else {
+    dim3 grid((unsigned)((kpad + 31) / 32), (unsigned)((rows + 31) / 32));
+    if (grid.y > 65535) return fail("split_bf16(transpose): too many rows (%lld)", (long long)rows);
+    prep_transpose_kernel<<<grid, 256, 0, st>>>(src, rows, cols, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), kpad,
+                                                terms, side);
+    B200_LAUNCH_OK("prep_transpose_kernel");
+  }
+  return 0;
+}
+
+extern "C" int b200rec_normalize_rows(const float* src, int64_t rows, int64_t cols, int64_t ld_src, int normalize,
+                                      int faiss_zero_rule, float* dst_f32, int64_t ld_dst, float* norms_out,
+                                      void* dst_bf16, int64_t kpad, int terms, int side, void* stream) {
+  using namespace b200;
+  if (!src) return fail("normalize_rows: null src");
+  if (rows <= 0 || cols <= 0) return fail("normalize_rows: empty input");
+  if (dst_bf16) {
+    if (kpad < cols || (kpad % 8)) return fail("normalize_rows: kpad must be >= cols and a multiple of 8");
+    if (check_terms(terms, side)) return 1;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t blocks = (rows + 7) / 8;
+  const int grid = (int)(blocks < (int64_t)num_sms() * 16 ? blocks : (int64_t)num_sms() * 16);
+  prep_rows_kernel<<<grid, 256, 0, st>>>(src, rows, cols, ld_src, normalize, faiss_zero_rule, dst_f32, ld_dst,
+                                         norms_out, reinterpret_cast<__nv_bfloat16*>(dst_bf16), kpad, terms, side);
+  B200_LAUNCH_OK("prep_rows_kernel");
+  return 0;
+}

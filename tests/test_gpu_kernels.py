@@ -1,0 +1,138 @@
+"""GPU parity tests of the low-level kernels, called through the C-ABI (ctypes) and checked against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16_round(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (100, 17, 20), (1024, 256, 3), (300, 128, 256), (4096, 64, 128)])
+@pytest.mark.parametrize("terms", [1, 6])
+def test_gemm_matches_fp32(M, N, K, terms):
+    from b200rec import kernels as KR
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    out = KR.matmul_nt(x.cuda(), w.cuda(), b.cuda(), terms=terms).cpu()
+    if terms == 1:
+        ref = _bf16_round(x).double() @ _bf16_round(w).double().T + b.double()
+        tol = 1e-5
+    else:
+        ref = x.double() @ w.double().T + b.double()
+        tol = 2e-6
+    err = (out.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= tol * max(scale, 1.0), f"gemm {M}x{N}x{K} terms={terms}: max abs err {err:.3e} (scale {scale:.3e})"
+
+
+def test_gemm_split_k():
+    from b200rec import kernels as KR
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(96, 5000, generator=g)
+    w = torch.randn(40, 5000, generator=g)
+    xo, wo = KR.split_bf16(x.cuda(), 6, 0), KR.split_bf16(w.cuda(), 6, 1)
+    out = KR.gemm_tn(xo, wo, 96, 40, xo.shape[1], None, 0.5, k_splits=16).cpu()
+    ref = 0.5 * (x.double() @ w.double().T)
+    assert (out.double() - ref).abs().max().item() <= 2e-4
+
+
+def test_split_transpose():
+    from b200rec import kernels as KR
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(70, 130, generator=g)
+    w = torch.randn(50, 130, generator=g)
+    # x^T [130,70] . w^T[130,50]^T  = x^T w  -> [70... ] check  (x^T)(w^T)^T = x^T w  is [130? no]
+    a = KR.split_bf16(x.cuda(), 6, 0, transpose=True)   # [130, 6*128]
+    b = KR.split_bf16(w.cuda(), 6, 1, transpose=True)   # [130, 6*64]
+    assert a.shape == (130, 6 * 128) and b.shape == (130, 6 * 64)
+    # contraction needs equal K: use x^T [130,70] against y^T with y [33,70]... build directly
+    y = torch.randn(33, 70, generator=g)
+    yo = KR.split_bf16(y.cuda(), 6, 1)                   # [33, 6*128]
+    out = KR.gemm_tn(a, yo, 130, 33, a.shape[1]).cpu()   # x^T y^T = (y x)^T
+    ref = (x.double().T @ y.double().T)
+    assert (out.double() - ref).abs().max().item() <= 2e-5
+
+
+def _oracle_topk(cat, qry, k, exclude=None):
+    from oracle.flat_ip import IndexFlatIP
+    ix = IndexFlatIP(cat.shape[1])
+    ix.add(cat)
+    return ix.search(qry, k, exclude=exclude)
+
+
+def _check_topk(D, I, rD, rI, cat, qry):
+    D, I = D.cpu().numpy(), I.cpu().numpy()
+    # scores: tensor-core fp32 accumulation of exact bf16 products vs numpy sgemm
+    assert np.allclose(D, rD, atol=2e-5, rtol=0), f"scores differ: max {np.abs(D - rD).max():.3e}"
+    same = I == rI
+    if not same.all():
+        # ids may legitimately differ only inside groups of scores tied within 1e-5 (north_star tolerance)
+        bad = np.argwhere(~same)
+        for qi, j in bad[:2000]:
+            s_ref = rD[qi, j]
+            s_got = float(cat[I[qi, j]].astype(np.float64) @ qry[qi].astype(np.float64)) if I[qi, j] >= 0 else None
+            assert s_got is not None and abs(s_got - s_ref) <= 1e-5, \
+                f"query {qi} rank {j}: got id {I[qi, j]} (score {s_got}) want {rI[qi, j]} (score {s_ref})"
+    for qi in range(D.shape[0]):
+        valid = I[qi] >= 0
+        assert len(set(I[qi][valid].tolist())) == valid.sum(), "duplicate ids in result"
+        assert (np.diff(D[qi]) <= 0).all(), "scores not descending"
+
+
+@pytest.mark.parametrize("N,Q,D,k", [(5000, 10, 128, 100), (20000, 130, 64, 10), (100000, 300, 128, 100),
+                                     (70000, 600, 128, 100), (3000, 5, 192, 1000), (50, 3, 64, 100),
+                                     (200000, 1100, 64, 37)])
+def test_flat_ip_topk_matches_oracle(N, Q, D, k):
+    from b200rec import kernels as KR
+    from oracle.flat_ip import bf16_round, normalize_L2
+    rng = np.random.default_rng(N + Q + D + k)
+    cat = bf16_round(normalize_L2(rng.standard_normal((N, D)).astype(np.float32)))
+    qry = bf16_round(normalize_L2(rng.standard_normal((Q, D)).astype(np.float32)))
+    rD, rI = _oracle_topk(cat, qry, k)
+    ld = (D + 63) // 64 * 64
+    c = torch.zeros((N, ld), dtype=torch.bfloat16, device="cuda")
+    q = torch.zeros((Q, ld), dtype=torch.bfloat16, device="cuda")
+    c[:, :D] = torch.from_numpy(cat).cuda().to(torch.bfloat16)
+    q[:, :D] = torch.from_numpy(qry).cuda().to(torch.bfloat16)
+    Dg, Ig = KR.flat_ip_topk(c, q, k)
+    torch.cuda.synchronize()
+    _check_topk(Dg, Ig, rD, rI, cat, qry)
+
+
+def test_flat_ip_topk_ties_and_exclusion():
+    from b200rec import kernels as KR
+    rng = np.random.default_rng(3)
+    N, Q, D, k = 40000, 140, 64, 50
+    base = rng.integers(-2, 3, size=(N, D)).astype(np.float32)   # small integers: exact scores, massive ties
+    qry = rng.integers(-2, 3, size=(Q, D)).astype(np.float32)
+    excl = [np.sort(rng.choice(N, size=rng.integers(0, 300), replace=False)).astype(np.int32) for _ in range(Q)]
+    rD, rI = _oracle_topk(base, qry, k, exclude=excl)
+    c = torch.from_numpy(base).cuda().to(torch.bfloat16)
+    q = torch.from_numpy(qry).cuda().to(torch.bfloat16)
+    indptr = torch.tensor(np.concatenate([[0], np.cumsum([len(e) for e in excl])]), dtype=torch.int64, device="cuda")
+    rows = torch.from_numpy(np.concatenate(excl)).cuda()
+    Dg, Ig = KR.flat_ip_topk(c, q, k, exclude_indptr=indptr, exclude_rows=rows)
+    torch.cuda.synchronize()
+    # exact integer scores: the total order (score desc, row asc) must be reproduced bit for bit
+    assert np.array_equal(Dg.cpu().numpy(), rD)
+    assert np.array_equal(Ig.cpu().numpy(), rI)
+
+
+def test_topk_merge_matches_oracle():
+    from b200rec import kernels as KR
+    from oracle.flat_ip import merge_topk
+    rng = np.random.default_rng(11)
+    parts, Q, kin, kout = 8, 77, 100, 100
+    s = rng.standard_normal((parts, Q, kin)).astype(np.float32)
+    s = np.round(s, 1)  # ties
+    ids = np.stack([rng.permutation(100000)[: Q * kin].reshape(Q, kin) + p * 100000 for p in range(parts)]).astype(np.int64)
+    ids[0, :, -5:] = -1
+    rs, ri = merge_topk([s[p] for p in range(parts)], [ids[p] for p in range(parts)], kout)
+    gs, gi = KR.topk_merge(torch.from_numpy(s).cuda(), torch.from_numpy(ids).cuda(), kout)
+    assert np.array_equal(gs.cpu().numpy(), rs)
+    assert np.array_equal(gi.cpu().numpy(), ri)
