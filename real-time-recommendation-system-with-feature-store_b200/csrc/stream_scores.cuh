@@ -5,7 +5,8 @@
 //
 // Work decomposition (persistent, static, perfectly balanced): the (supertile, X-tile) space is linearised and cut
 // into gridDim.x equal ranges, so a CTA handles at most a few "segments" (one supertile, a contiguous tile range).
-// Warp roles: 0 = TMA producer, 1 = tcgen05.mma issuer, 2 = TMEM allocator, 3 = idle, 4..11 = epilogue.
+// Warp roles: 0 = TMA producer, 1 = tcgen05.mma issuer, 2 = TMEM allocator, 3 = idle, 4..11 = epilogue (consume TMEM),
+// 12..15 = helper warps owned by the epilogue policy (asynchronous candidate compaction for top-K; idle for LSE).
 #pragma once
 #include "host_util.h"
 #include "tc_common.cuh"
@@ -13,11 +14,14 @@
 namespace b200 {
 
 constexpr int ST_EPI_WARP0 = 4;
-constexpr int ST_THREADS = 12 * 32;
+constexpr int ST_HELP_WARP0 = 12;
+constexpr int ST_HELP_WARPS = 4;
+constexpr int ST_THREADS = 16 * 32;
 constexpr int ST_QTILE_BYTES = 128 * 64 * 2;  // one 128-row x 64-col bf16 SW128 block
 constexpr int ST_MAX_STAGES = 16;
 constexpr int ST_SMEM_LIMIT = 232448;  // 227 KB
-constexpr int ST_TAIL_BYTES = 512 /*barriers + tmem slot*/ + 8 * 256 * 4 /*per-warp histograms*/;
+constexpr int ST_SCRATCH_BYTES = 2112 * 4 /*histograms + mailboxes*/ + 4 * 704 * 8 /*helper staging*/;
+constexpr int ST_TAIL_BYTES = 512 /*barriers + tmem slot*/ + ST_SCRATCH_BYTES;
 
 struct StreamGeom {
   long long N;      // streamed rows
@@ -75,6 +79,7 @@ stream_scores_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   constexpr int QPT = NQ >= 2 ? NQ / 2 : 1;          // queries owned by one epilogue thread
   constexpr int EPI_WARPS = NQ >= 2 ? 8 : 4;         // warps that actually consume TMEM
   constexpr int STAGE_BYTES = BN * 128;
+  static_assert(NQ <= 2, "helper-warp mailboxes are sized for 256 resident rows");
   static_assert(2 * NQ * BN <= 512, "two accumulator buffers must fit the 512 TMEM columns");
 
   extern __shared__ uint8_t smem_raw[];
@@ -89,7 +94,7 @@ stream_scores_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint64_t* q_full = acc_empty + 2;
   uint64_t* q_empty = q_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 1);
-  uint32_t* hist_all = reinterpret_cast<uint32_t*>(tail + 512);
+  uint32_t* scratch = reinterpret_cast<uint32_t*>(tail + 512);  // policy-owned shared scratch (ST_SCRATCH_BYTES)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -112,6 +117,7 @@ stream_scores_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 3) Epi::init_scratch(scratch, lane);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -195,7 +201,6 @@ stream_scores_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const int ew = warp - ST_EPI_WARP0;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
     const int half = ew >> 2;
-    uint32_t* hist = hist_all + ew * 256;
     Epi epi;
     uint32_t tc = 0;
     for (long long w = w_begin; w < w_end;) {
@@ -207,10 +212,10 @@ stream_scores_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       int qslot[QPT];
 #pragma unroll
       for (int a = 0; a < QPT; ++a) qslot[a] = (half * QPT + a) * 128 + quarter * 32 + lane;
-      epi.template begin_segment<NQ, QPT>(ea, g, s, qslot, lane);
+      epi.template begin_segment<NQ, QPT>(ea, g, s, part, qslot, lane, scratch);
       for (long long t = t0; t < t1; ++t, ++tc) {
         const uint32_t buf = tc & 1;
-        epi.template pre_tile<NQ, BN, QPT>(ea, g, qslot, lane, hist);
+        epi.template pre_tile<NQ, BN, QPT>(ea, g, qslot, lane, scratch);
         mbar_wait(&acc_full[buf], (tc >> 1) & 1);
         tc_fence_after();
 #pragma unroll
@@ -223,9 +228,12 @@ stream_scores_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
       }
-      epi.template end_segment<NQ, QPT>(ea, g, s, part, qslot, lane, hist);
+      epi.template end_segment<NQ, QPT>(ea, g, s, part, qslot, lane, scratch);
       w += t1 - t0;
     }
+    Epi::epilogue_exit(scratch, lane);
+  } else if (warp >= ST_HELP_WARP0) {
+    Epi::template helper<NQ, EPI_WARPS>(ea, g, warp - ST_HELP_WARP0, lane, scratch);
   }
   tc_fence_before();
   __syncthreads();

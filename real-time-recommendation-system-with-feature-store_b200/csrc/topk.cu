@@ -2,13 +2,18 @@
 // Replaces faiss.IndexFlatIP.search (reference src/serving/retrieval.py:171) and the np.dot+argsort eval twin
 // (scripts/evaluate_model.py:217-232, src/evaluation/metrics.py:381-396).
 //
-// Per (CTA, query): a running threshold tau (= current k-th best of what this CTA has seen) lives in a register of
-// the thread that owns the query's TMEM lane; a score enters the query's candidate buffer only if it beats tau
-// (strictly: at equal score the earlier = lower row id wins, faiss' heap rule).  When a buffer is about to overflow a
-// warp radix-selects its k best 64-bit keys (ordered score << 32 | ~row) and raises tau.  At segment end the k
-// survivors are published; a second small kernel merges the <= max_parts partial lists of every query and sorts them
-// (score desc, row asc).  Scores are never written to HBM.
+// Every query owns ONE running top-k list T in global memory (L2 resident) shared by all CTAs that scan a slice of
+// the catalogue for it, guarded by a spin lock, plus a published threshold tau = score of T's k-th entry.
+//   * epilogue threads (one TMEM lane = one query) only FILTER (score >= tau) and APPEND 64-bit keys
+//     (ordered score << 32 | ~row) to a private double-buffered candidate list;
+//   * when a list fills, its owner posts a request in a shared-memory mailbox and flips lists; four helper warps
+//     take the lock, merge list and T with a warp radix select staged in shared memory, raise tau, release;
+//   * helper warps also refresh the per-slot thresholds in shared memory from the global tau, so every feeder
+//     benefits from what the other feeders of the same query have already seen (single-stream insertion count).
+// Ties: keys order by (score desc, row asc) and the filter is >=, so the result is the exact faiss order even when a
+// later-merged feeder holds a lower row id at the threshold score.  Scores are never written to HBM.
 #include <cfloat>
+#include <cstdlib>
 #include "stream_scores.cuh"
 #include "../../include/b200rec.h"
 
@@ -57,17 +62,29 @@ __device__ __forceinline__ int warp_pick_digit(const uint32_t* hist, int& need, 
   return d;
 }
 
-// Keep the k largest of buf[0..n) (n > k, keys distinct), compacted to buf[0..k); returns the smallest kept key.
-__device__ __noinline__ uint64_t warp_compact_topk(uint64_t* buf, int n, int k, uint32_t* hist, int lane) {
+// Exact k-th-largest threshold of `n` distinct 64-bit keys produced by `load(i)` (n > k): returns (prefix, shift) such
+// that exactly k keys satisfy (key >> shift) >= prefix.  MSB-first radix select, 8-bit digits, one warp.
+template <class Loader>
+__device__ __forceinline__ void warp_select_threshold(const Loader& load, int n, int k, uint32_t* hist, int lane,
+                                                      uint64_t& prefix_out, int& shift_out) {
   uint64_t prefix = 0;
   int need = k, shift = 56;
   for (int pass = 0; pass < 8; ++pass, shift -= 8) {
     for (int i = lane; i < 256; i += 32) hist[i] = 0;
     __syncwarp();
-    for (int i = lane; i < n; i += 32) {
-      const uint64_t key = __ldcg(buf + i);
-      const bool match = (pass == 0) || ((key >> (shift + 8)) == prefix);
-      if (match) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
+    for (int i0 = 0; i0 < n; i0 += 128) {  // 4 independent loads in flight per lane
+      uint64_t key[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 32 + lane;
+        key[u] = (i < n) ? load(i) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 32 + lane;
+        const bool match = (i < n) && ((pass == 0) || ((key[u] >> (shift + 8)) == prefix));
+        if (match) atomicAdd(&hist[(uint32_t)(key[u] >> shift) & 255u], 1u);
+      }
     }
     __syncwarp();
     int bucket;
@@ -77,166 +94,330 @@ __device__ __noinline__ uint64_t warp_compact_topk(uint64_t* buf, int n, int k, 
     if (bucket == need) break;
   }
   if (shift < 0) shift = 0;
-  int base = 0;
-  uint64_t minkey = ~0ull;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  for (int i0 = 0; i0 < n; i0 += 32) {
-    const int i = i0 + lane;
-    const uint64_t key = (i < n) ? __ldcg(buf + i) : 0ull;
-    const bool keep = (i < n) && ((key >> shift) >= prefix);
-    const uint32_t b = __ballot_sync(FULL_MASK, keep);
-    __syncwarp();
-    if (keep) {
-      __stcg(buf + base + __popc(b & lt_mask), key);
-      minkey = key < minkey ? key : minkey;
-    }
-    base += __popc(b);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const uint64_t t = __shfl_xor_sync(FULL_MASK, minkey, o);
-    minkey = t < minkey ? t : minkey;
-  }
-  __syncwarp();
-  return minkey;
+  prefix_out = prefix;
+  shift_out = shift;
 }
+
+__device__ __noinline__ bool row_excluded(const int32_t* rows, int n, uint32_t row) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((uint32_t)__ldg(rows + mid) < row)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo < n && (uint32_t)__ldg(rows + lo) == row;
+}
+
+// development counters (B200REC_TOPK_DEBUG=2): appends, requests, epilogue wait cycles, helper busy cycles, lock misses
+__device__ unsigned long long g_topk_stats[8];
+
+struct QMeta {        // one per query, global memory
+  uint32_t lock;      // 0 free, 1 held by a helper warp
+  uint32_t tcount;    // valid keys in the current T list
+  uint32_t tsel;      // which of the two T buffers is current
+  float tau;          // score of T's k-th key once T is full, else the initial threshold
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // top-K epilogue policy for stream_scores_kernel
+// scratch words: [0,1024) helper histograms | [1024,1536) tau_pub (u64: q<<32 | tau bits) | [1536,1792) req
+//                | [1792,2048) qidx | [2048] done | [2112, ...) helper staging (4 x TOPK_STG keys)
 // ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t REQ_VALID = 1u << 31, REQ_FINAL = 1u << 30, REQ_BUF = 1u << 29, REQ_CNT = (1u << 29) - 1u;
+constexpr int TOPK_STG = 704;  // keys a helper warp can stage in shared memory (5.5 KB)
+static_assert(2112 * 4 + 4 * TOPK_STG * 8 <= ST_SCRATCH_BYTES, "top-k scratch does not fit");
+constexpr uint32_t NO_QUERY = 0xFFFFFFFFu;
+
 struct TopkEpi {
   struct Args {
-    uint64_t* cand;                 // [grid][128*NQ][cap]
-    uint64_t* parts;                // [S][max_parts][128*NQ][k]
+    uint64_t* lists;                // [grid][128*NQ][2*cap]   private candidate lists A/B
+    uint64_t* tlists;               // [Q][2*k]                shared running top-k lists T0/T1
+    QMeta* meta;                    // [Q]
     const int64_t* excl_indptr;     // [Q+1] or null
     const int32_t* excl_rows;       // sorted per query
     int k;
     int cap;
+    int debug;  // development knob: 1 = reject everything (MMA + fast-path ceiling), 2 = count events
   };
   float tau[2];
   int cnt[2];
+  uint32_t active[2];
+  uint32_t qid[2];
   uint64_t* buf[2];
   const int32_t* ex_lo[2];
   int ex_n[2];
 
+  static __device__ __forceinline__ void init_scratch(uint32_t* scratch, int lane) {
+    for (int i = lane; i < 256; i += 32) {
+      reinterpret_cast<uint64_t*>(scratch + 1024)[i] = ~0ull;  // tag NO_QUERY
+      scratch[1536 + i] = 0u;
+      scratch[1792 + i] = NO_QUERY;
+    }
+    if (lane == 0) scratch[2048] = 0u;
+  }
+  static __device__ __forceinline__ void epilogue_exit(uint32_t* scratch, int lane) {
+    __syncwarp();
+    if (lane == 0) atomicAdd(&scratch[2048], 1u);
+  }
+  static __device__ __forceinline__ void wait_idle(volatile uint32_t* req) {
+    while (*req != 0u) __nanosleep(40);
+  }
+
   template <int NQ, int QPT>
-  __device__ __forceinline__ void begin_segment(const Args& ea, const StreamGeom& g, int s, const int (&qslot)[QPT],
-                                                int lane) {
+  __device__ __forceinline__ void begin_segment(const Args& ea, const StreamGeom& g, int s, int part,
+                                                const int (&qslot)[QPT], int lane, uint32_t* scratch) {
 #pragma unroll
     for (int a = 0; a < QPT; ++a) {
       const long long q = (long long)s * 128 * NQ + qslot[a];
-      tau[a] = (q < g.Q) ? -FLT_MAX : INFINITY;
+      const bool valid = (q < g.Q) && ea.debug != 1;
+      qid[a] = valid ? (uint32_t)q : NO_QUERY;
+      tau[a] = valid ? __ldcg(&ea.meta[q].tau) : INFINITY;
       cnt[a] = 0;
-      buf[a] = ea.cand + ((size_t)blockIdx.x * (128 * NQ) + qslot[a]) * ea.cap;
+      active[a] = 0;
+      buf[a] = ea.lists + ((size_t)blockIdx.x * (128 * NQ) + qslot[a]) * (2 * (size_t)ea.cap);
       ex_lo[a] = nullptr;
       ex_n[a] = 0;
-      if (ea.excl_indptr != nullptr && q < g.Q) {
+      if (ea.excl_indptr != nullptr && valid) {
         const int64_t lo = ea.excl_indptr[q], hi = ea.excl_indptr[q + 1];
         ex_lo[a] = ea.excl_rows + lo;
         ex_n[a] = (int)(hi - lo);
       }
+      // the previous segment's FINAL request of this slot was acknowledged in end_segment: the mailbox is ours
+      *reinterpret_cast<volatile uint32_t*>(scratch + 1792 + qslot[a]) = qid[a];
     }
   }
 
-  // make room for a worst-case tile (BN appends) in every owned buffer
+  // pick up thresholds raised by any feeder of this query; hand over a list that could overflow during the next tile
   template <int NQ, int BN, int QPT>
   __device__ __forceinline__ void pre_tile(const Args& ea, const StreamGeom& g, const int (&qslot)[QPT], int lane,
-                                           uint32_t* hist) {
+                                           uint32_t* scratch) {
 #pragma unroll
     for (int a = 0; a < QPT; ++a) {
-      uint32_t todo = __ballot_sync(FULL_MASK, cnt[a] + BN > ea.cap);
-      while (todo) {
-        const int owner = __ffs(todo) - 1;
-        todo &= todo - 1;
-        uint64_t* b = reinterpret_cast<uint64_t*>(
-            __shfl_sync(FULL_MASK, reinterpret_cast<unsigned long long>(buf[a]), owner));
-        const int n = __shfl_sync(FULL_MASK, cnt[a], owner);
-        __syncwarp();
-        const uint64_t minkey = warp_compact_topk(b, n, ea.k, hist, lane);
-        if (lane == owner) {
-          cnt[a] = ea.k;
-          tau[a] = ord_f32((uint32_t)(minkey >> 32));
+      const uint64_t pub = *reinterpret_cast<volatile uint64_t*>(scratch + 1024 + 2 * qslot[a]);
+      if ((uint32_t)(pub >> 32) == qid[a] && qid[a] != NO_QUERY) tau[a] = fmaxf(tau[a], __uint_as_float((uint32_t)pub));
+      if (cnt[a] + BN > ea.cap) {
+        volatile uint32_t* req = scratch + 1536 + qslot[a];
+        if (ea.debug == 2) {
+          const long long t0 = clock64();
+          wait_idle(req);
+          atomicAdd(&g_topk_stats[2], (unsigned long long)(clock64() - t0));
+          atomicAdd(&g_topk_stats[1], 1ull);
+        } else {
+          wait_idle(req);
         }
+        __threadfence_block();
+        *req = REQ_VALID | (active[a] ? REQ_BUF : 0u) | (uint32_t)cnt[a];
+        active[a] ^= 1u;
+        cnt[a] = 0;
       }
     }
   }
 
-  __device__ __forceinline__ bool excluded(int a, uint32_t row) const {
-    int lo = 0, hi = ex_n[a];
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      const int32_t v = __ldg(ex_lo[a] + mid);
-      if ((uint32_t)v < row)
-        lo = mid + 1;
-      else
-        hi = mid;
-    }
-    return lo < ex_n[a] && (uint32_t)__ldg(ex_lo[a] + lo) == row;
-  }
-
-  __device__ __forceinline__ void consider(int a, float x, unsigned long long row, const StreamGeom& g) {
-    if (x > tau[a] && row < (unsigned long long)g.N) {
-      if (ex_n[a] == 0 || !excluded(a, (uint32_t)row)) {
-        __stcg(buf[a] + cnt[a], make_key(x, (uint32_t)row));
+  // Candidate test + append for one score.  Kept tiny on purpose: the whole epilogue loop must stay inside the
+  // instruction cache (a fully unrolled 64-column scan with an inlined exclusion search was 70 KB of SASS and
+  // spent 80% of its issue slots waiting for instruction fetch).
+  __device__ __forceinline__ void consider(const Args& ea, int a, float x, uint32_t row, const StreamGeom& g) {
+    if (x >= tau[a] && row < (uint32_t)g.N) {
+      if (ex_n[a] == 0 || !row_excluded(ex_lo[a], ex_n[a], row)) {
+        __stcg(buf[a] + (active[a] ? ea.cap : 0) + cnt[a], make_key(x, row));
         ++cnt[a];
+        if (ea.debug == 2) atomicAdd(&g_topk_stats[0], 1ull);
       }
     }
   }
 
   template <int BN>
   __device__ __forceinline__ void tile(const Args& ea, const StreamGeom& g, int a, uint32_t taddr,
-                                       unsigned long long row0) {
+                                       unsigned long long row0_ll) {
+    const uint32_t row0 = (uint32_t)row0_ll;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 64) {
-      uint32_t v0[32], v1[32];
-      tmem_ld_32x32(taddr + c, v0);
-      tmem_ld_32x32(taddr + c + 32, v1);
-      tmem_ld_wait();
-      filter32(a, v0, row0 + c, g);
-      filter32(a, v1, row0 + c + 32, g);
-    }
-  }
-
-  __device__ __forceinline__ void filter32(int a, const uint32_t (&v)[32], unsigned long long row0,
-                                           const StreamGeom& g) {
-    float gm[4];
+      uint32_t gbits;
+      {
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(taddr + c, v0);
+        tmem_ld_32x32(taddr + c + 32, v1);
+        tmem_ld_wait();
+        gbits = group_bits(v0, tau[a]) | (group_bits(v1, tau[a]) << 4);
+      }
+      // rare path (warp-uniform loop because tcgen05.ld is warp-collective): re-read only the flagged 8-column groups
+      uint32_t pending = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float m0 = fmax3(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]), __uint_as_float(v[8 * j + 2]));
-      const float m1 = fmax3(__uint_as_float(v[8 * j + 3]), __uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-      gm[j] = fmax3(m0, m1, fmaxf(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-    }
-    const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-    if (m > tau[a]) {
+      for (int j = 0; j < 8; ++j) pending |= (__ballot_sync(FULL_MASK, (gbits >> j) & 1u) != 0u) ? (1u << j) : 0u;
+#pragma unroll 1
+      while (pending) {
+        const int j = __ffs(pending) - 1;
+        pending &= pending - 1;
+        uint32_t w[8];
+        tmem_ld_32x8(taddr + c + 8 * j, w);
+        tmem_ld_wait();
+        if ((gbits >> j) & 1u) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (gm[j] > tau[a]) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) consider(a, __uint_as_float(v[8 * j + i]), row0 + 8 * j + i, g);
+          for (int i = 0; i < 8; ++i) consider(ea, a, __uint_as_float(w[i]), row0 + c + 8 * j + i, g);
         }
       }
     }
   }
 
+  // bit j set when the maximum of columns [8j, 8j+8) reaches tau
+  static __device__ __forceinline__ uint32_t group_bits(const uint32_t (&v)[32], float t) {
+    uint32_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float m0 = fmax3(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]), __uint_as_float(v[8 * j + 2]));
+      const float m1 = fmax3(__uint_as_float(v[8 * j + 3]), __uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+      const float gm = fmax3(m0, m1, fmaxf(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+      bits |= (gm >= t) ? (1u << j) : 0u;
+    }
+    return bits;
+  }
+
   template <int NQ, int QPT>
   __device__ __forceinline__ void end_segment(const Args& ea, const StreamGeom& g, int s, int part,
-                                              const int (&qslot)[QPT], int lane, uint32_t* hist) {
+                                              const int (&qslot)[QPT], int lane, uint32_t* scratch) {
 #pragma unroll
     for (int a = 0; a < QPT; ++a) {
-      for (int owner = 0; owner < 32; ++owner) {
-        uint64_t* b = reinterpret_cast<uint64_t*>(
-            __shfl_sync(FULL_MASK, reinterpret_cast<unsigned long long>(buf[a]), owner));
-        int n = __shfl_sync(FULL_MASK, cnt[a], owner);
-        const int slot = __shfl_sync(FULL_MASK, qslot[a], owner);
-        const long long q = (long long)s * 128 * NQ + slot;
-        if (q >= g.Q) continue;  // warp-uniform
-        __syncwarp();
-        if (n > ea.k) {
-          warp_compact_topk(b, n, ea.k, hist, lane);
-          n = ea.k;
+      volatile uint32_t* req = scratch + 1536 + qslot[a];
+      wait_idle(req);
+      __threadfence_block();
+      *req = REQ_VALID | REQ_FINAL | (active[a] ? REQ_BUF : 0u) | (uint32_t)cnt[a];
+    }
+#pragma unroll
+    for (int a = 0; a < QPT; ++a) wait_idle(scratch + 1536 + qslot[a]);
+  }
+
+  // ------------------------------------------------------------------ helper warps: asynchronous merge into T
+  struct SmemLoader {
+    const uint64_t* keys;
+    __device__ __forceinline__ uint64_t operator()(int i) const { return keys[i]; }
+  };
+  struct UnionLoader {
+    const uint64_t* t;
+    const uint64_t* src;
+    int tc;
+    __device__ __forceinline__ uint64_t operator()(int i) const { return i < tc ? __ldcg(t + i) : __ldcg(src + (i - tc)); }
+  };
+
+  template <class Loader>
+  static __device__ __forceinline__ float merge_select(const Loader& ld, int total, int k, uint64_t* tnext,
+                                                       uint32_t* hist, int lane) {
+    uint64_t prefix;
+    int shift;
+    warp_select_threshold(ld, total, k, hist, lane, prefix, shift);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    int outp = 0;
+    uint64_t minkey = ~0ull;
+    for (int i0 = 0; i0 < total; i0 += 32) {
+      const int i = i0 + lane;
+      const uint64_t key = (i < total) ? ld(i) : 0ull;
+      const bool keep = (i < total) && ((key >> shift) >= prefix);
+      const uint32_t b = __ballot_sync(FULL_MASK, keep);
+      if (keep) {
+        const int pos = outp + __popc(b & lt_mask);
+        if (pos < k) __stcg(tnext + pos, key);
+        minkey = key < minkey ? key : minkey;
+      }
+      outp += __popc(b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint64_t t = __shfl_xor_sync(FULL_MASK, minkey, o);
+      minkey = t < minkey ? t : minkey;
+    }
+    return ord_f32((uint32_t)(minkey >> 32));
+  }
+
+  template <int NQ, int EPI_WARPS>
+  static __device__ void helper(const Args& ea, const StreamGeom& g, int hw, int lane, uint32_t* scratch) {
+    constexpr int QS = 128 * NQ;
+    constexpr int PER_LANE = NQ;  // QS / (4 warps * 32 lanes)
+    uint32_t* hist = scratch + hw * 256;
+    volatile uint64_t* tau_pub = reinterpret_cast<volatile uint64_t*>(scratch + 1024);
+    volatile uint32_t* reqs = scratch + 1536;
+    volatile uint32_t* qidx = scratch + 1792;
+    volatile uint32_t* done = scratch + 2048;
+    uint64_t* stage = reinterpret_cast<uint64_t*>(scratch + 2112) + hw * TOPK_STG;
+    const int k = ea.k;
+    for (;;) {
+      const bool finished = (*done == (uint32_t)EPI_WARPS);
+      bool any = false;
+#pragma unroll
+      for (int j = 0; j < PER_LANE; ++j) {
+        const int my_slot = hw * 32 * PER_LANE + j * 32 + lane;
+        const uint32_t r = reqs[my_slot];
+        const uint32_t myq = qidx[my_slot];
+        // refresh this slot's published threshold from the query's global tau (tagged with the query id, so a slot that
+        // has meanwhile moved on to another query ignores it)
+        if (myq != NO_QUERY) {
+          const float t = __ldcg(&ea.meta[myq].tau);
+          tau_pub[my_slot] = ((uint64_t)myq << 32) | (uint64_t)__float_as_uint(t);
         }
-        uint64_t* dst = ea.parts + (((size_t)s * g.max_parts + part) * (128 * NQ) + slot) * ea.k;
-        for (int i = lane; i < ea.k; i += 32) dst[i] = (i < n) ? __ldcg(b + i) : 0ull;
+        uint32_t todo = __ballot_sync(FULL_MASK, (r & REQ_VALID) != 0u);
+        while (todo) {
+          any = true;
+          const long long hb0 = clock64();
+          const int owner = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const uint32_t ro = __shfl_sync(FULL_MASK, r, owner);
+          const uint32_t q = __shfl_sync(FULL_MASK, myq, owner);
+          const int slot = hw * 32 * PER_LANE + j * 32 + owner;
+          const int n = (int)(ro & REQ_CNT);
+          if (q == NO_QUERY || n == 0) {  // nothing to merge: acknowledge
+            __syncwarp();
+            if (lane == 0) reqs[slot] = 0u;
+            continue;
+          }
+          QMeta* m = ea.meta + q;
+          uint32_t got = 0;
+          if (lane == 0) got = (atomicCAS(&m->lock, 0u, 1u) == 0u) ? 1u : 0u;
+          got = __shfl_sync(FULL_MASK, got, 0);
+          if (!got) {  // another CTA is merging into this query's T: retry on the next poll
+            if (ea.debug == 2 && lane == 0) atomicAdd(&g_topk_stats[4], 1ull);
+            continue;
+          }
+          __threadfence();
+          const uint64_t* src = ea.lists + ((size_t)blockIdx.x * QS + slot) * (2 * (size_t)ea.cap) + ((ro & REQ_BUF) ? ea.cap : 0);
+          int tc = (int)__ldcg(&m->tcount);
+          int ts = (int)__ldcg(&m->tsel);
+          uint64_t* tcur = ea.tlists + (size_t)q * 2 * k + (size_t)ts * k;
+          uint64_t* tnext = ea.tlists + (size_t)q * 2 * k + (size_t)(ts ^ 1) * k;
+          if (tc + n <= k) {
+            for (int i = lane; i < n; i += 32) __stcg(tcur + tc + i, __ldcg(src + i));
+            tc += n;
+            __threadfence();
+            if (lane == 0) m->tcount = (uint32_t)tc;
+          } else {
+            const int total = tc + n;
+            float newtau;
+            if (total <= TOPK_STG) {
+              for (int i = lane; i < total; i += 32) stage[i] = (i < tc) ? __ldcg(tcur + i) : __ldcg(src + (i - tc));
+              __syncwarp();
+              newtau = merge_select(SmemLoader{stage}, total, k, tnext, hist, lane);
+            } else {
+              newtau = merge_select(UnionLoader{tcur, src, tc}, total, k, tnext, hist, lane);
+            }
+            __threadfence();
+            if (lane == 0) {
+              m->tsel = (uint32_t)(ts ^ 1);
+              m->tcount = (uint32_t)k;
+              *reinterpret_cast<volatile float*>(&m->tau) = newtau;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) {
+            __threadfence();
+            atomicExch(&m->lock, 0u);
+            reqs[slot] = 0u;
+          }
+          __syncwarp();
+          if (ea.debug == 2 && lane == 0) atomicAdd(&g_topk_stats[3], (unsigned long long)(clock64() - hb0));
+        }
+      }
+      if (!any) {
+        if (finished) break;
+        __nanosleep(64);
       }
     }
   }
@@ -336,32 +517,44 @@ __device__ __forceinline__ void write_result(const uint64_t* skeys, int k_out, i
   }
 }
 
-struct PartsLoader {
-  const uint64_t* base;
-  size_t part_stride;
-  int k;
-  __device__ __forceinline__ uint64_t operator()(int i) const {
-    const int p = i / k, j = i - p * k;
-    return __ldcg(base + (size_t)p * part_stride + j);
-  }
-};
-
-template <int NQ>
+// sort one query's final T list (<= k keys) and emit (score, id)
 __global__ void __launch_bounds__(FIN_THREADS)
-topk_finalize_kernel(const StreamGeom g, const uint64_t* __restrict__ parts, int k, int P, int64_t row_offset,
-                     float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+topk_sort_kernel(const uint64_t* __restrict__ tlists, const QMeta* __restrict__ meta, int k, int P, int64_t row_offset,
+                 float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
   extern __shared__ uint64_t fin_smem[];
-  __shared__ uint32_t hist[256];
-  __shared__ int s_misc[8];
   const int q = blockIdx.x;
-  const int s = q / (128 * NQ), slot = q - s * 128 * NQ;
-  const int nparts = geom_last_cta(g, s) - geom_first_cta(g, s) + 1;
-  PartsLoader ld;
-  ld.part_stride = (size_t)(128 * NQ) * k;
-  ld.base = parts + ((size_t)s * g.max_parts * (128 * NQ) + slot) * k;
-  ld.k = k;
-  block_select_sort(ld, nparts * k, k, fin_smem, P, hist, s_misc);
+  const int tc = (int)meta[q].tcount;
+  const uint64_t* t = tlists + (size_t)q * 2 * k + (size_t)meta[q].tsel * k;
+  for (int i = threadIdx.x; i < P; i += FIN_THREADS) fin_smem[i] = (i < tc) ? __ldcg(t + i) : 0ull;
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < P / 2; i += FIN_THREADS) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const uint64_t x = fin_smem[lo], y = fin_smem[hi];
+        if ((x < y) == desc) {
+          fin_smem[lo] = y;
+          fin_smem[hi] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
   write_result(fin_smem, k, row_offset, out_scores + (size_t)q * k, out_ids + (size_t)q * k);
+}
+
+__global__ void topk_init_kernel(QMeta* meta, int Q, float tau0) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < Q) {
+    QMeta m;
+    m.lock = 0u;
+    m.tcount = 0u;
+    m.tsel = 0u;
+    m.tau = tau0;
+    meta[q] = m;
+  }
 }
 
 struct ListLoader {
@@ -393,6 +586,56 @@ topk_merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
   write_result(fin_smem, k_out, 0, out_scores + (size_t)q * k_out, out_ids + (size_t)q * k_out);
 }
 
+// Initial thresholds from a strided catalogue sample: tau0[q] = (a lower bound of) the k-th largest of the m sampled
+// scores S[q, :].  The sampled rows are scanned again by the main pass, so tau0 only has to be a valid lower bound
+// of the final k-th score: it removes the cold-start phase in which every score is a candidate.
+__global__ void __launch_bounds__(FIN_THREADS)
+sample_kth_kernel(const float* __restrict__ S, int m, int k, QMeta* __restrict__ meta) {
+  __shared__ uint32_t hist[256];
+  __shared__ int s_misc[4];
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* row = S + (size_t)q * m;
+  uint32_t prefix = 0;
+  int need = k, shift = 24;
+  for (int pass = 0; pass < 4; ++pass, shift -= 8) {
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < m; i += FIN_THREADS) {
+      const uint32_t key = f32_ord(__ldcg(row + i));
+      const bool match = (pass == 0) || ((key >> (shift + 8)) == prefix);
+      if (match) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int bucket, nd = need;
+      const int d = warp_pick_digit(hist, nd, bucket, lane);
+      if (lane == 0) {
+        s_misc[0] = d;
+        s_misc[1] = nd;
+        s_misc[2] = bucket;
+      }
+    }
+    __syncthreads();
+    prefix = (prefix << 8) | (uint32_t)s_misc[0];
+    need = s_misc[1];
+    const int bucket = s_misc[2];
+    __syncthreads();
+    if (bucket == need) break;
+  }
+  if (shift < 0) shift = 0;
+  if (tid == 0) {
+    uint32_t key = prefix << shift;         // smallest key carrying the selected prefix: <= the true k-th key
+    key = key > 64u ? key - 64u : 0u;        // 64 ulps of slack against accumulation-order differences
+    const float floor0 = nextafterf(-FLT_MAX, 0.f);
+    QMeta mm;
+    mm.lock = 0u;
+    mm.tcount = 0u;
+    mm.tsel = 0u;
+    mm.tau = fmaxf(ord_f32(key), floor0);
+    meta[q] = mm;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
@@ -406,10 +649,16 @@ struct TopkPlan {
   int nq, bn;
   StreamGeom g;
   int cap;
-  size_t cand_bytes, parts_bytes;
+  size_t lists_bytes, tlists_bytes, meta_bytes, sample_bytes;
+  int64_t sample_m, sample_stride;  // 0 = no sampling pass
+  size_t total() const { return lists_bytes + tlists_bytes + meta_bytes + sample_bytes; }
 };
 
-static int cap_for(int k, int bn) { return ((2 * k + bn + 31) / 32) * 32; }
+static int cap_for(int k, int bn) {
+  const char* e = getenv("B200REC_TOPK_CAPMULT");
+  const int mult = e ? atoi(e) : 2;
+  return ((mult * k + bn + 31) / 32) * 32;
+}
 
 static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k) {
   if (N <= 0 || Q <= 0) return fail("topk: empty catalogue or query set");
@@ -421,8 +670,12 @@ static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k) {
   const int sms = num_sms();
   const int q128 = (int)((Q + 127) / 128);
   bool ok = false;
-  if (q128 >= 3 && stream_geom<4, 64>(p.g, N, (int)Q, KB, sms) && p.g.stages >= 4) {
-    p.nq = 4, p.bn = 64, ok = true;
+  const char* force = getenv("B200REC_TOPK_NQ");
+  const int fnq = force ? atoi(force) : 0;
+  if (fnq == 2 && stream_geom<2, 128>(p.g, N, (int)Q, KB, sms)) {
+    p.nq = 2, p.bn = 128, ok = true;
+  } else if (fnq == 1 && stream_geom<1, 256>(p.g, N, (int)Q, KB, sms)) {
+    p.nq = 1, p.bn = 256, ok = true;
   } else if (q128 >= 2 && stream_geom<2, 128>(p.g, N, (int)Q, KB, sms) && p.g.stages >= 3) {
     p.nq = 2, p.bn = 128, ok = true;
   } else if (stream_geom<1, 256>(p.g, N, (int)Q, KB, sms) && p.g.stages >= 3) {
@@ -432,8 +685,22 @@ static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k) {
   }
   if (!ok) return fail("topk: dimension too large for the resident query tile (ld=%lld)", (long long)ld);
   p.cap = cap_for(k, p.bn);
-  p.cand_bytes = (size_t)p.g.grid * 128 * p.nq * p.cap * sizeof(uint64_t);
-  p.parts_bytes = (size_t)p.g.S * p.g.max_parts * 128 * p.nq * k * sizeof(uint64_t);
+  p.lists_bytes = (size_t)p.g.grid * 128 * p.nq * 2 * (size_t)p.cap * sizeof(uint64_t);
+  p.tlists_bytes = (size_t)Q * 2 * (size_t)k * sizeof(uint64_t);
+  p.meta_bytes = (((size_t)Q * sizeof(QMeta)) + 255) / 256 * 256;
+  // sampling pass: m strided rows, m*Q scores materialised once (<= 256 MB), only when it is a small fraction of N
+  int64_t m = (64ll << 20) / Q;
+  if (m > 65536) m = 65536;
+  m = m / 128 * 128;
+  const char* ns = getenv("B200REC_TOPK_NOSAMPLE");
+  if (m >= 4 * (int64_t)k && m >= 1024 && N >= 8 * m && !(ns && atoi(ns))) {
+    p.sample_m = m;
+    p.sample_stride = N / m;
+    p.sample_bytes = (size_t)Q * m * sizeof(float);
+  } else {
+    p.sample_m = p.sample_stride = 0;
+    p.sample_bytes = 0;
+  }
   return 0;
 }
 
@@ -445,33 +712,57 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
   if (make_tmap_bf16_2d(&tq, queries, (uint64_t)Q, (uint64_t)ld, (uint64_t)ld, 128)) return 1;
   if (make_tmap_bf16_2d(&tx, catalogue, (uint64_t)N, (uint64_t)ld, (uint64_t)ld, BN)) return 1;
   TopkEpi::Args ea;
-  ea.cand = reinterpret_cast<uint64_t*>(workspace);
-  ea.parts = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(workspace) + p.cand_bytes);
+  ea.lists = reinterpret_cast<uint64_t*>(workspace);
+  ea.tlists = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(workspace) + p.lists_bytes);
+  ea.meta = reinterpret_cast<QMeta*>(reinterpret_cast<uint8_t*>(workspace) + p.lists_bytes + p.tlists_bytes);
   ea.excl_indptr = excl_indptr;
   ea.excl_rows = excl_rows;
   ea.k = k;
   ea.cap = p.cap;
+  ea.debug = getenv("B200REC_TOPK_DEBUG") ? atoi(getenv("B200REC_TOPK_DEBUG")) : 0;
   auto kern = stream_scores_kernel<NQ, BN, TopkEpi>;
   static int smem_set = 0;
   if (smem_set < p.g.smem_bytes) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_LIMIT));
     smem_set = ST_SMEM_LIMIT;
   }
+  if (p.sample_m > 0 && excl_indptr == nullptr) {
+    float* S = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + p.lists_bytes + p.tlists_bytes + p.meta_bytes);
+    if (b200rec_gemm_bf16_tn(queries, ld, Q, catalogue, ld * p.sample_stride, p.sample_m, ld, S, p.sample_m, nullptr,
+                             1.0f, 1, st))
+      return 1;
+    sample_kth_kernel<<<(unsigned)Q, FIN_THREADS, 0, st>>>(S, (int)p.sample_m, k, ea.meta);
+    B200_LAUNCH_OK("sample_kth_kernel");
+  } else {
+    // every finite score must be able to enter: start just above -FLT_MAX (faiss' heap neutral, never returned)
+    topk_init_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(ea.meta, (int)Q, nextafterf(-FLT_MAX, 0.f));
+    B200_LAUNCH_OK("topk_init_kernel");
+  }
   kern<<<p.g.grid, ST_THREADS, p.g.smem_bytes, st>>>(tq, tx, p.g, ea);
   B200_LAUNCH_OK("stream_scores_kernel<topk>");
   const int P = next_pow2(k);
-  topk_finalize_kernel<NQ><<<(unsigned)Q, FIN_THREADS, P * sizeof(uint64_t), st>>>(p.g, ea.parts, k, P, row_offset,
-                                                                                  out_scores, out_ids);
-  B200_LAUNCH_OK("topk_finalize_kernel");
+  topk_sort_kernel<<<(unsigned)Q, FIN_THREADS, P * sizeof(uint64_t), st>>>(ea.tlists, ea.meta, k, P, row_offset,
+                                                                           out_scores, out_ids);
+  B200_LAUNCH_OK("topk_sort_kernel");
   return 0;
 }
 
 }  // namespace b200
 
+extern "C" int b200rec_debug_topk_stats(unsigned long long* out8_host, int reset) {
+  using namespace b200;
+  B200_CUDA_OK(cudaMemcpyFromSymbol(out8_host, g_topk_stats, sizeof(unsigned long long) * 8));
+  if (reset) {
+    unsigned long long z[8] = {0};
+    B200_CUDA_OK(cudaMemcpyToSymbol(g_topk_stats, z, sizeof(z)));
+  }
+  return 0;
+}
+
 extern "C" size_t b200rec_topk_workspace_bytes(int64_t N, int64_t ld, int64_t Q, int k) {
   b200::TopkPlan p;
   if (b200::plan_topk(p, N, ld, Q, k)) return 0;
-  return p.cand_bytes + p.parts_bytes;
+  return p.total();
 }
 
 extern "C" int b200rec_flat_ip_topk(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k,
@@ -482,11 +773,9 @@ extern "C" int b200rec_flat_ip_topk(const void* catalogue, int64_t N, int64_t ld
   if (!catalogue || !queries || !out_scores || !out_ids || !workspace) return fail("topk: null pointer");
   TopkPlan p;
   if (plan_topk(p, N, ld, Q, k)) return 1;
-  if (workspace_bytes < p.cand_bytes + p.parts_bytes)
-    return fail("topk: workspace too small (%zu < %zu)", workspace_bytes, p.cand_bytes + p.parts_bytes);
+  if (workspace_bytes < p.total()) return fail("topk: workspace too small (%zu < %zu)", workspace_bytes, p.total());
   if ((exclude_indptr == nullptr) != (exclude_rows == nullptr)) return fail("topk: exclusion CSR needs both arrays");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (p.nq == 4) return launch_topk<4, 64>(p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st);
   if (p.nq == 2) return launch_topk<2, 128>(p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st);
   if (p.bn == 256) return launch_topk<1, 256>(p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st);
   return launch_topk<1, 64>(p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st);
