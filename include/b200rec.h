@@ -1,13 +1,15 @@
 /*
- * b200rec — C-ABI of the B200-native two-tower hot path.
+ * b200rec — C-ABI of the B200-native two-tower hot path (libb200rec.so, sm_100a).
  *
- * The reference (yxyxcyx/Real-Time-Recommendation-System-with-Feature-Store) is pure Python and has no FFI;
- * each entry point below replaces the LIBRARY CALL the reference makes at the cited line.  Conventions:
+ * The reference (yxyxcyx/Real-Time-Recommendation-System-with-Feature-Store) is pure Python and has no FFI of its
+ * own; each entry point below replaces the LIBRARY CALL the reference makes at the cited file:line (paths relative
+ * to the reference root).  INTEGRATION.md shows the ctypes binding a maintainer would add on the reference side.
+ * Conventions:
  *   - every pointer is a DEVICE pointer unless its name ends in _host; sizes are element counts;
  *   - `stream` is a cudaStream_t passed as void*; every launch is asynchronous on it;
- *   - nothing is allocated or freed inside; workspaces are caller-owned (query *_workspace_bytes first);
+ *   - nothing is allocated or freed inside; workspaces / scratch buffers are caller-owned;
  *   - return 0 on success, non-zero on argument / CUDA error; b200rec_last_error() explains (thread-local);
- *   - bf16 operands are raw uint16 storage, row-major, leading dimension in ELEMENTS, a multiple of 64.
+ *   - bf16 operands are raw 16-bit storage, row-major, leading dimension in ELEMENTS.
  */
 #ifndef B200REC_H
 #define B200REC_H
@@ -23,121 +25,139 @@ int b200rec_version(void);
 /* number of kernels launched by this library since load (bench.py's `gpu_launches`) */
 int64_t b200rec_launch_count(void);
 
-/* ---------------------------------------------------------------- operand preparation
- * fp32 -> bf16 tensor-core operand.  terms==1: plain round-to-nearest bf16 (bf16 mode).
- * terms==3: split-bf16 "fp32 mode": x = hi + lo; side 0 (left operand) writes [hi|lo|hi], side 1 (right
- * operand) writes [hi|hi|lo], each block `kpad` wide, so that  left . right^T = hi*hi + lo*hi + hi*lo.
- * transpose!=0 reads src as [cols, rows] (writes the transposed operand).  dst is [rows, terms*kpad], zero padded.
- * Replaces nothing in the reference (ATen consumes fp32 directly: two_tower.py:129,276,470). */
-int b200rec_split_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_src, int transpose,
-                       void* dst, int64_t kpad, int terms, int side, void* stream);
+/* ---------------------------------------------------------------- operand preparation (csrc/prep.cu)
+ * fp32 -> bf16 tensor-core operand [rows, terms*kpad] (zero padded to kpad columns per block).
+ *   x = h + m + l exactly (h = bf16(x), m = bf16(x-h), l = bf16(x-h-m))
+ *   terms 1: [h] | [h]                  plain bf16 (2e-2 budget of the bf16 mode)
+ *   terms 3: [h m h] | [h h m]          (~2^-17 per product)
+ *   terms 6: [h h m h l m] | [h m h l h m]   fp32-grade products (drops only m*l, l*m, l*l)
+ * side 0 = left operand pattern, side 1 = right operand pattern.  transpose != 0 reads src as [cols, rows].
+ * Feeds the GEMM that replaces ATen addmm / matmul (src/models/two_tower.py:62,70,129,276,470). */
+int b200rec_split_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_src, int transpose, void* dst,
+                       int64_t kpad, int terms, int side, void* stream);
 
-/* faiss.normalize_L2 (retrieval.py:86,167,214) / F.normalize(p=2,eps=1e-12) (two_tower.py:132,279), fused with the
- * operand cast: dst_f32 (nullable) gets the normalised fp32 rows, dst_bf16 (nullable) the bf16 operand
- * [rows, terms*kpad] as b200rec_split_bf16.  normalize==0 only casts.  faiss_zero_rule!=0 leaves zero rows
- * untouched (faiss); otherwise divides by max(norm, eps) (torch).  norms_out (nullable) receives max(norm,eps). */
+/* faiss.normalize_L2 (src/serving/retrieval.py:86,167,214; faiss_zero_rule=1: zero rows untouched) and
+ * F.normalize(p=2, eps=1e-12) (src/models/two_tower.py:132,279; faiss_zero_rule=0), fused with the operand cast:
+ * dst_f32 (nullable) gets the normalised fp32 rows, dst_bf16 (nullable) the operand as b200rec_split_bf16,
+ * norms_out (nullable) the row norms (clamped to eps under the torch rule).  normalize == 0 only casts. */
 int b200rec_normalize_rows(const float* src, int64_t rows, int64_t cols, int64_t ld_src, int normalize,
                            int faiss_zero_rule, float* dst_f32, int64_t ld_dst, float* norms_out, void* dst_bf16,
                            int64_t kpad, int terms, int side, void* stream);
 
-/* ---------------------------------------------------------------- tensor-core GEMM (tcgen05 + TMA)
- * C[M,N] (+)= alpha * A[M,K] . B[N,K]^T + bias[N]   A,B bf16 K-major (lda/ldb elements, K multiple of 64),
- * C fp32 row-major.  k_splits>1 accumulates partial sums with fp32 atomics (C must be pre-zeroed by the caller).
- * Replaces ATen addmm/matmul: nn.Linear fwd/bwd two_tower.py:62,70,129,276 and matmul :470. */
+/* ---------------------------------------------------------------- tensor-core GEMM (csrc/gemm.cu; tcgen05 + TMA)
+ * C[M,N] (+)= alpha * A[M,K] . B[N,K]^T + bias[N];  A,B bf16 K-major (lda/ldb multiples of 8), C fp32 row-major.
+ * k_splits > 1 splits K over CTAs and ACCUMULATES into C with fp32 atomics (caller pre-zeroes or pre-loads C);
+ * k_splits < 0 means |k_splits| splits and accumulate even if only one split remains (C += ...).
+ * Replaces nn.Linear forward/backward (two_tower.py:62,70) and torch.matmul (:470). */
 int b200rec_gemm_bf16_tn(const void* A, int64_t lda, int64_t M, const void* B, int64_t ldb, int64_t N, int64_t K,
                          float* C, int64_t ldc, const float* bias, float alpha, int k_splits, void* stream);
 
-/* ---------------------------------------------------------------- exact inner-product top-K (K4)
- * Replaces faiss.IndexFlatIP.search(q, k) (retrieval.py:171) and np.dot+argsort (scripts/evaluate_model.py:217-232).
- * catalogue: bf16 [N, ld] (ld = padded dim, multiple of 64), queries: bf16 [Q, ld].  out_scores fp32 [Q,k]
- * descending, out_ids int64 [Q,k] = row + row_offset; unfilled slots: -FLT_MAX / -1.  Order: score desc, row asc.
- * exclude_* (nullable): CSR of per-query catalogue rows (LOCAL row numbers, sorted ascending per query) that must
- * never be returned — the eval twin's -inf masking of train items. */
+/* ---------------------------------------------------------------- exact inner-product top-K (csrc/topk.cu)
+ * Replaces faiss.IndexFlatIP.search(q, k) (src/serving/retrieval.py:171) and the np.dot + argsort twin
+ * (scripts/evaluate_model.py:217-232, src/evaluation/metrics.py:381-396).
+ * catalogue bf16 [N, ld], queries bf16 [Q, ld] (ld = padded dim, multiple of 64).  out_scores fp32 [Q,k] descending,
+ * out_ids int64 [Q,k] = row + row_offset; unfilled slots -FLT_MAX / -1.  Total order: score desc, row asc.
+ * exclude_* (nullable): CSR of per-query LOCAL rows (ascending) that must never be returned (the -inf mask of
+ * evaluate_model.py:225-228).  k <= 2048, N < 2^32 - 1 per shard. */
 size_t b200rec_topk_workspace_bytes(int64_t N, int64_t ld, int64_t Q, int k);
 int b200rec_flat_ip_topk(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k,
                          int64_t row_offset, const int64_t* exclude_indptr, const int32_t* exclude_rows,
                          float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream);
-/* k-way merge of `parts` sorted-or-not candidate lists laid out [parts][Q][k_in] (score fp32, id int64, id<0 = empty)
- * into the global top k_out under the same order.  The exchange step after the all-gather of per-GPU results. */
+/* k-way merge of `parts` candidate lists laid out [parts][Q][k_in] (id < 0 = empty, ids < 2^32) into the global top
+ * k_out under the same order: the exchange step after the all-gather of per-GPU results. */
 int b200rec_topk_merge(const float* scores, const int64_t* ids, int parts, int64_t Q, int k_in, int k_out,
                        float* out_scores, int64_t* out_ids, void* stream);
 
-/* ---------------------------------------------------------------- embedding bags (K1)
- * Fused multi-field gather: out[b, col_off[f] : col_off[f]+width[f]] = table_f[idx_f[b], :width[f]] for F fields,
- * plus the numerical block copied to out[b, 0:num_cols].  Replaces nn.Embedding fwd + 2x torch.cat
- * (two_tower.py:113-126, :254-273).  tables/indices are device arrays of F device pointers. */
-int b200rec_gather_concat(const float* numerical, int64_t num_cols, int64_t ld_num, const float* const* tables,
-                          const int64_t* const* indices, const int32_t* widths, const int32_t* table_ld,
-                          const int32_t* col_off, int F, int64_t B, float* out, int64_t ld_out, void* stream);
-/* Sparse row-gradient of one table: given idx[B] and dY (the field's column block of d(out), row stride ld_dy),
- * emits the coalesced (unique_rows[U] ascending, grad_rows[U,width]) with duplicates summed and the padding row
- * (idx 0) dropped — the non-zero rows of ATen embedding_dense_backward (nn.Embedding(padding_idx=0), two_tower.py:46-50).
- * n_unique_out is a device int32.  B <= 16384 per call in this version. */
+/* ---------------------------------------------------------------- embedding bags (csrc/embedding.cu)
+ * out[b, 0:num_cols] = numerical[b, :]; out[b, col_off[f] : +width[f]] = table_f[idx_f[b], :width[f]].
+ * Replaces nn.Embedding forward + 2x torch.cat (two_tower.py:113-126, :254-273).  The *_host arrays are HOST arrays
+ * of F entries (F <= 16).  err_flag (nullable device int) is set to 1+f when field f holds an out-of-range index. */
+int b200rec_gather_concat(const float* numerical, int64_t num_cols, int64_t ld_num, const float* const* tables_host,
+                          const int64_t* const* indices_host, const int64_t* table_rows_host,
+                          const int32_t* widths_host, const int32_t* table_ld_host, const int32_t* col_off_host, int F,
+                          int64_t B, float* out, int64_t ld_out, int32_t* err_flag, void* stream);
+/* Sparse row gradient of one table: coalesced (unique_rows[U] ascending, grad_rows[U,width]), duplicates summed, the
+ * padding row dropped — the non-zero rows of ATen embedding_dense_backward (nn.Embedding(padding_idx=0)).
+ * n_unique_out is a device int32.  table_rows (> 0) bounds the sort key width. */
 size_t b200rec_sparse_grad_workspace_bytes(int64_t B);
 int b200rec_embedding_sparse_grad(const int64_t* idx, int64_t B, const float* dY, int64_t ld_dy, int width,
-                                  int64_t* unique_rows, float* grad_rows, int32_t* n_unique_out, void* workspace,
-                                  size_t workspace_bytes, void* stream);
-/* Row-sparse Adam on the touched rows only (replaces dense torch.optim.Adam on the table, trainers/two_tower.py:60-64). */
-int b200rec_sparse_adam(float* table, float* exp_avg, float* exp_avg_sq, int64_t ld, int width,
-                        const int64_t* rows, const float* grad_rows, const int32_t* n_rows, int64_t max_rows,
-                        float lr, float beta1, float beta2, float eps, float bias_c1, float bias_c2,
-                        float grad_scale, void* stream);
+                                  int64_t padding_idx, int64_t table_rows, int64_t* unique_rows, float* grad_rows,
+                                  int32_t* n_unique_out, void* workspace, size_t workspace_bytes, void* stream);
+/* dense[rows[u], :width] (+)= grad_rows[u, :] for u < *n_rows (rows distinct) — materialises the dense gradient
+ * the reference's optimizer expects. */
+int b200rec_scatter_rows(const int64_t* rows, const float* grad_rows, const int32_t* n_rows, int64_t max_rows,
+                         int width, float* dense, int64_t ld, int accumulate, void* stream);
 
-/* ---------------------------------------------------------------- tower MLP pieces (K2)
+/* ---------------------------------------------------------------- tower MLP pieces (csrc/tower_ops.cu)
  * act: 0 relu, 1 gelu(erf), 2 leaky_relu(0.1), 3 tanh, 4 sigmoid, 5 identity  (two_tower.py:77-86).
- * Column statistics of a = act(z) over B rows: sums[0:H] = sum a, sums[H:2H] = sum a^2 (fp32, pre-zeroed). */
-int b200rec_bn_stats(const float* z, int64_t B, int64_t H, int64_t ld, int act, float* sums, void* stream);
-/* y = ((act(z) - mean) * invstd * gamma + beta) * dropout_mask/(1-p); writes y fp32 (nullable) and the next layer's
- * bf16 operand (nullable).  mean/invstd are [H].  Dropout mask = Philox(seed, element index) < keep. */
-int b200rec_bn_apply(const float* z, int64_t B, int64_t H, int64_t ld, int act, const float* mean,
-                     const float* invstd, const float* gamma, const float* beta, float drop_p, uint64_t seed,
-                     float* y, int64_t ld_y, void* y_bf16, int64_t kpad, int terms, int side, void* stream);
-/* BatchNorm backward, pass 1: sums[0:H] = sum dy' , sums[H:2H] = sum dy'*xhat  with dy' = dy*mask/(1-p). */
-int b200rec_bn_bwd_stats(const float* dy, int64_t ld_dy, const float* z, int64_t ld_z, int64_t B, int64_t H, int act,
-                         const float* mean, const float* invstd, float drop_p, uint64_t seed, float* sums,
-                         void* stream);
-/* pass 2: dz = act'(z) * invstd*gamma/n_total * (n_total*dy' - sum1 - xhat*sum2)  (training) or dy'*gamma*invstd (eval,
- * n_total==0).  Also dbias[h] += sum_b dz (fp32 atomics, pre-zeroed). */
-int b200rec_bn_bwd_apply(const float* dy, int64_t ld_dy, const float* z, int64_t ld_z, int64_t B, int64_t H, int act,
-                         const float* mean, const float* invstd, const float* gamma, const float* sums,
-                         float n_total, float drop_p, uint64_t seed, float* dz, int64_t ld_dz, float* dbias,
-                         void* stream);
+ * One hidden block after its Linear:  y = dropout(BatchNorm1d(act(z)))  (order of two_tower.py:56-72).
+ * training != 0: batch statistics (biased variance), running stats updated with `momentum` (unbiased variance),
+ * dropout mask = Philox(seed, element index).  training == 0: running statistics, no dropout.
+ * mean / invstd [H] are outputs kept for the backward.  scratch: >= 3*H doubles. */
+int b200rec_bn_forward(const float* z, int64_t B, int64_t H, int64_t ld, int act, int training, float eps,
+                       float momentum, const float* gamma, const float* beta, float* running_mean,
+                       float* running_var, float drop_p, uint64_t seed, float* mean, float* invstd, float* y,
+                       int64_t ld_y, double* scratch, void* stream);
+/* dz [B,H] from dy; dgamma, dbeta and (nullable) dbias = colsum(dz) are ACCUMULATED into their outputs. */
+int b200rec_bn_backward(const float* dy, int64_t ld_dy, const float* z, int64_t ld_z, int64_t B, int64_t H, int act,
+                        int training, const float* mean, const float* invstd, const float* gamma, float drop_p,
+                        uint64_t seed, float* dz, int64_t ld_dz, float* dgamma, float* dbeta, float* dbias,
+                        double* scratch, void* stream);
+/* y = dropout(act(z)) without BatchNorm (ItemTower.content_projection, two_tower.py:184-191) and its backward. */
+int b200rec_act_dropout(const float* z, int64_t B, int64_t H, int64_t ld, int act, float drop_p, uint64_t seed,
+                        float* y, int64_t ld_y, void* stream);
+int b200rec_act_dropout_bwd(const float* dy, int64_t ld_dy, const float* z, int64_t ld_z, int64_t B, int64_t H,
+                            int act, float drop_p, uint64_t seed, float* dz, int64_t ld_dz, void* stream);
+/* out[h] (+)= sum_b x[b,h]  — Linear bias gradients.  scratch: >= H doubles. */
+int b200rec_colsum(const float* x, int64_t B, int64_t H, int64_t ld, float* out, int accumulate, double* scratch,
+                   void* stream);
 /* F.normalize backward: dO = (dE - E * rowsum(E*dE)) / norm. */
 int b200rec_normalize_bwd(const float* dE, const float* E, const float* norms, int64_t B, int64_t D, float* dO,
                           void* stream);
-/* column sums: out[h] += sum_b x[b,h] (pre-zeroed) — Linear bias gradients. */
-int b200rec_colsum(const float* x, int64_t B, int64_t H, int64_t ld, float* out, void* stream);
 
-/* ---------------------------------------------------------------- losses (K3)
- * In-batch softmax cross-entropy, logits never materialised (two_tower.py:467-479):
- *   loss = mean_i( logsumexp_j(U_i.I_j / T) - U_i.I_i / T ).
- * U,I given as bf16 operands (terms*kpad wide: left side for U, right side for I).  lse_out [B] is kept for backward.
- * Under data parallelism I may hold more rows (NI >= B, all-gathered); `diag_offset` is this rank's first row in I. */
-size_t b200rec_inbatch_ce_workspace_bytes(int64_t B, int64_t NI);
-int b200rec_inbatch_ce_fwd(const void* U, const void* I, int64_t ld, int64_t B, int64_t NI, int64_t diag_offset,
-                           float inv_temperature, float* lse_out, float* loss_sum_out, void* workspace,
-                           size_t workspace_bytes, void* stream);
-/* Backward by tile-wise recomputation: dU[B,E] = g/(T*Btot) * (softmax(S) - onehot) . I ;
- * dI[NI,E] = g/(T*Btot) * (softmax(S) - onehot)^T . U.   I_t / U_t are the same matrices as MN-major-free transposed
- * bf16 operands ([E', NI] / [E', B]); see DESIGN.md. */
-int b200rec_inbatch_ce_bwd(const void* U, const void* I, int64_t ld, int64_t B, int64_t NI, int64_t diag_offset,
-                           float inv_temperature, const float* lse, float grad_scale, const float* U_f32,
-                           const float* I_f32, int64_t E, float* dU, float* dI, void* workspace,
-                           size_t workspace_bytes, void* stream);
-/* Explicit-negative CE (two_tower.py:422-451): logits[b] = [u.p/T + ub + ib, u.n_{b,0..R-1}/T]; label 0; sum over b of
- * the per-row loss is ADDED to loss_sum_out.  If dU != NULL also writes gradients scaled by grad_scale/B
- * (dU, dP [B,E], dN [B*R,E], dbias += sum_b dlogit0). */
+/* ---------------------------------------------------------------- losses (csrc/loss_ops.cu, csrc/inbatch_lse.cu)
+ * In-batch softmax cross-entropy (two_tower.py:467-479), forward fused with the logits GEMM: the B x NI logits live
+ * only in TMEM.  U_op [B, ld] / I_op [NI, ld] are split-bf16 operands (left / right patterns).  Output per row:
+ * lse[b] = logsumexp_j(inv_T * <u_b, i_j>).  Under data parallelism I may hold more rows than U (all-gathered). */
+size_t b200rec_inbatch_lse_workspace_bytes(int64_t B, int64_t NI, int64_t ld);
+int b200rec_inbatch_lse(const void* U_op, const void* I_op, int64_t ld, int64_t B, int64_t NI, float inv_temperature,
+                        float* lse_out, void* workspace, size_t workspace_bytes, void* stream);
+/* Row-wise pieces used by the chunked backward (and by the unfused forward):
+ * lse[r] = logsumexp_j(scale*S[r,j]); pos[r] (nullable) = scale*S[r, diag0 + r]. */
+int b200rec_lse_rows(const float* S, int64_t ld, int64_t rows, int64_t cols, float scale, int64_t diag0, float* lse,
+                     float* pos, void* stream);
+/* G[r,j] = coef * (*coef_dev) * (exp(scale*S[r,j] - lse[r]) - [j == diag0 + r])   (in place allowed; coef_dev nullable) */
+int b200rec_softmax_grad(const float* S, int64_t ld, int64_t rows, int64_t cols, float scale, const float* lse,
+                         int64_t diag0, float coef, const float* coef_dev, float* G, int64_t ldg, void* stream);
+/* *acc += sum_r (lse[r] - pos[r])   (pos nullable: plain sum) */
+int b200rec_ce_sum(const float* lse, const float* pos, int64_t n, float* acc, void* stream);
+/* Explicit-negative CE (two_tower.py:422-451): logits[b] = [<u,p>/T + ub + ib, <u,n_{b,0..R-1}>/T], label 0.
+ * row_loss[b] is written; when dU != NULL the gradients scaled by grad_scale are written too
+ * (dU, dP [B,E], dN [B*R,E], row_dbias[b] = grad_scale * dlogit_0). */
 int b200rec_explicit_ce(const float* U, const float* P, const float* Nn, int64_t B, int64_t R, int64_t E,
-                        float inv_temperature, float bias_sum, float* loss_sum_out, float grad_scale, float* dU,
-                        float* dP, float* dN, float* dbias, void* stream);
+                        float inv_temperature, const float* user_bias, const float* item_bias, float* row_loss,
+                        float grad_scale, const float* grad_scale_dev, float* dU, float* dP, float* dN,
+                        float* row_dbias, void* stream);
+/* compute_similarity (two_tower.py:380-404): out[b] = <u_b, i_b> * scale + ub + ib, and its backward. */
+int b200rec_rowdot(const float* U, const float* I, int64_t B, int64_t E, float scale, const float* user_bias,
+                   const float* item_bias, float* out, void* stream);
+int b200rec_rowdot_bwd(const float* g, const float* U, const float* I, int64_t B, int64_t E, float scale, float* dU,
+                       float* dI, void* stream);
 
-/* ---------------------------------------------------------------- optimiser helpers (K5)
- * sum of squares of n floats added to out (pre-zeroed) — the pieces of clip_grad_norm_. */
-int b200rec_sumsq(const float* x, int64_t n, float* out, void* stream);
-/* Dense Adam with L2-coupled weight decay on a flat fp32 buffer; `clip_coef_dev` (device float, nullable) scales g. */
+/* ---------------------------------------------------------------- optimiser (csrc/optim.cu)
+ * clip_grad_norm_ (src/training/trainers/two_tower.py:144): *out += sum x^2 (fp64); coef = min(1, max/(norm+1e-6)). */
+int b200rec_sumsq(const float* x, int64_t n, double* out, void* stream);
+int b200rec_clip_coef(const double* sumsq, float max_norm, float* coef, float* norm_out, void* stream);
+/* torch.optim.Adam with L2-coupled weight decay (trainers/two_tower.py:60-64,146) on a flat fp32 buffer;
+ * clip_coef_dev (device float, nullable) scales g first.  bias_c1 = 1-beta1^t, bias_c2_sqrt = sqrt(1-beta2^t). */
 int b200rec_adam_dense(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                       float eps, float weight_decay, float bias_c1, float bias_c2, const float* clip_coef_dev,
+                       float eps, float weight_decay, float bias_c1, float bias_c2_sqrt, const float* clip_coef_dev,
                        void* stream);
+/* Row-sparse Adam on the touched rows only (large embedding tables; no weight decay on untouched rows). */
+int b200rec_sparse_adam(float* table, float* exp_avg, float* exp_avg_sq, int64_t ld, int width, const int64_t* rows,
+                        const float* grad_rows, const int32_t* n_rows, int64_t max_rows, float lr, float beta1,
+                        float beta2, float eps, float bias_c1, float bias_c2_sqrt, const float* clip_coef_dev,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,7 @@ _SZ = C.c_size_t
 _U64 = C.c_uint64
 
 # name -> (restype, argtypes); one entry per symbol declared in include/b200rec.h
+_D = C.c_double
 SIGNATURES = {
     "b200rec_last_error": (C.c_char_p, []),
     "b200rec_version": (_I, []),
@@ -29,6 +30,30 @@ SIGNATURES = {
     "b200rec_topk_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I]),
     "b200rec_flat_ip_topk": (_I, [_P, _I64, _I64, _P, _I64, _I, _I64, _P, _P, _P, _P, _P, _SZ, _P]),
     "b200rec_topk_merge": (_I, [_P, _P, _I, _I64, _I, _I, _P, _P, _P]),
+    "b200rec_gather_concat": (_I, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P, _I, _I64, _P, _I64, _P, _P]),
+    "b200rec_sparse_grad_workspace_bytes": (_SZ, [_I64]),
+    "b200rec_embedding_sparse_grad": (_I, [_P, _I64, _P, _I64, _I, _I64, _I64, _P, _P, _P, _P, _SZ, _P]),
+    "b200rec_scatter_rows": (_I, [_P, _P, _P, _I64, _I, _P, _I64, _I, _P]),
+    "b200rec_bn_forward": (_I, [_P, _I64, _I64, _I64, _I, _I, _F, _F, _P, _P, _P, _P, _F, _U64, _P, _P, _P, _I64, _P,
+                                _P]),
+    "b200rec_bn_backward": (_I, [_P, _I64, _P, _I64, _I64, _I64, _I, _I, _P, _P, _P, _F, _U64, _P, _I64, _P, _P, _P,
+                                 _P, _P]),
+    "b200rec_act_dropout": (_I, [_P, _I64, _I64, _I64, _I, _F, _U64, _P, _I64, _P]),
+    "b200rec_act_dropout_bwd": (_I, [_P, _I64, _P, _I64, _I64, _I64, _I, _F, _U64, _P, _I64, _P]),
+    "b200rec_colsum": (_I, [_P, _I64, _I64, _I64, _P, _I, _P, _P]),
+    "b200rec_normalize_bwd": (_I, [_P, _P, _P, _I64, _I64, _P, _P]),
+    "b200rec_inbatch_lse_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
+    "b200rec_inbatch_lse": (_I, [_P, _P, _I64, _I64, _I64, _F, _P, _P, _SZ, _P]),
+    "b200rec_lse_rows": (_I, [_P, _I64, _I64, _I64, _F, _I64, _P, _P, _P]),
+    "b200rec_softmax_grad": (_I, [_P, _I64, _I64, _I64, _F, _P, _I64, _F, _P, _P, _I64, _P]),
+    "b200rec_ce_sum": (_I, [_P, _P, _I64, _P, _P]),
+    "b200rec_explicit_ce": (_I, [_P, _P, _P, _I64, _I64, _I64, _F, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
+    "b200rec_rowdot": (_I, [_P, _P, _I64, _I64, _F, _P, _P, _P, _P]),
+    "b200rec_rowdot_bwd": (_I, [_P, _P, _P, _I64, _I64, _F, _P, _P, _P]),
+    "b200rec_sumsq": (_I, [_P, _I64, _P, _P]),
+    "b200rec_clip_coef": (_I, [_P, _F, _P, _P, _P]),
+    "b200rec_adam_dense": (_I, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _F, _P, _P]),
+    "b200rec_sparse_adam": (_I, [_P, _P, _P, _I64, _I, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P, _P]),
 }
 
 

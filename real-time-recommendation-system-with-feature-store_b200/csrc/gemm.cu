@@ -20,6 +20,11 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN <= 64) ? 8 : 6;
+  // tcgen05 accumulates in fp32 with truncation, so the error of one accumulator chain grows linearly with the
+  // number of MMAs added into it.  K-blocks are dealt round-robin onto NACC TMEM accumulators that the epilogue sums
+  // with round-to-nearest adds: 4x shorter chains for the fp32-grade (split-bf16) products.
+  static constexpr int NACC = 4;
+  static constexpr int TMEM_COLS = NACC * BN;  // 512 or 256
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -57,7 +62,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     mbar_init(acc_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -89,8 +94,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
-            umma_bf16(tmem_base, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
-                      (i | k) != 0);
+            umma_bf16(tmem_base + (i % Cfg::NACC) * BN, umma_desc_k_sw128(a_addr + k * 32),
+                      umma_desc_k_sw128(b_addr + k * 32), idesc, (i >= Cfg::NACC) || (k != 0));
           }
           umma_commit(&empty_bar[s]);
         }
@@ -108,6 +113,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint32_t v[32];
         tmem_ld_32x32(taddr + c, v);
         tmem_ld_wait();
+        const int nacc = nkb < Cfg::NACC ? nkb : Cfg::NACC;
+        for (int a = 1; a < nacc; ++a) {
+          uint32_t w[32];
+          tmem_ld_32x32(taddr + a * BN + c, w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+        }
         if (row < M) {
           float* crow = C + static_cast<long long>(row) * ldc;
           const int col0 = n0 + c;
@@ -150,7 +163,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -162,6 +175,8 @@ static int launch_gemm(const void* A, int64_t lda, int64_t M, const void* B, int
   if (make_tmap_bf16_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM)) return 1;
   if (make_tmap_bf16_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN)) return 1;
   const int kb_total = (int)((K + GEMM_BK - 1) / GEMM_BK);
+  const bool force_atomic = k_splits < 0;  // negative: accumulate into C even when a single split remains
+  if (force_atomic) k_splits = -k_splits;
   if (k_splits < 1) k_splits = 1;
   if (k_splits > kb_total) k_splits = kb_total;
   const int kb_per_split = (kb_total + k_splits - 1) / k_splits;
@@ -175,7 +190,7 @@ static int launch_gemm(const void* A, int64_t lda, int64_t M, const void* B, int
   dim3 grid((unsigned)((M + GEMM_BM - 1) / GEMM_BM), (unsigned)((N + BN - 1) / BN), (unsigned)k_splits);
   gemm_bf16_tn_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, C, (long long)ldc, (int)M, (int)N,
                                                                        kb_total, kb_per_split, bias, alpha,
-                                                                       k_splits > 1 ? 1 : 0);
+                                                                       (k_splits > 1 || force_atomic) ? 1 : 0);
   B200_LAUNCH_OK("gemm_bf16_tn_kernel");
   return 0;
 }

@@ -1,0 +1,139 @@
+// Optimiser step pieces (K5): global gradient-norm clipping and Adam with L2-coupled weight decay on flat fp32 buffers
+// (reference src/training/trainers/two_tower.py:60-64 Adam(lr, weight_decay), :144 clip_grad_norm_(1.0), :146 step),
+// plus the row-sparse Adam used for large embedding tables.  Pure HBM-bound streaming kernels, 128-bit accesses.
+#include "host_util.h"
+#include "tc_common.cuh"
+#include "../../include/b200rec.h"
+
+namespace b200 {
+
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ x, int64_t n, double* __restrict__ out) {
+  __shared__ double red[8];
+  double s = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? n / 4 : 0;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(x4 + i);
+    s += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = __ldg(x + i);
+    s += (double)v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL_MASK, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(out, t);
+  }
+}
+
+// clip_grad_norm_: coef = min(1, max_norm / (total_norm + 1e-6)); also exports the norm
+__global__ void clip_coef_kernel(const double* __restrict__ sumsq, float max_norm, float* __restrict__ coef,
+                                 float* __restrict__ norm_out) {
+  const float nrm = (float)sqrt(*sumsq);
+  float c = max_norm / (nrm + 1e-6f);
+  *coef = c < 1.f ? c : 1.f;
+  if (norm_out) *norm_out = nrm;
+}
+
+__global__ void __launch_bounds__(256)
+adam_dense_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                  int64_t n, float lr, float beta1, float beta2, float eps, float wd, float bias_c1, float bias_c2_sqrt,
+                  const float* __restrict__ clip_coef) {
+  const float cc = clip_coef ? __ldg(clip_coef) : 1.f;
+  const float step_size = lr / bias_c1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float pi = p[i];
+    float gi = __ldg(g + i) * cc;
+    gi = fmaf(wd, pi, gi);
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bias_c2_sqrt + eps;
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+
+// one warp per touched row
+__global__ void __launch_bounds__(256)
+sparse_adam_kernel(float* __restrict__ table, float* __restrict__ m, float* __restrict__ v, int64_t ld, int width,
+                   const int64_t* __restrict__ rows, const float* __restrict__ grad_rows,
+                   const int32_t* __restrict__ n_rows, float lr, float beta1, float beta2, float eps, float bias_c1,
+                   float bias_c2_sqrt, const float* __restrict__ clip_coef) {
+  const int lane = threadIdx.x & 31;
+  const int n = __ldg(n_rows);
+  const float cc = clip_coef ? __ldg(clip_coef) : 1.f;
+  const float step_size = lr / bias_c1;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < n; u += warps) {
+    const int64_t r = __ldg(rows + u);
+    for (int c = lane; c < width; c += 32) {
+      const int64_t o = r * ld + c;
+      const float gi = __ldg(grad_rows + u * width + c) * cc;
+      const float mi = beta1 * m[o] + (1.f - beta1) * gi;
+      const float vi = beta2 * v[o] + (1.f - beta2) * gi * gi;
+      m[o] = mi;
+      v[o] = vi;
+      table[o] -= step_size * (mi / (sqrtf(vi) / bias_c2_sqrt + eps));
+    }
+  }
+}
+
+static int flat_grid(int64_t total) {
+  int64_t g = (total + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200rec_sumsq(const float* x, int64_t n, double* out, void* stream) {
+  if (!x || !out) return fail("sumsq: null pointer");
+  if (n <= 0) return fail("sumsq: empty input");
+  sumsq_kernel<<<flat_grid((n + 3) / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, n, out);
+  B200_LAUNCH_OK("sumsq_kernel");
+  return 0;
+}
+
+extern "C" int b200rec_clip_coef(const double* sumsq, float max_norm, float* coef, float* norm_out, void* stream) {
+  if (!sumsq || !coef) return fail("clip_coef: null pointer");
+  clip_coef_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sumsq, max_norm, coef, norm_out);
+  B200_LAUNCH_OK("clip_coef_kernel");
+  return 0;
+}
+
+extern "C" int b200rec_adam_dense(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                                  float beta2, float eps, float weight_decay, float bias_c1, float bias_c2_sqrt,
+                                  const float* clip_coef_dev, void* stream) {
+  if (!p || !g || !m || !v) return fail("adam_dense: null pointer");
+  if (n <= 0) return fail("adam_dense: empty input");
+  adam_dense_kernel<<<flat_grid(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2_sqrt, clip_coef_dev);
+  B200_LAUNCH_OK("adam_dense_kernel");
+  return 0;
+}
+
+extern "C" int b200rec_sparse_adam(float* table, float* exp_avg, float* exp_avg_sq, int64_t ld, int width,
+                                   const int64_t* rows, const float* grad_rows, const int32_t* n_rows, int64_t max_rows,
+                                   float lr, float beta1, float beta2, float eps, float bias_c1, float bias_c2_sqrt,
+                                   const float* clip_coef_dev, void* stream) {
+  if (!table || !exp_avg || !exp_avg_sq || !rows || !grad_rows || !n_rows) return fail("sparse_adam: null pointer");
+  if (max_rows <= 0 || width <= 0) return fail("sparse_adam: empty input");
+  const int64_t blocks = (max_rows + 7) / 8;
+  const int grid = (int)(blocks < (int64_t)num_sms() * 16 ? blocks : (int64_t)num_sms() * 16);
+  sparse_adam_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      table, exp_avg, exp_avg_sq, ld, width, rows, grad_rows, n_rows, lr, beta1, beta2, eps, bias_c1, bias_c2_sqrt,
+      clip_coef_dev);
+  B200_LAUNCH_OK("sparse_adam_kernel");
+  return 0;
+}

@@ -20,8 +20,7 @@ constexpr int ST_THREADS = 16 * 32;
 constexpr int ST_QTILE_BYTES = 128 * 64 * 2;  // one 128-row x 64-col bf16 SW128 block
 constexpr int ST_MAX_STAGES = 16;
 constexpr int ST_SMEM_LIMIT = 232448;  // 227 KB
-constexpr int ST_SCRATCH_BYTES = 2112 * 4 /*histograms + mailboxes*/ + 4 * 704 * 8 /*helper staging*/;
-constexpr int ST_TAIL_BYTES = 512 /*barriers + tmem slot*/ + ST_SCRATCH_BYTES;
+constexpr int ST_BAR_BYTES = 512;  // barriers + tmem slot; the policy-owned scratch (Epi::SCRATCH_BYTES) follows
 
 struct StreamGeom {
   long long N;      // streamed rows
@@ -38,7 +37,8 @@ struct StreamGeom {
 };
 
 template <int NQ, int BN>
-inline bool stream_geom(StreamGeom& g, long long N, int Q, int KB, int sms) {
+inline bool stream_geom(StreamGeom& g, long long N, int Q, int KB, int sms, int scratch_bytes) {
+  const int ST_TAIL_BYTES = ST_BAR_BYTES + scratch_bytes;
   g.N = N;
   g.Q = Q;
   g.KB = KB;
@@ -94,7 +94,7 @@ stream_scores_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint64_t* q_full = acc_empty + 2;
   uint64_t* q_empty = q_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 1);
-  uint32_t* scratch = reinterpret_cast<uint32_t*>(tail + 512);  // policy-owned shared scratch (ST_SCRATCH_BYTES)
+  uint32_t* scratch = reinterpret_cast<uint32_t*>(tail + ST_BAR_BYTES);  // policy-owned scratch (Epi::SCRATCH_BYTES)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;

@@ -127,10 +127,10 @@ struct QMeta {        // one per query, global memory
 // ---------------------------------------------------------------------------------------------------------------
 constexpr uint32_t REQ_VALID = 1u << 31, REQ_FINAL = 1u << 30, REQ_BUF = 1u << 29, REQ_CNT = (1u << 29) - 1u;
 constexpr int TOPK_STG = 704;  // keys a helper warp can stage in shared memory (5.5 KB)
-static_assert(2112 * 4 + 4 * TOPK_STG * 8 <= ST_SCRATCH_BYTES, "top-k scratch does not fit");
 constexpr uint32_t NO_QUERY = 0xFFFFFFFFu;
 
 struct TopkEpi {
+  static constexpr int SCRATCH_BYTES = 2112 * 4 + 4 * TOPK_STG * 8;
   struct Args {
     uint64_t* lists;                // [grid][128*NQ][2*cap]   private candidate lists A/B
     uint64_t* tlists;               // [Q][2*k]                shared running top-k lists T0/T1
@@ -672,15 +672,15 @@ static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k) {
   bool ok = false;
   const char* force = getenv("B200REC_TOPK_NQ");
   const int fnq = force ? atoi(force) : 0;
-  if (fnq == 2 && stream_geom<2, 128>(p.g, N, (int)Q, KB, sms)) {
+  if (fnq == 2 && stream_geom<2, 128>(p.g, N, (int)Q, KB, sms, TopkEpi::SCRATCH_BYTES)) {
     p.nq = 2, p.bn = 128, ok = true;
-  } else if (fnq == 1 && stream_geom<1, 256>(p.g, N, (int)Q, KB, sms)) {
+  } else if (fnq == 1 && stream_geom<1, 256>(p.g, N, (int)Q, KB, sms, TopkEpi::SCRATCH_BYTES)) {
     p.nq = 1, p.bn = 256, ok = true;
-  } else if (q128 >= 2 && stream_geom<2, 128>(p.g, N, (int)Q, KB, sms) && p.g.stages >= 3) {
+  } else if (q128 >= 2 && stream_geom<2, 128>(p.g, N, (int)Q, KB, sms, TopkEpi::SCRATCH_BYTES) && p.g.stages >= 3) {
     p.nq = 2, p.bn = 128, ok = true;
-  } else if (stream_geom<1, 256>(p.g, N, (int)Q, KB, sms) && p.g.stages >= 3) {
+  } else if (stream_geom<1, 256>(p.g, N, (int)Q, KB, sms, TopkEpi::SCRATCH_BYTES) && p.g.stages >= 3) {
     p.nq = 1, p.bn = 256, ok = true;
-  } else if (stream_geom<1, 64>(p.g, N, (int)Q, KB, sms)) {
+  } else if (stream_geom<1, 64>(p.g, N, (int)Q, KB, sms, TopkEpi::SCRATCH_BYTES)) {
     p.nq = 1, p.bn = 64, ok = true;
   }
   if (!ok) return fail("topk: dimension too large for the resident query tile (ld=%lld)", (long long)ld);

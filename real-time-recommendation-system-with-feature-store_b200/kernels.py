@@ -48,15 +48,20 @@ def normalize_rows(x: torch.Tensor, normalize: bool = True, faiss_rule: bool = F
 
 # ------------------------------------------------------------------------------------------------ GEMM
 def gemm_tn(a_op: torch.Tensor, b_op: torch.Tensor, M: int, Nn: int, K: int, bias: Optional[torch.Tensor] = None,
-            alpha: float = 1.0, k_splits: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """C[M,N] = alpha * A[M,K] . B[N,K]^T + bias, bf16 operands, fp32 result."""
+            alpha: float = 1.0, k_splits: int = 1, out: Optional[torch.Tensor] = None,
+            accumulate: bool = False) -> torch.Tensor:
+    """C[M,N] = alpha * A[M,K] . B[N,K]^T + bias, bf16 operands, fp32 result.  accumulate=True adds into `out`
+    (needs k_splits >= 2: the split-K path accumulates with fp32 atomics)."""
     assert a_op.dtype == BF16 and b_op.dtype == BF16
-    if out is None:
+    if accumulate:
+        assert out is not None and k_splits >= 2
+    elif out is None:
         out = (torch.zeros if k_splits > 1 else torch.empty)((M, Nn), dtype=torch.float32, device=a_op.device)
     elif k_splits > 1:
         out.zero_()
     N.check(N.lib().b200rec_gemm_bf16_tn(N.ptr(a_op), a_op.stride(0), M, N.ptr(b_op), b_op.stride(0), Nn, K,
-                                         N.ptr(out), out.stride(0), N.ptr(bias), float(alpha), k_splits, N.stream()),
+                                         N.ptr(out), out.stride(0), N.ptr(bias), float(alpha), -k_splits if accumulate else k_splits,
+                                         N.stream()),
             "gemm_bf16_tn")
     return out
 
@@ -104,3 +109,198 @@ def topk_merge(scores: torch.Tensor, ids: torch.Tensor, k_out: int) -> Tuple[tor
     N.check(N.lib().b200rec_topk_merge(N.ptr(scores), N.ptr(ids), parts, q, k_in, k_out, N.ptr(out_s), N.ptr(out_i),
                                        N.stream()), "topk_merge")
     return out_s, out_i
+
+
+# ------------------------------------------------------------------------------------------------ embedding bags
+import ctypes as _C  # noqa: E402
+
+
+def gather_concat(numerical: Optional[torch.Tensor], tables, indices, widths, col_offsets, out_cols: int,
+                  batch: int, device) -> torch.Tensor:
+    """Fused multi-field gather writing the MLP input [B, out_cols] (numerical block first)."""
+    F = len(tables)
+    out = torch.empty((batch, out_cols), dtype=torch.float32, device=device)
+    num_cols = 0 if numerical is None else numerical.shape[1]
+    tp = (_C.c_void_p * max(F, 1))(*[t.data_ptr() for t in tables])
+    ip = (_C.c_void_p * max(F, 1))(*[i.data_ptr() for i in indices])
+    rows = (_C.c_int64 * max(F, 1))(*[t.shape[0] for t in tables])
+    wd = (_C.c_int32 * max(F, 1))(*widths)
+    tld = (_C.c_int32 * max(F, 1))(*[t.stride(0) for t in tables])
+    co = (_C.c_int32 * max(F, 1))(*col_offsets)
+    err = torch.zeros((1,), dtype=torch.int32, device=device)
+    N.check(N.lib().b200rec_gather_concat(N.ptr(numerical), num_cols, numerical.stride(0) if numerical is not None else 0,
+                                          tp, ip, rows, wd, tld, co, F, batch, N.ptr(out), out.stride(0), N.ptr(err),
+                                          N.stream()), "gather_concat")
+    return out, err
+
+
+def embedding_sparse_grad(idx: torch.Tensor, dY: torch.Tensor, width: int, table_rows: int, padding_idx: int = 0):
+    """dY: [B, >=width] view (column block of the concat gradient).  Returns (rows int64 [B], grads [B,width], n int32[1]);
+    only the first n entries are valid."""
+    B = idx.shape[0]
+    rows = torch.empty((B,), dtype=torch.int64, device=idx.device)
+    grads = torch.empty((B, width), dtype=torch.float32, device=idx.device)
+    n = torch.zeros((1,), dtype=torch.int32, device=idx.device)
+    ws_bytes = int(N.lib().b200rec_sparse_grad_workspace_bytes(B))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=idx.device)
+    N.check(N.lib().b200rec_embedding_sparse_grad(N.ptr(idx), B, N.ptr(dY), dY.stride(0), width, padding_idx,
+                                                  table_rows, N.ptr(rows), N.ptr(grads), N.ptr(n), N.ptr(ws), ws_bytes,
+                                                  N.stream()), "embedding_sparse_grad")
+    return rows, grads, n
+
+
+def scatter_rows(rows, grads, n, dense: torch.Tensor, accumulate: bool = False) -> None:
+    N.check(N.lib().b200rec_scatter_rows(N.ptr(rows), N.ptr(grads), N.ptr(n), rows.shape[0], grads.shape[1],
+                                         N.ptr(dense), dense.stride(0), int(accumulate), N.stream()), "scatter_rows")
+
+
+# ------------------------------------------------------------------------------------------------ tower pieces
+ACT_IDS = {"relu": 0, "gelu": 1, "leaky_relu": 2, "tanh": 3, "sigmoid": 4, "identity": 5}
+
+
+def _scratch(n_doubles: int, device) -> torch.Tensor:
+    return torch.empty((n_doubles,), dtype=torch.float64, device=device)
+
+
+def bn_forward(z, act: int, training: bool, eps: float, momentum: float, gamma, beta, running_mean, running_var,
+               drop_p: float, seed: int):
+    B, H = z.shape
+    y = torch.empty_like(z)
+    mean = torch.empty((H,), dtype=torch.float32, device=z.device)
+    invstd = torch.empty((H,), dtype=torch.float32, device=z.device)
+    N.check(N.lib().b200rec_bn_forward(N.ptr(z), B, H, z.stride(0), act, int(training), eps, momentum, N.ptr(gamma),
+                                       N.ptr(beta), N.ptr(running_mean), N.ptr(running_var), drop_p, seed, N.ptr(mean),
+                                       N.ptr(invstd), N.ptr(y), y.stride(0), N.ptr(_scratch(3 * H, z.device)),
+                                       N.stream()), "bn_forward")
+    return y, mean, invstd
+
+
+def bn_backward(dy, z, act: int, training: bool, mean, invstd, gamma, drop_p: float, seed: int):
+    B, H = z.shape
+    dz = torch.empty_like(z)
+    dgamma = torch.zeros((H,), dtype=torch.float32, device=z.device)
+    dbeta = torch.zeros((H,), dtype=torch.float32, device=z.device)
+    N.check(N.lib().b200rec_bn_backward(N.ptr(dy), dy.stride(0), N.ptr(z), z.stride(0), B, H, act, int(training),
+                                        N.ptr(mean), N.ptr(invstd), N.ptr(gamma), drop_p, seed, N.ptr(dz), dz.stride(0),
+                                        N.ptr(dgamma), N.ptr(dbeta), None, N.ptr(_scratch(3 * H, z.device)),
+                                        N.stream()), "bn_backward")
+    return dz, dgamma, dbeta
+
+
+def act_dropout(z, act: int, drop_p: float, seed: int):
+    B, H = z.shape
+    y = torch.empty_like(z)
+    N.check(N.lib().b200rec_act_dropout(N.ptr(z), B, H, z.stride(0), act, drop_p, seed, N.ptr(y), y.stride(0),
+                                        N.stream()), "act_dropout")
+    return y
+
+
+def act_dropout_bwd(dy, z, act: int, drop_p: float, seed: int):
+    B, H = z.shape
+    dz = torch.empty_like(z)
+    N.check(N.lib().b200rec_act_dropout_bwd(N.ptr(dy), dy.stride(0), N.ptr(z), z.stride(0), B, H, act, drop_p, seed,
+                                            N.ptr(dz), dz.stride(0), N.stream()), "act_dropout_bwd")
+    return dz
+
+
+def colsum(x) -> torch.Tensor:
+    B, H = x.shape
+    out = torch.empty((H,), dtype=torch.float32, device=x.device)
+    N.check(N.lib().b200rec_colsum(N.ptr(x), B, H, x.stride(0), N.ptr(out), 0, N.ptr(_scratch(H, x.device)),
+                                   N.stream()), "colsum")
+    return out
+
+
+def normalize_bwd(dE, E, norms):
+    dE = _f32c(dE)
+    dO = torch.empty_like(E)
+    N.check(N.lib().b200rec_normalize_bwd(N.ptr(dE), N.ptr(E), N.ptr(norms), E.shape[0], E.shape[1], N.ptr(dO),
+                                          N.stream()), "normalize_bwd")
+    return dO
+
+
+# ------------------------------------------------------------------------------------------------ losses
+def inbatch_lse(u_op, i_op, B: int, NI: int, inv_t: float):
+    """Fused logits GEMM + online log-sum-exp; returns None when the operand is too wide for the resident tile."""
+    ld = u_op.stride(0)
+    need = int(N.lib().b200rec_inbatch_lse_workspace_bytes(B, NI, ld))
+    if need == 0:
+        return None
+    ws = torch.empty((need,), dtype=torch.uint8, device=u_op.device)
+    lse = torch.empty((B,), dtype=torch.float32, device=u_op.device)
+    N.check(N.lib().b200rec_inbatch_lse(N.ptr(u_op), N.ptr(i_op), ld, B, NI, inv_t, N.ptr(lse), N.ptr(ws), need,
+                                        N.stream()), "inbatch_lse")
+    return lse
+
+
+def lse_rows(S, scale: float, diag0: int, want_pos: bool):
+    rows, cols = S.shape
+    lse = torch.empty((rows,), dtype=torch.float32, device=S.device)
+    pos = torch.empty((rows,), dtype=torch.float32, device=S.device) if want_pos else None
+    N.check(N.lib().b200rec_lse_rows(N.ptr(S), S.stride(0), rows, cols, scale, diag0, N.ptr(lse), N.ptr(pos),
+                                     N.stream()), "lse_rows")
+    return lse, pos
+
+
+def softmax_grad_(S, scale: float, lse, diag0: int, coef: float, coef_dev=None):
+    rows, cols = S.shape
+    N.check(N.lib().b200rec_softmax_grad(N.ptr(S), S.stride(0), rows, cols, scale, N.ptr(lse), diag0, coef,
+                                         N.ptr(coef_dev), N.ptr(S), S.stride(0), N.stream()), "softmax_grad")
+    return S
+
+
+def ce_sum(lse, pos, acc) -> None:
+    N.check(N.lib().b200rec_ce_sum(N.ptr(lse), N.ptr(pos), lse.shape[0], N.ptr(acc), N.stream()), "ce_sum")
+
+
+def explicit_ce(U, P, Nn, R: int, inv_t: float, user_bias, item_bias, grad_scale: float = 0.0, grad_scale_dev=None,
+                want_grad: bool = False):
+    B, E = U.shape
+    row_loss = torch.empty((B,), dtype=torch.float32, device=U.device)
+    dU = dP = dN = dbias = None
+    if want_grad:
+        dU, dP, dN = torch.empty_like(U), torch.empty_like(P), torch.empty_like(Nn)
+        dbias = torch.empty((B,), dtype=torch.float32, device=U.device)
+    N.check(N.lib().b200rec_explicit_ce(N.ptr(U), N.ptr(P), N.ptr(Nn), B, R, E, inv_t, N.ptr(user_bias),
+                                        N.ptr(item_bias), N.ptr(row_loss), grad_scale, N.ptr(grad_scale_dev), N.ptr(dU),
+                                        N.ptr(dP), N.ptr(dN), N.ptr(dbias), N.stream()), "explicit_ce")
+    return row_loss, dU, dP, dN, dbias
+
+
+def rowdot(U, I, scale: float, user_bias, item_bias):
+    B, E = U.shape
+    out = torch.empty((B,), dtype=torch.float32, device=U.device)
+    N.check(N.lib().b200rec_rowdot(N.ptr(U), N.ptr(I), B, E, scale, N.ptr(user_bias), N.ptr(item_bias), N.ptr(out),
+                                   N.stream()), "rowdot")
+    return out
+
+
+def rowdot_bwd(g, U, I, scale: float):
+    dU, dI = torch.empty_like(U), torch.empty_like(I)
+    N.check(N.lib().b200rec_rowdot_bwd(N.ptr(g), N.ptr(U), N.ptr(I), U.shape[0], U.shape[1], scale, N.ptr(dU),
+                                       N.ptr(dI), N.stream()), "rowdot_bwd")
+    return dU, dI
+
+
+# ------------------------------------------------------------------------------------------------ optimiser
+def sumsq_(x_flat, acc64) -> None:
+    N.check(N.lib().b200rec_sumsq(N.ptr(x_flat), x_flat.numel(), N.ptr(acc64), N.stream()), "sumsq")
+
+
+def clip_coef(acc64, max_norm: float, coef, norm_out=None) -> None:
+    N.check(N.lib().b200rec_clip_coef(N.ptr(acc64), max_norm, N.ptr(coef), N.ptr(norm_out), N.stream()), "clip_coef")
+
+
+def adam_dense_(p, g, m, v, lr, beta1, beta2, eps, wd, step: int, clip=None) -> None:
+    bc1 = 1.0 - beta1 ** step
+    bc2s = (1.0 - beta2 ** step) ** 0.5
+    N.check(N.lib().b200rec_adam_dense(N.ptr(p), N.ptr(g), N.ptr(m), N.ptr(v), p.numel(), lr, beta1, beta2, eps, wd, bc1,
+                                       bc2s, N.ptr(clip), N.stream()), "adam_dense")
+
+
+def sparse_adam_(table, m, v, rows, grads, n, lr, beta1, beta2, eps, step: int, clip=None) -> None:
+    bc1 = 1.0 - beta1 ** step
+    bc2s = (1.0 - beta2 ** step) ** 0.5
+    N.check(N.lib().b200rec_sparse_adam(N.ptr(table), N.ptr(m), N.ptr(v), table.stride(0), grads.shape[1], N.ptr(rows),
+                                        N.ptr(grads), N.ptr(n), rows.shape[0], lr, beta1, beta2, eps, bc1, bc2s,
+                                        N.ptr(clip), N.stream()), "sparse_adam")

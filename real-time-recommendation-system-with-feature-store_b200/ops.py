@@ -1,0 +1,278 @@
+"""torch.autograd glue around the b200rec kernels: each Function's forward AND backward run hand-written sm_100a
+kernels through the C-ABI; torch only owns the tensors and the autograd graph.  Shapes follow the reference modules
+(src/models/two_tower.py)."""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+from torch.autograd import Function
+
+from . import kernels as K
+
+NUM_SMS = 148
+
+
+def _c32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("b200rec modules run on CUDA (sm_100a) tensors only; there is no CPU path — "
+                               "move the model and its inputs to a B200 device")
+
+
+class LinearFn(Function):
+    """z = x W^T + b on tcgen05 (nn.Linear, two_tower.py:62,70).  terms: 6 = fp32-grade split-bf16, 1 = bf16."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, terms: int):
+        require_cuda(x, w)
+        x, w = _c32(x), _c32(w)
+        xo = K.split_bf16(x, terms, 0)
+        wo = K.split_bf16(w, terms, 1)
+        z = K.gemm_tn(xo, wo, x.shape[0], w.shape[0], xo.shape[1], None if b is None else _c32(b))
+        ctx.save_for_backward(x, w)
+        ctx.terms = terms
+        ctx.has_bias = b is not None
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, w = ctx.saved_tensors
+        terms = ctx.terms
+        dz = _c32(dz)
+        B, out_f, in_f = x.shape[0], w.shape[0], w.shape[1]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dzo = K.split_bf16(dz, terms, 0)
+            wt = K.split_bf16(w, terms, 1, transpose=True)          # operand of W^T: [in, terms*kpad(out)]
+            dx = K.gemm_tn(dzo, wt, B, in_f, dzo.shape[1])
+        if ctx.needs_input_grad[1]:
+            dzt = K.split_bf16(dz, terms, 0, transpose=True)        # [out, terms*kpad(B)]
+            xt = K.split_bf16(x, terms, 1, transpose=True)          # [in,  terms*kpad(B)]
+            tiles = math.ceil(out_f / 128) * math.ceil(in_f / (64 if in_f <= 64 else 128))
+            ks = max(1, min(64, NUM_SMS // tiles, dzt.shape[1] // 64))
+            dw = K.gemm_tn(dzt, xt, out_f, in_f, dzt.shape[1], k_splits=ks)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = K.colsum(dz)
+        return dx, dw, db, None
+
+
+class ActBNDropFn(Function):
+    """y = Dropout(BatchNorm1d(act(z)))  — the hidden block after each Linear (two_tower.py:60-66)."""
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, running_mean, running_var, act: int, training: bool, eps: float, momentum: float,
+                drop_p: float, seed: int):
+        z = _c32(z)
+        y, mean, invstd = K.bn_forward(z, act, training, eps, momentum, gamma, beta, running_mean, running_var,
+                                       drop_p, seed)
+        ctx.save_for_backward(z, mean, invstd, gamma)
+        ctx.cfg = (act, training, drop_p, seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, mean, invstd, gamma = ctx.saved_tensors
+        act, training, drop_p, seed = ctx.cfg
+        dz, dgamma, dbeta = K.bn_backward(_c32(dy), z, act, training, mean, invstd, gamma, drop_p, seed)
+        return dz, dgamma, dbeta, None, None, None, None, None, None, None, None
+
+
+class ActDropFn(Function):
+    """y = Dropout(act(z)) (content_projection, two_tower.py:184-191)."""
+
+    @staticmethod
+    def forward(ctx, z, act: int, drop_p: float, seed: int):
+        z = _c32(z)
+        ctx.save_for_backward(z)
+        ctx.cfg = (act, drop_p, seed)
+        return K.act_dropout(z, act, drop_p, seed)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (z,) = ctx.saved_tensors
+        act, drop_p, seed = ctx.cfg
+        return K.act_dropout_bwd(_c32(dy), z, act, drop_p, seed), None, None, None
+
+
+class NormalizeFn(Function):
+    """F.normalize(p=2, dim=-1, eps=1e-12) (two_tower.py:132,279)."""
+
+    @staticmethod
+    def forward(ctx, o):
+        o = _c32(o)
+        e, norms, _ = K.normalize_rows(o, normalize=True, faiss_rule=False, want_f32=True, want_norms=True)
+        ctx.save_for_backward(e, norms)
+        return e
+
+    @staticmethod
+    def backward(ctx, de):
+        e, norms = ctx.saved_tensors
+        return K.normalize_bwd(de, e, norms)
+
+
+class GatherConcatFn(Function):
+    """cat([numerical, emb_f(idx_f) ...], -1) in one kernel (two_tower.py:113-126); backward = coalesced sparse row
+    gradients per table, delivered as the dense gradient nn.Embedding(sparse=False) produces (padding row 0 gets none),
+    or kept row-sparse on `weight._b200_sparse_grad` when the table opted in (large tables + sparse Adam)."""
+
+    @staticmethod
+    def forward(ctx, numerical, n_fields: int, *rest):
+        indices = list(rest[:n_fields])
+        tables = list(rest[n_fields:])
+        require_cuda(numerical, *tables)
+        numerical = _c32(numerical)
+        B = numerical.shape[0]
+        widths = [t.shape[1] for t in tables]
+        offs, c = [], numerical.shape[1]
+        for w in widths:
+            offs.append(c)
+            c += w
+        idx64 = [i.to(torch.int64).contiguous() for i in indices]
+        out, err = K.gather_concat(numerical if numerical.shape[1] > 0 else None, tables, idx64, widths, offs, c, B,
+                                   numerical.device)
+        ctx.save_for_backward(*idx64)
+        ctx.tables = tables
+        ctx.meta = (numerical.shape[1], widths, offs)
+        ctx.err = err
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        idx64 = ctx.saved_tensors
+        num_cols, widths, offs = ctx.meta
+        dout = _c32(dout)
+        dnum = dout[:, :num_cols] if ctx.needs_input_grad[0] else None
+        grads: List[Optional[torch.Tensor]] = []
+        for f, table in enumerate(ctx.tables):
+            if not ctx.needs_input_grad[2 + len(idx64) + f]:
+                grads.append(None)
+                continue
+            rows, vals, n = K.embedding_sparse_grad(idx64[f], dout[:, offs[f]:], widths[f], table.shape[0], 0)
+            if getattr(table, "_b200_sparse", False):
+                prev = getattr(table, "_b200_sparse_grad", None)
+                table._b200_sparse_grad = (prev or []) + [(rows, vals, n)]
+                grads.append(None)
+            else:
+                dense = torch.zeros_like(table)
+                K.scatter_rows(rows, vals, n, dense)
+                grads.append(dense)
+        return (dnum, None, *([None] * len(idx64)), *grads)
+
+
+class RowDotFn(Function):
+    """compute_similarity: sum(u*i, -1)/T + user_bias + item_bias (two_tower.py:395-402)."""
+
+    @staticmethod
+    def forward(ctx, u, i, user_bias, item_bias, inv_t: float):
+        require_cuda(u, i)
+        u, i = _c32(u), _c32(i)
+        ctx.save_for_backward(u, i)
+        ctx.inv_t = inv_t
+        ctx.has_bias = user_bias is not None
+        return K.rowdot(u, i, inv_t, user_bias, item_bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        u, i = ctx.saved_tensors
+        g = _c32(g)
+        du, di = K.rowdot_bwd(g, u, i, ctx.inv_t)
+        gb = None
+        if ctx.has_bias:
+            acc = torch.zeros((1,), dtype=torch.float32, device=g.device)
+            K.ce_sum(g, None, acc)
+            gb = acc
+        return du, di, gb, gb, None
+
+
+class ExplicitCEFn(Function):
+    """contrastive_loss with explicit negatives (two_tower.py:406-451): mean CE over [pos | R negatives], label 0."""
+
+    @staticmethod
+    def forward(ctx, u, p, n, user_bias, item_bias, inv_t: float):
+        require_cuda(u, p, n)
+        u, p, n = _c32(u), _c32(p), _c32(n)
+        B = u.shape[0]
+        R = n.shape[0] // B
+        row_loss, *_ = K.explicit_ce(u, p, n, R, inv_t, user_bias, item_bias)
+        acc = torch.zeros((1,), dtype=torch.float32, device=u.device)
+        K.ce_sum(row_loss, None, acc)
+        ctx.save_for_backward(u, p, n, user_bias, item_bias)
+        ctx.cfg = (R, inv_t)
+        return (acc / B).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        u, p, n, ub, ib = ctx.saved_tensors
+        R, inv_t = ctx.cfg
+        B = u.shape[0]
+        gdev = _c32(g).reshape(1)
+        _, du, dp, dn, dbias = K.explicit_ce(u, p, n, R, inv_t, ub, ib, grad_scale=1.0 / B, grad_scale_dev=gdev,
+                                             want_grad=True)
+        gb = None
+        if ub is not None:
+            gb = torch.zeros((1,), dtype=torch.float32, device=u.device)
+            K.ce_sum(dbias, None, gb)
+        return du, dp, dn, gb, gb, None
+
+
+class InBatchCEFn(Function):
+    """in_batch_negative_loss (two_tower.py:453-479): mean_b( logsumexp_j(<u_b,i_j>/T) - <u_b,i_b>/T ).
+
+    Forward: logits GEMM fused with the online log-sum-exp (never materialised); when the split operand is too wide
+    for the resident tile the row chunks go through the plain GEMM + row LSE.  Backward: recomputes logits chunk by
+    chunk (chunk x NI fp32, L2 sized), turns them into softmax - onehot in place and feeds two GEMMs.
+    `diag_offset`: first row of this rank's positives inside `i` (data parallel: i is the all-gathered item batch)."""
+
+    CHUNK = 2048
+
+    @staticmethod
+    def forward(ctx, u, i, inv_t: float, terms: int, diag_offset: int, total_rows: int):
+        require_cuda(u, i)
+        u, i = _c32(u), _c32(i)
+        B, NI = u.shape[0], i.shape[0]
+        uo = K.split_bf16(u, terms, 0)
+        io = K.split_bf16(i, terms, 1)
+        lse = K.inbatch_lse(uo, io, B, NI, inv_t)
+        if lse is None:
+            parts = []
+            for r0 in range(0, B, InBatchCEFn.CHUNK):
+                r1 = min(B, r0 + InBatchCEFn.CHUNK)
+                S = K.gemm_tn(uo[r0:r1], io, r1 - r0, NI, uo.shape[1])
+                parts.append(K.lse_rows(S, inv_t, 0, False)[0])
+            lse = parts[0] if len(parts) == 1 else torch.cat(parts)
+        ipos = i[diag_offset:diag_offset + B] if (diag_offset != 0 or NI != B) else i
+        pos = K.rowdot(u, _c32(ipos), inv_t, None, None)
+        acc = torch.zeros((1,), dtype=torch.float32, device=u.device)
+        K.ce_sum(lse, pos, acc)
+        ctx.save_for_backward(u, i, uo, io, lse)
+        ctx.cfg = (inv_t, terms, diag_offset, total_rows)
+        return (acc / total_rows).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        u, i, uo, io, lse = ctx.saved_tensors
+        inv_t, terms, diag_offset, total_rows = ctx.cfg
+        B, NI, E = u.shape[0], i.shape[0], u.shape[1]
+        gdev = _c32(g).reshape(1)
+        du = torch.empty_like(u)
+        di = torch.zeros_like(i)
+        it = K.split_bf16(i, terms, 1, transpose=True)               # operand of I^T: [E, terms*kpad(NI)]
+        for r0 in range(0, B, InBatchCEFn.CHUNK):
+            r1 = min(B, r0 + InBatchCEFn.CHUNK)
+            rows = r1 - r0
+            S = K.gemm_tn(uo[r0:r1], io, rows, NI, uo.shape[1])
+            K.softmax_grad_(S, inv_t, lse[r0:r1], diag_offset + r0, inv_t / total_rows, gdev)
+            go = K.split_bf16(S, terms, 0)                            # [rows, terms*kpad(NI)]
+            K.gemm_tn(go, it, rows, E, go.shape[1], out=du[r0:r1])
+            gt = K.split_bf16(S, terms, 0, transpose=True)            # [NI, terms*kpad(rows)]
+            ut = K.split_bf16(u[r0:r1], terms, 1, transpose=True)     # [E,  terms*kpad(rows)]
+            K.gemm_tn(gt, ut, NI, E, gt.shape[1], k_splits=2, out=di, accumulate=True)
+        return du, di, None, None, None, None

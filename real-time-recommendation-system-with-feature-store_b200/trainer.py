@@ -1,0 +1,211 @@
+"""Mirror of the reference's `src/training/trainers/two_tower.py` (TwoTowerTrainer :25-273) with the optimiser step on
+B200 kernels: one flat fp32 parameter / gradient buffer, one fused sum-of-squares + clip coefficient (clip_grad_norm_
+:144), one fused Adam with L2-coupled weight decay (:60-64,146); embedding tables that opted into row-sparse training
+get a row-sparse Adam on their touched rows.  `train_step` is the step body of `train_epoch` (:98-151) on tensors that
+are already on the device — what bench.py times."""
+from __future__ import annotations
+
+import logging
+import time
+from pathlib import Path
+from typing import Any, Dict, List, Optional
+
+import torch
+
+from . import kernels as K
+from .two_tower import TwoTowerModel
+
+logger = logging.getLogger("b200rec")
+
+
+class FlatAdam:
+    """torch.optim.Adam(lr, betas=(0.9,0.999), eps=1e-8, weight_decay) + clip_grad_norm_(max_norm) on flat buffers."""
+
+    def __init__(self, params, lr: float = 1e-3, weight_decay: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8,
+                 max_grad_norm: Optional[float] = 1.0):
+        params = [p for p in params if p.requires_grad]
+        self.dense = [p for p in params if not getattr(p, "_b200_sparse", False)]
+        self.sparse = [p for p in params if getattr(p, "_b200_sparse", False)]
+        if not self.dense:
+            raise ValueError("FlatAdam needs at least one dense parameter")
+        dev = self.dense[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FlatAdam runs on CUDA parameters only (no CPU path)")
+        n = sum(p.numel() for p in self.dense)
+        self.flat = torch.empty((n,), dtype=torch.float32, device=dev)
+        self.grad = torch.zeros((n,), dtype=torch.float32, device=dev)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        off = 0
+        for p in self.dense:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view(p.shape)
+            p.grad = self.grad[off:off + k].view(p.shape)
+            off += k
+        self.sparse_state = {id(p): (torch.zeros_like(p.data), torch.zeros_like(p.data)) for p in self.sparse}
+        self.lr, self.wd, self.betas, self.eps, self.max_grad_norm = lr, weight_decay, betas, eps, max_grad_norm
+        self.step_count = 0
+        self._acc = torch.zeros((1,), dtype=torch.float64, device=dev)
+        self._coef = torch.ones((1,), dtype=torch.float32, device=dev)
+        self.grad_norm = torch.zeros((1,), dtype=torch.float32, device=dev)
+        self.param_groups = [{"lr": lr}]
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        self.grad.zero_()
+        for p in self.sparse:
+            p._b200_sparse_grad = None
+
+    def _sparse_lists(self, p):
+        lists = getattr(p, "_b200_sparse_grad", None) or []
+        if len(lists) <= 1:
+            return lists
+        # several gathers hit the table this step: concatenate and coalesce again (invalid tail rows are 0 = padding)
+        rows = torch.cat([r for r, _, _ in lists])
+        vals = torch.cat([v for _, v, _ in lists])
+        return [K.embedding_sparse_grad(rows, vals, vals.shape[1], p.shape[0], 0)]
+
+    def step(self) -> None:
+        self.step_count += 1
+        lr = self.param_groups[0]["lr"]
+        clip = None
+        sparse = [(p, self._sparse_lists(p)) for p in self.sparse]
+        if self.max_grad_norm is not None:
+            self._acc.zero_()
+            K.sumsq_(self.grad, self._acc)
+            for _, lists in sparse:
+                for _, vals, _ in lists:
+                    K.sumsq_(vals.reshape(-1), self._acc)   # rows beyond n are zero-filled by the coalescing kernel
+            K.clip_coef(self._acc, float(self.max_grad_norm), self._coef, self.grad_norm)
+            clip = self._coef
+        K.adam_dense_(self.flat, self.grad, self.m, self.v, lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                      self.step_count, clip)
+        for p, lists in sparse:
+            m, v = self.sparse_state[id(p)]
+            for rows, vals, n in lists:
+                K.sparse_adam_(p.data, m, v, rows, vals, n, lr, self.betas[0], self.betas[1], self.eps,
+                               self.step_count, clip)
+
+    def state_dict(self) -> Dict[str, Any]:
+        return {"step": self.step_count, "exp_avg": self.m, "exp_avg_sq": self.v, "lr": self.param_groups[0]["lr"]}
+
+
+class TwoTowerTrainer:
+    """Trainer for the Two-Tower model (reference trainers/two_tower.py:25-273): same constructor, same methods, same
+    checkpoint keys; the step runs entirely in b200rec kernels."""
+
+    def __init__(self, model: TwoTowerModel, train_loader, val_loader, config: Dict[str, Any], device: str = "cuda"):
+        if not str(device).startswith("cuda"):
+            raise RuntimeError("b200rec TwoTowerTrainer needs device='cuda' (no CPU path)")
+        self.model = model.to(device)
+        self.train_loader = train_loader
+        self.val_loader = val_loader
+        self.config = config
+        self.device = device
+        self.optimizer = FlatAdam(self.model.parameters(), lr=config.get("learning_rate", 0.001),
+                                  weight_decay=config.get("weight_decay", 1e-5),
+                                  max_grad_norm=config.get("max_grad_norm", 1.0))
+        self.scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(_LRShim(self.optimizer), mode="min", factor=0.5,
+                                                                    patience=2)
+        self.early_stopping_patience = config.get("early_stopping_patience", 5)
+        self.best_val_loss = float("inf")
+        self.patience_counter = 0
+        self.checkpoint_dir = Path(config.get("checkpoint_dir", "models/checkpoints"))
+        self.checkpoint_dir.mkdir(parents=True, exist_ok=True)
+        self.train_losses: List[float] = []
+        self.val_losses: List[float] = []
+
+    # ------------------------------------------------------------------ the hot step (trainers/two_tower.py:98-146)
+    def train_step(self, user_features: torch.Tensor, pos_item_features: torch.Tensor,
+                   neg_item_features: Optional[torch.Tensor] = None,
+                   user_categorical: Optional[Dict[str, torch.Tensor]] = None,
+                   item_categorical: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+        model = self.model
+        self.optimizer.zero_grad()
+        u = model.get_user_embeddings({"numerical": user_features, "categorical": user_categorical or {}})
+        p = model.get_item_embeddings({"numerical": pos_item_features, "categorical": item_categorical or {}})
+        if neg_item_features is not None:
+            batch_size, num_neg, feat_dim = neg_item_features.shape
+            n = model.get_item_embeddings({"numerical": neg_item_features.view(-1, feat_dim), "categorical": {}})
+            explicit_loss = model.contrastive_loss(u, p, n)
+            in_batch_loss = model.in_batch_negative_loss(u, p)
+            loss = 0.7 * explicit_loss + 0.3 * in_batch_loss
+        else:
+            loss = model.in_batch_negative_loss(u, p)
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
+    def train_epoch(self, epoch: int) -> float:
+        self.model.train()
+        total = torch.zeros((), dtype=torch.float32, device=self.device)
+        num_batches = 0
+        for batch in self.train_loader:
+            uf = batch["user_features"].to(self.device, non_blocking=True)
+            pf = batch["pos_item_features"].to(self.device, non_blocking=True)
+            nf = batch["neg_item_features"].to(self.device, non_blocking=True) if "neg_item_features" in batch else None
+            total += self.train_step(uf, pf, nf)   # no per-step host sync; one .item() per epoch
+            num_batches += 1
+        avg_loss = float(total.item()) / num_batches if num_batches > 0 else 0.0
+        self.train_losses.append(avg_loss)
+        return avg_loss
+
+    @torch.no_grad()
+    def validate(self) -> float:
+        self.model.eval()
+        total = torch.zeros((), dtype=torch.float32, device=self.device)
+        num_batches = 0
+        for batch in self.val_loader:
+            uf = batch["user_features"].to(self.device, non_blocking=True)
+            pf = batch["pos_item_features"].to(self.device, non_blocking=True)
+            u = self.model.get_user_embeddings({"numerical": uf, "categorical": {}})
+            p = self.model.get_item_embeddings({"numerical": pf, "categorical": {}})
+            total += self.model.in_batch_negative_loss(u, p)
+            num_batches += 1
+        avg_loss = float(total.item()) / num_batches if num_batches > 0 else 0.0
+        self.val_losses.append(avg_loss)
+        return avg_loss
+
+    def save_checkpoint(self, epoch: int, is_best: bool = False) -> None:
+        checkpoint = {"epoch": epoch, "user_tower_state": self.model.user_tower.state_dict(),
+                      "item_tower_state": self.model.item_tower.state_dict(),
+                      "temperature": self.model.temperature, "user_bias": self.model.user_bias,
+                      "item_bias": self.model.item_bias, "optimizer_state": self.optimizer.state_dict(),
+                      "train_losses": self.train_losses, "val_losses": self.val_losses}
+        torch.save(checkpoint, self.checkpoint_dir / "two_tower_latest.pth")
+        if is_best:
+            torch.save(checkpoint, self.checkpoint_dir / "two_tower_best.pth")
+
+    def train(self, num_epochs: int) -> Dict[str, List[float]]:
+        for epoch in range(1, num_epochs + 1):
+            start = time.time()
+            train_loss = self.train_epoch(epoch)
+            val_loss = self.validate()
+            self.scheduler.step(val_loss)
+            logger.info("Epoch %d/%d - train %.4f val %.4f (%.1fs)", epoch, num_epochs, train_loss, val_loss,
+                        time.time() - start)
+            is_best = val_loss < self.best_val_loss
+            if is_best:
+                self.best_val_loss = val_loss
+                self.patience_counter = 0
+            else:
+                self.patience_counter += 1
+            self.save_checkpoint(epoch, is_best)
+            if self.patience_counter >= self.early_stopping_patience:
+                logger.info("Early stopping triggered after %d epochs", epoch)
+                break
+        return {"train_losses": self.train_losses, "val_losses": self.val_losses}
+
+
+class _LRShim(torch.optim.Optimizer):
+    """Lets torch's ReduceLROnPlateau drive FlatAdam's learning rate (it only touches param_groups[*]['lr'])."""
+
+    def __init__(self, flat: FlatAdam):
+        self._flat = flat
+        super().__init__([torch.nn.Parameter(torch.zeros(1))], {"lr": flat.param_groups[0]["lr"]})
+        self.param_groups = flat.param_groups
+        for g in self.param_groups:
+            g.setdefault("params", [])
+
+    def step(self, closure=None):  # pragma: no cover - never called
+        return None

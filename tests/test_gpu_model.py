@@ -1,0 +1,231 @@
+"""GPU parity of the drop-in towers / losses / trainer step against golden vectors generated from the imported
+reference (tests/golden/make_golden.py), plus the reference's own property tests re-stated for CUDA tensors.
+Tolerances: fp32 mode 1e-5 relative on losses and embeddings (north_star); gradients 1e-4 of the tensor's max."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _load_tower(tower, g, prefix):
+    sd = {k[len(prefix) + 1:]: torch.from_numpy(np.asarray(g[k])) for k in g.files
+          if k.startswith(prefix + ".") and not k.startswith("grad.") and not k.startswith("after.")}
+    tower.load_state_dict(sd)
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def _build_step_model(g, user_dim, item_dim, cfg):
+    from b200rec.training_utils import create_two_tower_model_for_training
+    model = create_two_tower_model_for_training(user_dim, item_dim, cfg)
+    _load_tower(model.user_tower, g, "user")
+    _load_tower(model.item_tower, g, "item")
+    with torch.no_grad():
+        model.user_bias.copy_(torch.from_numpy(g["user_bias"]))
+        model.item_bias.copy_(torch.from_numpy(g["item_bias"]))
+    return model.to(DEV)
+
+
+STEP_CASES = {
+    "step_ml1m": (3, 20, {"embedding_dim": 128, "hidden_layers": [256, 128], "dropout_rate": 0.0, "temperature": 0.05}),
+    "step_small": (6, 9, {"embedding_dim": 64, "hidden_layers": [128, 64], "dropout_rate": 0.0, "temperature": 0.1}),
+}
+
+
+@pytest.mark.parametrize("name", list(STEP_CASES))
+def test_trainer_step_matches_reference(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    user_dim, item_dim, cfg = STEP_CASES[name]
+    model = _build_step_model(g, user_dim, item_dim, cfg)
+    model.train()
+    uf = torch.from_numpy(g["user_features"]).to(DEV)
+    pf = torch.from_numpy(g["pos_item_features"]).to(DEV)
+    nf = torch.from_numpy(g["neg_item_features"]).to(DEV)
+    u = model.get_user_embeddings({"numerical": uf, "categorical": {}})
+    p = model.get_item_embeddings({"numerical": pf, "categorical": {}})
+    n = model.get_item_embeddings({"numerical": nf.view(-1, item_dim), "categorical": {}})
+    for t in (u, p, n):
+        t.retain_grad()
+    explicit = model.contrastive_loss(u, p, n)
+    inbatch = model.in_batch_negative_loss(u, p)
+    loss = 0.7 * explicit + 0.3 * inbatch
+    loss.backward()
+    torch.cuda.synchronize()
+    # embeddings and losses: 1e-5 relative
+    assert _rel(u.detach().cpu(), g["user_emb"]) <= 1e-5
+    assert _rel(p.detach().cpu(), g["pos_emb"]) <= 1e-5
+    assert _rel(n.detach().cpu(), g["neg_emb"]) <= 1e-5
+    assert abs(explicit.item() - float(g["explicit_loss"])) <= 1e-5 * abs(float(g["explicit_loss"]))
+    assert abs(inbatch.item() - float(g["inbatch_loss"])) <= 1e-5 * abs(float(g["inbatch_loss"]))
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    # gradients of the embeddings and of every parameter
+    assert _rel(u.grad.cpu(), g["grad.user_emb"]) <= 1e-4
+    assert _rel(p.grad.cpu(), g["grad.pos_emb"]) <= 1e-4
+    assert _rel(n.grad.cpu(), g["grad.neg_emb"]) <= 1e-4
+    assert _rel(model.user_bias.grad.cpu(), g["grad.user_bias"]) <= 1e-4
+    assert _rel(model.item_bias.grad.cpu(), g["grad.item_bias"]) <= 1e-4
+    for prefix, tower in (("user", model.user_tower), ("item", model.item_tower)):
+        for k, prm in tower.named_parameters():
+            ref = g[f"grad.{prefix}.{k}"]
+            assert _rel(prm.grad.cpu(), ref) <= 2e-4, f"grad {prefix}.{k}: {_rel(prm.grad.cpu(), ref):.3e}"
+    # running statistics after the step (item tower saw two batches) and the eval-mode forward
+    for prefix, tower in (("user", model.user_tower), ("item", model.item_tower)):
+        for k, v in tower.state_dict().items():
+            if "running" in k:
+                assert _rel(v.cpu(), g[f"after.{prefix}.{k}"]) <= 1e-5, k
+            if "num_batches" in k:
+                assert int(v.item()) == int(g[f"after.{prefix}.{k}"]), k
+    model.eval()
+    with torch.no_grad():
+        ue = model.get_user_embeddings({"numerical": uf, "categorical": {}})
+        pe = model.get_item_embeddings({"numerical": pf, "categorical": {}})
+        le = model.in_batch_negative_loss(ue, pe)
+    assert _rel(ue.cpu(), g["user_emb_eval"]) <= 1e-5
+    assert _rel(pe.cpu(), g["pos_emb_eval"]) <= 1e-5
+    assert abs(le.item() - float(g["inbatch_loss_eval"])) <= 1e-5 * abs(float(g["inbatch_loss_eval"]))
+
+
+@pytest.mark.parametrize("act", ["relu", "gelu", "leaky_relu", "tanh", "sigmoid"])
+def test_categorical_towers_match_reference(golden_dir, act):
+    from b200rec.two_tower import ItemTower, TwoTowerModel, UserTower
+    g = np.load(os.path.join(golden_dir, f"cat_{act}.npz"))
+    ut = UserTower(input_dim=10, embedding_dim=32, hidden_layers=[64, 32], dropout_rate=0.0, activation=act,
+                   categorical_features={"category": 10, "subcategory": 5})
+    it = ItemTower(input_dim=15, embedding_dim=32, hidden_layers=[64, 32], dropout_rate=0.0, activation=act,
+                   categorical_features={"genre": 30, "studio": 200}, use_content_embedding=False)
+    _load_tower(ut, g, "user")
+    _load_tower(it, g, "item")
+    model = TwoTowerModel(ut, it, temperature=0.1).to(DEV)
+    model.train()
+    uc = {k: torch.from_numpy(g[f"user_cat.{k}"]).to(DEV) for k in ("category", "subcategory")}
+    ic = {k: torch.from_numpy(g[f"item_cat.{k}"]).to(DEV) for k in ("genre", "studio")}
+    res = model({"numerical": torch.from_numpy(g["user_num"]).to(DEV), "categorical": uc},
+                {"numerical": torch.from_numpy(g["item_num"]).to(DEV), "categorical": ic}, compute_loss=True)
+    res["loss"].backward()
+    torch.cuda.synchronize()
+    assert _rel(res["user_embedding"].detach().cpu(), g["user_emb"]) <= 1e-5
+    assert _rel(res["item_embedding"].detach().cpu(), g["item_emb"]) <= 1e-5
+    assert _rel(res["similarity"].detach().cpu(), g["similarity"]) <= 1e-5
+    assert abs(res["loss"].item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    for prefix, tower in (("user", ut), ("item", it)):
+        for k, prm in tower.named_parameters():
+            ref = g[f"grad.{prefix}.{k}"]
+            got = prm.grad.cpu().numpy()
+            if "embeddings" in k:
+                # gradient index sets are bit-exact: same touched rows, padding row 0 untouched
+                assert np.array_equal(np.abs(got).sum(1) > 0, np.abs(ref).sum(1) > 0), k
+                assert not got[0].any()
+            assert _rel(got, ref) <= 2e-4, f"grad {prefix}.{k}: {_rel(got, ref):.3e}"
+
+
+def test_kat_losses(golden_dir):
+    from b200rec.two_tower import ItemTower, TwoTowerModel, UserTower
+    g = np.load(os.path.join(golden_dir, "kat_losses.npz"))
+    ut = UserTower(input_dim=4, embedding_dim=8, hidden_layers=[8])
+    it = ItemTower(input_dim=4, embedding_dim=8, hidden_layers=[8], use_content_embedding=False)
+    m = TwoTowerModel(ut, it, temperature=0.1).to(DEV)
+    U = torch.eye(4, 8, device=DEV)
+    neg = torch.from_numpy(g["neg"]).to(DEV)
+    # these losses are differences of two O(10) fp32 logits (lse - pos): one ulp at 10 is 9.5e-7, so the comparison is
+    # absolute at that scale (the reference itself is 6e-8 away from the closed form 1.3619e-4)
+    tol = 1e-6
+    assert abs(m.in_batch_negative_loss(U, U).item() - float(g["inbatch"])) <= tol
+    assert abs(m.contrastive_loss(U, U, neg).item() - float(g["explicit"])) <= tol
+    with torch.no_grad():
+        m.user_bias.fill_(0.5)
+        m.item_bias.fill_(0.25)
+    assert abs(m.contrastive_loss(U, U, neg).item() - float(g["explicit_bias"])) <= tol
+    with pytest.raises(RuntimeError):
+        m.contrastive_loss(U, U, U)  # one negative per sample: the reference raises too (two_tower.py:439-443)
+
+
+# ---------------------------------------------------------------- the reference's own property tests, on CUDA tensors
+def _model(cfg=None):
+    from b200rec.two_tower import create_two_tower_model
+    cfg = cfg or {"embedding_dim": 64, "temperature": 0.1,
+                  "user_tower": {"input_dim": 10, "hidden_layers": [128, 64], "dropout_rate": 0.1},
+                  "item_tower": {"input_dim": 15, "hidden_layers": [128, 64], "dropout_rate": 0.1,
+                                 "use_content_embedding": False}}
+    return create_two_tower_model(cfg).to(DEV)
+
+
+def test_shapes_norms_and_batch_sizes():
+    m = _model()
+    m.eval()
+    for b in (1, 4, 16, 64):
+        u = m.get_user_embeddings({"numerical": torch.randn(b, 10, device=DEV)})
+        i = m.get_item_embeddings({"numerical": torch.randn(b, 15, device=DEV)})
+        assert u.shape == (b, 64) and i.shape == (b, 64)
+        assert torch.allclose(u.norm(dim=1), torch.ones(b, device=DEV), atol=1e-5)
+        assert torch.allclose(i.norm(dim=1), torch.ones(b, device=DEV), atol=1e-5)
+
+
+def test_forward_dict_loss_and_gradient_flow():
+    m = _model()
+    m.train()
+    x = torch.randn(8, 10, device=DEV, requires_grad=True)
+    out = m({"numerical": x}, {"numerical": torch.randn(8, 15, device=DEV)}, compute_loss=True)
+    assert set(out) == {"user_embedding", "item_embedding", "similarity", "loss"}
+    assert out["similarity"].shape == (8,) and out["loss"].dim() == 0 and out["loss"].item() >= 0
+    out["loss"].backward()
+    assert x.grad is not None and x.grad.abs().sum().item() > 0
+    assert all(p.grad is not None for p in m.user_tower.parameters())
+
+
+def test_train_mode_batch_of_one_raises():
+    m = _model()
+    m.train()
+    with pytest.raises(ValueError):
+        m.get_user_embeddings({"numerical": torch.randn(1, 10, device=DEV)})
+
+
+def test_content_embedding_branch():
+    from b200rec.two_tower import ItemTower
+    it = ItemTower(input_dim=15, embedding_dim=32, hidden_layers=[64], use_content_embedding=True).to(DEV)
+    it.eval()
+    e = it(torch.randn(4, 15, device=DEV), None, torch.randn(4, 768, device=DEV))
+    assert e.shape == (4, 32)
+    assert torch.allclose(e.norm(dim=1), torch.ones(4, device=DEV), atol=1e-5)
+
+
+def test_eval_determinism_and_save_load_roundtrip(tmp_path):
+    m = _model()
+    m.eval()
+    x = {"numerical": torch.randn(5, 10, device=DEV)}
+    a, b = m.get_user_embeddings(x), m.get_user_embeddings(x)
+    assert torch.equal(a, b)
+    path = str(tmp_path / "ckpt.pth")
+    m.save_model(path)
+    m2 = _model()
+    m2.load_model(path)
+    m2.eval()
+    assert torch.allclose(m2.get_user_embeddings(x), a, atol=1e-4)
+
+
+def test_smoke_training_reduces_loss():
+    from b200rec.trainer import TwoTowerTrainer
+    torch.manual_seed(0)
+    m = _model()
+    tr = TwoTowerTrainer(m, [], [], {"learning_rate": 1e-2, "checkpoint_dir": "/tmp/b200rec_ckpt"}, device=DEV)
+    m.train()
+    uf, pf = torch.randn(64, 10, device=DEV), torch.randn(64, 15, device=DEV)
+    nf = torch.randn(64, 4, 15, device=DEV)
+    losses = [tr.train_step(uf, pf, nf).item() for _ in range(30)]
+    assert losses[-1] < losses[0]
+
+
+def test_dropout_mask_rate_and_scaling():
+    from b200rec import kernels as K
+    z = torch.ones(4096, 64, device=DEV)
+    y = K.act_dropout(z, K.ACT_IDS["identity"], 0.2, 1234)
+    kept = (y > 0).float().mean().item()
+    assert abs(kept - 0.8) < 0.01
+    assert torch.allclose(y[y > 0], torch.full_like(y[y > 0], 1.25))
+    assert torch.equal(y, K.act_dropout(z, K.ACT_IDS["identity"], 0.2, 1234))  # same seed, same mask

@@ -1,0 +1,90 @@
+"""GPU parity of the training-side kernels against plain fp32 torch / the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_gather_concat_and_sparse_grad_match_oracle():
+    from b200rec import kernels as K
+    from oracle.two_tower import embedding_touched_rows
+    rng = np.random.default_rng(0)
+    B = 1000
+    tabs = [torch.randn(501, 50), torch.randn(20001, 64), torch.randn(7, 3)]
+    idx = [torch.from_numpy(rng.integers(0, t.shape[0], size=B)) for t in tabs]
+    idx[1][:300] = 17  # hot row
+    num = torch.randn(B, 5)
+    widths = [50, 64, 3]
+    offs = [5, 55, 119]
+    out, err = K.gather_concat(num.to(DEV), [t.to(DEV) for t in tabs], [i.to(DEV) for i in idx], widths, offs, 122, B, DEV)
+    ref = torch.cat([num] + [t[i] for t, i in zip(tabs, idx)], dim=1)
+    assert torch.equal(out.cpu(), ref)  # gathers are bit-exact
+    assert int(err.item()) == 0
+    dout = torch.randn(B, 122)
+    for f, (t, i) in enumerate(zip(tabs, idx)):
+        rows, vals, n = K.embedding_sparse_grad(i.to(DEV), dout.to(DEV)[:, offs[f]:], widths[f], t.shape[0], 0)
+        n = int(n.item())
+        want_rows = embedding_touched_rows(i.numpy())
+        assert np.array_equal(rows[:n].cpu().numpy(), want_rows)  # gradient index sets are bit-exact
+        dense = torch.zeros_like(t).index_add_(0, i, dout[:, offs[f]:offs[f] + widths[f]])
+        dense[0] = 0
+        got = torch.zeros_like(t)
+        got[rows[:n].cpu()] = vals[:n].cpu()
+        assert torch.allclose(got, dense, atol=1e-4, rtol=1e-5)
+
+
+def test_flat_adam_matches_torch_adam_with_clipping():
+    from b200rec.trainer import FlatAdam
+    torch.manual_seed(1)
+    shapes = [(64, 20), (64,), (128, 64), (1,)]
+    ref_p = [torch.nn.Parameter(torch.randn(s)) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone().to(DEV)) for p in ref_p]
+    ref_opt = torch.optim.Adam(ref_p, lr=1e-3, weight_decay=1e-5)
+    ours = FlatAdam(our_p, lr=1e-3, weight_decay=1e-5, max_grad_norm=1.0)
+    for step in range(5):
+        grads = [torch.randn(s) * (3.0 if step % 2 == 0 else 0.01) for s in shapes]
+        ref_opt.zero_grad()
+        ours.zero_grad()
+        for p, g in zip(ref_p, grads):
+            p.grad = g.clone()
+        for p, g in zip(our_p, grads):
+            p.grad.copy_(g.to(DEV))
+        norm = torch.nn.utils.clip_grad_norm_(ref_p, max_norm=1.0)
+        ref_opt.step()
+        ours.step()
+        assert abs(ours.grad_norm.item() - norm.item()) <= 1e-5 * norm.item()
+        for a, b in zip(our_p, ref_p):
+            assert torch.allclose(a.detach().cpu(), b.detach(), atol=1e-6, rtol=1e-5)
+
+
+def test_inbatch_loss_large_batch_and_backward_vs_torch():
+    from b200rec import ops
+    torch.manual_seed(2)
+    for B, E, terms, tol in ((8192, 64, 6, 1e-5), (3000, 128, 6, 1e-5), (4096, 64, 1, 2e-2)):
+        u = torch.nn.functional.normalize(torch.randn(B, E), dim=1)
+        i = torch.nn.functional.normalize(torch.randn(B, E) + 0.5 * u, dim=1)
+        uc, ic = u.clone().to(DEV).requires_grad_(), i.clone().to(DEV).requires_grad_()
+        loss = ops.InBatchCEFn.apply(uc, ic, 20.0, terms, 0, B)
+        loss.backward()
+        ur, ir = u.clone().double().requires_grad_(), i.clone().double().requires_grad_()
+        ref = torch.nn.functional.cross_entropy(ur @ ir.T * 20.0, torch.arange(B))
+        ref.backward()
+        assert abs(loss.item() - ref.item()) <= tol * abs(ref.item()), (B, E, terms, loss.item(), ref.item())
+        gtol = 1e-4 if terms == 6 else 5e-2
+        assert (uc.grad.cpu().double() - ur.grad).abs().max() <= gtol * ur.grad.abs().max()
+        assert (ic.grad.cpu().double() - ir.grad).abs().max() <= gtol * ir.grad.abs().max()
+
+
+def test_bf16_mode_within_budget():
+    from b200rec.training_utils import create_two_tower_model_for_training
+    torch.manual_seed(3)
+    m = create_two_tower_model_for_training(16, 16, {"embedding_dim": 64, "hidden_layers": [128, 64],
+                                                     "dropout_rate": 0.0}).to(DEV)
+    m.eval()
+    x = torch.randn(512, 16, device=DEV)
+    a = m.get_user_embeddings({"numerical": x})
+    m.precision = "bf16"
+    b = m.get_user_embeddings({"numerical": x})
+    assert (a - b).abs().max().item() <= 2e-2 * a.abs().max().item()
