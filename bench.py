@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 two-tower hot path (contract: one JSON line on rank 0).
+
+Primary workload (BASELINE.json config 3): exact inner-product top-100 over a 10 M x 128 bf16 catalogue, query batch
+4096, catalogue row-sharded over the N GPUs of one box (total work fixed => "strong" scaling).  `value` = whole-job
+QPS with queries resident in HBM; `e2e` = the same through the public index API with HOST query / result buffers.
+The `train` block reports BASELINE.json config 2 (1 M users x 100 K items, dim 64, batch 8192, in-batch negatives) as
+train samples/s on rank 0's GPU (N=1 only).  `--impl reference` times the CPU restatement of the reference's path
+(oracle/: numpy sgemm + select standing in for faiss-cpu, which cannot be installed offline).
+
+  python bench.py --gpus 1 --steps 20 --warmup 5
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 bench.py --gpus 8
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_ITEMS = 10_000_000
+DIM = 128
+N_QUERIES = 4096
+TOPK = 100
+SEED = 1234
+METRIC = "top-100 exact-IP QPS over 10M items"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "tflops": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+        self.thread = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+                for name, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ data
+def make_queries_host(seed: int = SEED) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    q = torch.nn.functional.normalize(torch.randn(N_QUERIES, DIM, generator=g), dim=1)
+    return q
+
+
+def make_catalogue_shard(lo: int, hi: int, device) -> torch.Tensor:
+    """Rows [lo, hi) of the synthetic catalogue normalize(N(0,1)) -> bf16; generated block-wise from (seed, block) so
+    any sharding sees the same global rows."""
+    out = torch.empty((hi - lo, DIM), dtype=torch.bfloat16, device=device)
+    blk = 1 << 20
+    b0 = lo // blk
+    while b0 * blk < hi:
+        s, e = b0 * blk, min((b0 + 1) * blk, N_ITEMS)
+        g = torch.Generator(device=device).manual_seed(SEED * 1000003 + b0)
+        x = torch.nn.functional.normalize(torch.randn(e - s, DIM, device=device, generator=g), dim=1).to(torch.bfloat16)
+        a, b = max(s, lo), min(e, hi)
+        out[a - lo:b - lo] = x[a - s:b - s]
+        b0 += 1
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_retrieval_baseline(rows: int, queries: int, threads: int):
+    """Flat IP top-100 with the oracle (numpy sgemm + exact select) on a bounded sample; QPS scaled to 10 M rows."""
+    from oracle.flat_ip import IndexFlatIP, normalize_L2
+    torch.set_num_threads(threads)
+    rng = np.random.default_rng(SEED)
+    cat = normalize_L2(rng.standard_normal((rows, DIM)).astype(np.float32))
+    qry = normalize_L2(rng.standard_normal((queries, DIM)).astype(np.float32))
+    ix = IndexFlatIP(DIM)
+    ix.add(cat)
+    t0 = time.perf_counter()
+    ix.search(qry, TOPK)
+    dt = time.perf_counter() - t0
+    qps_full = queries / (dt * (N_ITEMS / rows))
+    return qps_full, dt
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rows, queries = 1_000_000, 128
+    vals = []
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_retrieval_baseline(rows // 4, 32, threads)
+    t_all = time.perf_counter()
+    steps = max(1, min(args.steps, 3))
+    for _ in range(steps):
+        qps, dt = cpu_retrieval_baseline(rows, queries, threads)
+        vals.append(qps)
+    ms = (time.perf_counter() - t_all) / steps * 1e3
+    v = float(np.median(vals))
+    sample = (f"{queries} queries x {rows} rows fp32 per step, oracle/flat_ip.py (numpy sgemm + exact select, faiss-cpu "
+              f"restated), QPS scaled linearly to {N_ITEMS} rows")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "exact IP top-100, 10M x 128, query batch 4096 (CPU arm: bounded sample)"},
+            "cpu_baseline": {"value": v, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ training block
+def run_train_block(device, steps: int, warmup: int, cpu_baseline: bool):
+    """BASELINE config 2: 1 M users x 100 K items, dim 64, batch 8192, in-batch negatives, one B200."""
+    from b200rec import _native as N
+    from b200rec.trainer import TwoTowerTrainer
+    from b200rec.training_utils import create_two_tower_model_for_training
+    B, NU, NI, FD = 8192, 1_000_000, 100_000, 16
+    torch.manual_seed(SEED)
+    cfg = {"embedding_dim": 64, "hidden_layers": [128, 64], "dropout_rate": 0.2, "temperature": 0.05,
+           "user_categorical_features": {"user_id": NU}, "item_categorical_features": {"item_id": NI},
+           "embedding_dims": {"user_id": 64, "item_id": 64}}
+    model = create_two_tower_model_for_training(FD, FD, cfg)
+    trainer = TwoTowerTrainer(model, [], [], {"learning_rate": 1e-3, "weight_decay": 1e-5,
+                                              "checkpoint_dir": "/tmp/b200rec_bench_ckpt"}, device=str(device))
+    model.train()
+    rng = np.random.default_rng(SEED)
+    pool = 8
+
+    def zipf_ids(n, hi):
+        return np.clip(rng.zipf(1.05, size=n), 1, hi).astype(np.int64)
+
+    host = [{"uf": torch.randn(B, FD).pin_memory(), "pf": torch.randn(B, FD).pin_memory(),
+             "uid": torch.from_numpy(zipf_ids(B, NU)).pin_memory(),
+             "iid": torch.from_numpy(zipf_ids(B, NI)).pin_memory()} for _ in range(pool)]
+    dev = [{k: v.to(device) for k, v in b.items()} for b in host]
+
+    def step_dev(b):
+        return trainer.train_step(b["uf"], b["pf"], None, {"user_id": b["uid"]}, {"item_id": b["iid"]})
+
+    for i in range(max(warmup, 3)):
+        step_dev(dev[i % pool])
+    torch.cuda.synchronize()
+    l0 = N.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step_dev(dev[i % pool])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = (N.launch_count() - l0) // steps
+    # end to end: host batches (pinned) -> device every step, loss read back every step
+    t0 = time.perf_counter()
+    for i in range(steps):
+        b = {k: v.to(device, non_blocking=True) for k, v in host[i % pool].items()}
+        float(step_dev(b).item())
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / steps * 1e3
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    out = {"metric": "train samples/s", "value": B / ms * 1e3, "unit": "samples/s", "ms_per_step": ms,
+           "config": {"workload": "synthetic 1M users x 100K items, dim 64, batch 8192, in-batch negatives, fp32-grade "
+                                  "split-bf16 GEMMs, dense Adam + clip (reference semantics)"},
+           "e2e": {"value": B / e2e_ms * 1e3, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+           "gpu_launches_per_step": int(launches), "dtype": "f32 (bf16x6 split products, fp32 accumulate)"}
+    if cpu_baseline:
+        out["cpu_baseline"] = cpu_train_baseline(B, FD)
+    del trainer, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def cpu_train_baseline(B: int, FD: int):
+    """Oracle port of the step's forward + backward (numpy fp32; no optimiser) at the config-2 shape, tables reduced
+    to the touched rows' width (the gather itself is a memcpy on CPU)."""
+    from oracle.two_tower import TowerOracle, in_batch_loss
+    rng = np.random.default_rng(SEED)
+
+    def params(inp):
+        p = {}
+        dims = [inp, 128, 64]
+        for l in range(2):
+            p[f"mlp.{4 * l}.weight"] = rng.standard_normal((dims[l + 1], dims[l])).astype(np.float32) * 0.1
+            p[f"mlp.{4 * l}.bias"] = np.zeros(dims[l + 1], np.float32)
+            p[f"mlp.{4 * l + 2}.weight"] = np.ones(dims[l + 1], np.float32)
+            p[f"mlp.{4 * l + 2}.bias"] = np.zeros(dims[l + 1], np.float32)
+            p[f"mlp.{4 * l + 2}.running_mean"] = np.zeros(dims[l + 1], np.float32)
+            p[f"mlp.{4 * l + 2}.running_var"] = np.ones(dims[l + 1], np.float32)
+        p["mlp.8.weight"] = rng.standard_normal((64, 64)).astype(np.float32) * 0.1
+        p["mlp.8.bias"] = np.zeros(64, np.float32)
+        return p
+
+    ut, it = TowerOracle(params(FD + 64), 2, dtype=np.float32), TowerOracle(params(FD + 64), 2, dtype=np.float32)
+    xu = rng.standard_normal((B, FD + 64)).astype(np.float32)
+    xi = rng.standard_normal((B, FD + 64)).astype(np.float32)
+    steps = 3
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        u, i = ut.forward(xu, training=True), it.forward(xi, training=True)
+        _, du, di = in_batch_loss(u, i, 0.05, want_grad=True)
+        ut.backward(du)
+        it.backward(di)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": B / dt, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"{steps} steps of oracle/two_tower.py forward+backward+in-batch loss (numpy fp32, no optimiser) "
+                      f"at batch {B}"}
+
+
+# ------------------------------------------------------------------------------------------------ main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-train", action="store_true", help="skip the config-2 training block")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the b200rec kernels")
+    import torch.distributed as dist
+    from b200rec import _native as N
+    from b200rec import kernels as K
+    from b200rec.dist import ShardedFlatIndex, shard_bounds
+    from b200rec.retrieval import FlatIPDeviceIndex
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    warmup = max(args.warmup, 3)
+    steps = max(args.steps, 1)
+
+    lo, hi = shard_bounds(N_ITEMS, world, rank)
+    index = FlatIPDeviceIndex(DIM, storage="bf16", device=device, row_offset=lo)
+    index.add_bf16_rows(make_catalogue_shard(lo, hi, device))
+    sharded = ShardedFlatIndex.from_device_index(index)
+    q_host = make_queries_host().pin_memory()
+    q_op = index.prepare_queries(q_host, normalize=False)  # resident bf16 operand for the `value` region
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        s, i = sharded.search(q_op, TOPK)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = N.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        s, i = sharded.search(q_op, TOPK)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    launches = N.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # dominant kernel alone (CUDA events recorded by the library around stream_scores_kernel<topk> on its stream)
+    import ctypes
+    lib = N.lib()
+    lib.b200rec_debug_topk_kernel_timing.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
+    lib.b200rec_debug_topk_kernel_timing(1, None)
+    kms = []
+    for _ in range(min(steps, 10)):
+        sharded.search(q_op, TOPK)
+        out = ctypes.c_float(0)
+        lib.b200rec_debug_topk_kernel_timing(1, ctypes.byref(out))
+        kms.append(out.value)
+    lib.b200rec_debug_topk_kernel_timing(0, None)
+    kernel_ms = float(np.mean(kms))
+
+    # end to end through the public API: host fp32 queries -> (D, I) on the host, copies inside the timed region
+    d_host = torch.empty((N_QUERIES, TOPK), dtype=torch.float32).pin_memory()
+    i_host = torch.empty((N_QUERIES, TOPK), dtype=torch.int64).pin_memory()
+
+    def e2e_once():
+        qo = index.prepare_queries(q_host, normalize=True)   # H2D copy + faiss.normalize_L2 + operand cast
+        ds, ii = sharded.search(qo, TOPK)
+        d_host.copy_(ds, non_blocking=True)
+        i_host.copy_(ii, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        e2e_once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_once()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) / steps * 1e3
+
+    t = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, kernel_ms = [float(x) for x in t.tolist()]
+
+    train = None
+    cpu = None
+    if rank == 0 and world == 1:
+        del sharded, index, q_op
+        torch.cuda.empty_cache()
+        if not args.no_train:
+            train = run_train_block(device, max(steps, 10), warmup, not args.no_cpu_baseline)
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            rows, queries = 1_000_000, 128
+            v, dt = cpu_retrieval_baseline(rows, queries, threads)
+            cpu = {"value": v, "unit": "queries/s", "cores": threads, "kind": "port",
+                   "sample": f"{queries} queries x {rows} rows fp32 ({dt:.1f} s), oracle/flat_ip.py numpy sgemm + exact "
+                             f"select (faiss-cpu restated), QPS scaled linearly to {N_ITEMS} rows"}
+    if rank == 0:
+        peaks = _peaks()
+        n_local = (N_ITEMS + world - 1) // world
+        flops = 2.0 * N_QUERIES * n_local * DIM
+        achieved = flops / (kernel_ms * 1e-3) / 1e12
+        line = {"metric": METRIC, "value": N_QUERIES / ms * 1e3, "unit": "queries/s", "n_gpus": world, "steps": steps,
+                "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "exact IP top-100 retrieval, 10M items x 128-dim bf16, query batch 4096, "
+                                       f"catalogue row-sharded over {world} GPU(s)",
+                           "l2": "catalogue shard (>= 320 MB) exceeds L2 between iterations", "seed": SEED},
+                "e2e": {"value": N_QUERIES / e2e_ms * 1e3, "unit": "queries/s",
+                        "h2d_bytes_per_step": N_QUERIES * DIM * 4, "d2h_bytes_per_step": N_QUERIES * TOPK * 12},
+                "gpu_launches": int(launches),
+                "clocks": clocks,
+                "roofline": {"kernel": "stream_scores_kernel<topk> (scoring GEMM fused with top-K select)",
+                             "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                             "frac": achieved / peaks["tflops"], "traffic": None, "kernel_ms": kernel_ms,
+                             "flops_per_launch": flops, "peak_source": peaks["source"],
+                             "hbm_floor_ms": n_local * DIM * 2 / (peaks["hbm_gbs"] * 1e9) * 1e3},
+                "cpu_baseline": cpu, "train": train}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

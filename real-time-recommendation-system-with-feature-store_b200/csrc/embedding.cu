@@ -66,28 +66,49 @@ __global__ void mark_heads_kernel(const int64_t* __restrict__ sidx, int64_t n, i
   }
 }
 
-// one warp per sorted position that is a head: sum the segment's dY rows
+// One warp per chunk of 32 consecutive SORTED positions (a hot row with thousands of duplicates — Zipf ids — is then
+// spread over many warps instead of being walked serially by one): lanes own gradient columns, the 32 row ids /
+// source positions are exchanged by shuffles so every dY load address is known up front, a run of equal rows is
+// summed in registers and flushed once with atomicAdd (runs may continue in the neighbouring chunks; grad_rows is
+// pre-zeroed).  slot = exclusive scan of the head flags, so position i belongs to output row slot[i] + head[i] - 1.
 __global__ void __launch_bounds__(256)
 segment_sum_kernel(const int64_t* __restrict__ sidx, const int32_t* __restrict__ spos, const int32_t* __restrict__ head,
-                   const int32_t* __restrict__ slot, int64_t n, const float* __restrict__ dY, int64_t ld_dy, int width,
-                   int64_t* __restrict__ unique_rows, float* __restrict__ grad_rows, int32_t* __restrict__ n_unique) {
+                   const int32_t* __restrict__ slot, int64_t n, int64_t padding_idx, const float* __restrict__ dY,
+                   int64_t ld_dy, int width, int64_t* __restrict__ unique_rows, float* __restrict__ grad_rows,
+                   int32_t* __restrict__ n_unique) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
-    if (i == n - 1 && lane == 0) *n_unique = slot[i] + head[i];
-    if (!head[i]) continue;
-    const int64_t r = sidx[i];
-    const int32_t u = slot[i];
-    int64_t e = i + 1;
-    while (e < n && sidx[e] == r) ++e;
+  const int64_t chunks = (n + 31) / 32;
+  for (int64_t ch = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ch < chunks; ch += warps) {
+    const int64_t i = ch * 32 + lane;
+    int32_t my_u = -1, my_pos = 0;
+    if (i < n) {
+      const int64_t r = sidx[i];
+      const int32_t h = head[i], sl = slot[i];
+      if (r != padding_idx) {
+        my_u = sl + h - 1;
+        my_pos = spos[i];
+        if (h) unique_rows[my_u] = r;
+      }
+      if (i == n - 1) *n_unique = sl + h;
+    }
+    const int cnt = (int)((n - ch * 32) < 32 ? (n - ch * 32) : 32);
     for (int c0 = 0; c0 < width; c0 += 32) {
       const int c = c0 + lane;
       float acc = 0.f;
-      if (c < width)
-        for (int64_t j = i; j < e; ++j) acc += __ldg(dY + (int64_t)spos[j] * ld_dy + c);
-      if (c < width) grad_rows[(int64_t)u * width + c] = acc;
+      int cur = -1;
+      for (int j = 0; j < cnt; ++j) {
+        const int32_t u = __shfl_sync(FULL_MASK, my_u, j);
+        const int32_t p = __shfl_sync(FULL_MASK, my_pos, j);
+        if (u != cur) {
+          if (cur >= 0 && c < width) atomicAdd(grad_rows + (int64_t)cur * width + c, acc);
+          acc = 0.f;
+          cur = u;
+        }
+        if (u >= 0 && c < width) acc += __ldg(dY + (int64_t)p * ld_dy + c);
+      }
+      if (cur >= 0 && c < width) atomicAdd(grad_rows + (int64_t)cur * width + c, acc);
     }
-    if (lane == 0) unique_rows[u] = r;
   }
 }
 
@@ -208,10 +229,10 @@ extern "C" int b200rec_embedding_sparse_grad(const int64_t* idx, int64_t B, cons
   tmp = w.cub_bytes;
   B200_CUDA_OK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.head, w.slot, (int)B, st));
   b200::g_launches.fetch_add(1);
-  const int64_t blocks = (B + 7) / 8;
+  const int64_t blocks = ((B + 31) / 32 + 7) / 8;
   const int grid = (int)(blocks < (int64_t)num_sms() * 16 ? blocks : (int64_t)num_sms() * 16);
-  segment_sum_kernel<<<grid, 256, 0, st>>>(w.sidx, w.spos, w.head, w.slot, B, dY, ld_dy, width, unique_rows, grad_rows,
-                                           n_unique_out);
+  segment_sum_kernel<<<grid, 256, 0, st>>>(w.sidx, w.spos, w.head, w.slot, B, padding_idx, dY, ld_dy, width,
+                                           unique_rows, grad_rows, n_unique_out);
   B200_LAUNCH_OK("segment_sum_kernel");
   return 0;
 }

@@ -645,6 +645,10 @@ static int next_pow2(int v) {
   return p;
 }
 
+// optional CUDA-event bracket around the dominant kernel (bench.py's roofline line), on the launching stream
+static int g_time_kernel = 0;
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+
 struct TopkPlan {
   int nq, bn;
   StreamGeom g;
@@ -738,8 +742,16 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
     topk_init_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(ea.meta, (int)Q, nextafterf(-FLT_MAX, 0.f));
     B200_LAUNCH_OK("topk_init_kernel");
   }
+  if (g_time_kernel) {
+    if (!g_ev0) {
+      B200_CUDA_OK(cudaEventCreate(&g_ev0));
+      B200_CUDA_OK(cudaEventCreate(&g_ev1));
+    }
+    B200_CUDA_OK(cudaEventRecord(g_ev0, st));
+  }
   kern<<<p.g.grid, ST_THREADS, p.g.smem_bytes, st>>>(tq, tx, p.g, ea);
   B200_LAUNCH_OK("stream_scores_kernel<topk>");
+  if (g_time_kernel) B200_CUDA_OK(cudaEventRecord(g_ev1, st));
   const int P = next_pow2(k);
   topk_sort_kernel<<<(unsigned)Q, FIN_THREADS, P * sizeof(uint64_t), st>>>(ea.tlists, ea.meta, k, P, row_offset,
                                                                            out_scores, out_ids);
@@ -756,6 +768,19 @@ extern "C" int b200rec_debug_topk_stats(unsigned long long* out8_host, int reset
     unsigned long long z[8] = {0};
     B200_CUDA_OK(cudaMemcpyToSymbol(g_topk_stats, z, sizeof(z)));
   }
+  return 0;
+}
+
+extern "C" int b200rec_debug_topk_kernel_timing(int enable, float* last_ms_host) {
+  using namespace b200;
+  if (last_ms_host) {
+    *last_ms_host = 0.f;
+    if (g_ev0 && g_ev1) {
+      B200_CUDA_OK(cudaEventSynchronize(g_ev1));
+      B200_CUDA_OK(cudaEventElapsedTime(last_ms_host, g_ev0, g_ev1));
+    }
+  }
+  g_time_kernel = enable;
   return 0;
 }
 

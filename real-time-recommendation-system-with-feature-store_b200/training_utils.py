@@ -22,10 +22,12 @@ def create_two_tower_model_for_training(user_feature_dim: int, item_feature_dim:
     use_bias = config.get("use_bias", True)
     user_tower = UserTower(input_dim=user_feature_dim, embedding_dim=embedding_dim, hidden_layers=hidden_layers,
                            dropout_rate=dropout_rate, activation=activation,
-                           categorical_features=config.get("user_categorical_features"))
+                           categorical_features=config.get("user_categorical_features"),
+                           embedding_dims=config.get("embedding_dims"))
     item_tower = ItemTower(input_dim=item_feature_dim, embedding_dim=embedding_dim, hidden_layers=hidden_layers,
                            dropout_rate=dropout_rate, activation=activation,
-                           categorical_features=config.get("item_categorical_features"), use_content_embedding=False)
+                           categorical_features=config.get("item_categorical_features"), use_content_embedding=False,
+                           embedding_dims=config.get("embedding_dims"))
     return TwoTowerModel(user_tower=user_tower, item_tower=item_tower, temperature=temperature, use_bias=use_bias)
 
 

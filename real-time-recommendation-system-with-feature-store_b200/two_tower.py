@@ -45,7 +45,8 @@ class _TowerBase(nn.Module):
     """Shared machinery of the two towers: embeddings dict + [Linear, act, BatchNorm1d, Dropout]xL + Linear."""
 
     def _build(self, input_dim: int, embedding_dim: int, hidden_layers: List[int], dropout_rate: float,
-               activation: str, categorical_features: Optional[Dict[str, int]], extra_dim: int = 0) -> None:
+               activation: str, categorical_features: Optional[Dict[str, int]],
+               embedding_dims: Optional[Dict[str, int]] = None) -> None:
         self.input_dim = input_dim
         self.embedding_dim = embedding_dim
         self.categorical_features = categorical_features or {}
@@ -56,7 +57,9 @@ class _TowerBase(nn.Module):
         self.embeddings = nn.ModuleDict()
         total_embedding_dim = 0
         for feat_name, cardinality in self.categorical_features.items():
-            embed_dim = min(50, (cardinality + 1) // 2)
+            embed_dim = min(50, (cardinality + 1) // 2)  # the reference's heuristic (two_tower.py:45,175)
+            if embedding_dims and feat_name in embedding_dims:
+                embed_dim = int(embedding_dims[feat_name])  # B200 extension: 16-byte aligned rows (64 / 128 wide)
             self.embeddings[feat_name] = nn.Embedding(cardinality + 1, embed_dim, padding_idx=0)
             total_embedding_dim += embed_dim
         self._total_embedding_dim = total_embedding_dim
@@ -129,9 +132,11 @@ class UserTower(_TowerBase):
 
     def __init__(self, input_dim: int, embedding_dim: int = 128, hidden_layers: List[int] = [512, 256, 128],
                  dropout_rate: float = 0.2, activation: str = "relu",
-                 categorical_features: Optional[Dict[str, int]] = None):
+                 categorical_features: Optional[Dict[str, int]] = None,
+                 embedding_dims: Optional[Dict[str, int]] = None):
         super().__init__()
-        self._build(input_dim, embedding_dim, hidden_layers, dropout_rate, activation, categorical_features)
+        self._build(input_dim, embedding_dim, hidden_layers, dropout_rate, activation, categorical_features,
+                    embedding_dims)
         self._build_mlp(input_dim + self._total_embedding_dim, hidden_layers, dropout_rate, activation, embedding_dim)
         self._init_weights()
 
@@ -147,9 +152,10 @@ class ItemTower(_TowerBase):
     def __init__(self, input_dim: int, embedding_dim: int = 128, hidden_layers: List[int] = [512, 256, 128],
                  dropout_rate: float = 0.2, activation: str = "relu",
                  categorical_features: Optional[Dict[str, int]] = None, use_content_embedding: bool = True,
-                 content_embedding_dim: int = 768):
+                 content_embedding_dim: int = 768, embedding_dims: Optional[Dict[str, int]] = None):
         super().__init__()
-        self._build(input_dim, embedding_dim, hidden_layers, dropout_rate, activation, categorical_features)
+        self._build(input_dim, embedding_dim, hidden_layers, dropout_rate, activation, categorical_features,
+                    embedding_dims)
         self.use_content_embedding = use_content_embedding
         total = self._total_embedding_dim
         if use_content_embedding:
