@@ -62,7 +62,7 @@ struct LseEpi {
 
   template <int NQ, int QPT>
   __device__ __forceinline__ void end_segment(const Args& ea, const StreamGeom& g, int sidx, int part,
-                                              const int (&qslot)[QPT], int, uint32_t*) {
+                                              const int (&qslot)[QPT], int, uint32_t*, bool) {
 #pragma unroll
     for (int a = 0; a < QPT; ++a) {
       const size_t o = ((size_t)sidx * g.max_parts + part) * (128 * NQ) + qslot[a];

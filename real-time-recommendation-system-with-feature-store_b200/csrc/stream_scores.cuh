@@ -228,7 +228,7 @@ stream_scores_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
       }
-      epi.template end_segment<NQ, QPT>(ea, g, s, part, qslot, lane, scratch);
+      epi.template end_segment<NQ, QPT>(ea, g, s, part, qslot, lane, scratch, /*last=*/(w + (t1 - t0)) >= w_end);
       w += t1 - t0;
     }
     Epi::epilogue_exit(scratch, lane);

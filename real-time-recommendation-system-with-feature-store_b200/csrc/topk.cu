@@ -135,10 +135,12 @@ struct TopkEpi {
     uint64_t* lists;                // [grid][128*NQ][2*cap]   private candidate lists A/B
     uint64_t* tlists;               // [Q][2*k]                shared running top-k lists T0/T1
     QMeta* meta;                    // [Q]
+    uint32_t* left;                 // [grid][128*NQ]  leftover (list id << 31 | count) of each CTA's last segment
     const int64_t* excl_indptr;     // [Q+1] or null
     const int32_t* excl_rows;       // sorted per query
     int k;
     int cap;
+    int flush;  // hand a list to the helper warps once it holds this many candidates (keeps tau fresh)
     int debug;  // development knob: 1 = reject everything (MMA + fast-path ceiling), 2 = count events
   };
   float tau[2];
@@ -197,8 +199,10 @@ struct TopkEpi {
     for (int a = 0; a < QPT; ++a) {
       const uint64_t pub = *reinterpret_cast<volatile uint64_t*>(scratch + 1024 + 2 * qslot[a]);
       if ((uint32_t)(pub >> 32) == qid[a] && qid[a] != NO_QUERY) tau[a] = fmaxf(tau[a], __uint_as_float((uint32_t)pub));
-      if (cnt[a] + BN > ea.cap) {
-        volatile uint32_t* req = scratch + 1536 + qslot[a];
+      const bool must = cnt[a] + BN > ea.cap;   // the list could overflow during the next tile
+      volatile uint32_t* reqp = scratch + 1536 + qslot[a];
+      if (must || (cnt[a] >= ea.flush && *reqp == 0u)) {
+        volatile uint32_t* req = reqp;
         if (ea.debug == 2) {
           const long long t0 = clock64();
           wait_idle(req);
@@ -274,9 +278,22 @@ struct TopkEpi {
     return bits;
   }
 
+  // End of a segment.  A CTA's LAST segment does not merge: it waits for its in-flight merges and publishes what is
+  // left in the active list (id << 31 | count); the final per-query kernel selects over T u leftovers with one CTA per
+  // query, which replaces a serialised tail of ~38 K locked merges.  Earlier segments (CTAs spanning a supertile
+  // boundary) hand the list to the helper warps as usual because their buffers are reused by the next segment.
   template <int NQ, int QPT>
   __device__ __forceinline__ void end_segment(const Args& ea, const StreamGeom& g, int s, int part,
-                                              const int (&qslot)[QPT], int lane, uint32_t* scratch) {
+                                              const int (&qslot)[QPT], int lane, uint32_t* scratch, bool last) {
+    if (last) {
+#pragma unroll
+      for (int a = 0; a < QPT; ++a) {
+        wait_idle(scratch + 1536 + qslot[a]);
+        ea.left[(size_t)blockIdx.x * (128 * NQ) + qslot[a]] =
+            (qid[a] != NO_QUERY) ? ((active[a] << 31) | (uint32_t)cnt[a]) : 0u;
+      }
+      return;
+    }
 #pragma unroll
     for (int a = 0; a < QPT; ++a) {
       volatile uint32_t* req = scratch + 1536 + qslot[a];
@@ -424,6 +441,68 @@ struct TopkEpi {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// Sampling pass policy: the same streaming kernel over a strided sample of the catalogue (m = N/32 rows), fast path
+// only — each epilogue thread writes the MAXIMUM score of every group of `gw` sampled rows for its query.  Group
+// maxima belong to distinct rows, so the k-th largest of them is a valid lower bound of the final k-th score; with
+// thousands of groups per query it is nearly as tight as the exact k-th of the whole sample, and it costs no
+// selection at all.  It removes the cold-start phase in which almost every score is a candidate.
+// ---------------------------------------------------------------------------------------------------------------
+struct SampleMaxEpi {
+  static constexpr int SCRATCH_BYTES = 64;
+  struct Args {
+    float* out;     // [Q][ngroups]
+    int ngroups;    // m / gw
+    int gw;         // 32, 64 or 128 sampled rows per group
+  };
+  long long qrow[2];
+
+  static __device__ __forceinline__ void init_scratch(uint32_t*, int) {}
+  static __device__ __forceinline__ void epilogue_exit(uint32_t*, int) {}
+  template <int NQ, int EPI_WARPS>
+  static __device__ __forceinline__ void helper(const Args&, const StreamGeom&, int, int, uint32_t*) {}
+
+  template <int NQ, int QPT>
+  __device__ __forceinline__ void begin_segment(const Args&, const StreamGeom& g, int s, int, const int (&qslot)[QPT],
+                                                int, uint32_t*) {
+#pragma unroll
+    for (int a = 0; a < QPT; ++a) {
+      const long long q = (long long)s * 128 * NQ + qslot[a];
+      qrow[a] = q < g.Q ? q : -1;
+    }
+  }
+  template <int NQ, int BN, int QPT>
+  __device__ __forceinline__ void pre_tile(const Args&, const StreamGeom&, const int (&)[QPT], int, uint32_t*) {}
+
+  template <int BN>
+  __device__ __forceinline__ void tile(const Args& ea, const StreamGeom&, int a, uint32_t taddr,
+                                       unsigned long long row0) {
+    float run = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + c, v);
+      tmem_ld_wait();
+      float m4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float m0 = fmax3(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]), __uint_as_float(v[8 * j + 2]));
+        const float m1 = fmax3(__uint_as_float(v[8 * j + 3]), __uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+        m4[j] = fmax3(m0, m1, fmaxf(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+      }
+      run = fmaxf(run, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+      if (((c + 32) % ea.gw) == 0) {
+        if (qrow[a] >= 0) ea.out[(size_t)qrow[a] * ea.ngroups + (row0 + c) / ea.gw] = run;
+        run = -INFINITY;
+      }
+    }
+  }
+
+  template <int NQ, int QPT>
+  __device__ __forceinline__ void end_segment(const Args&, const StreamGeom&, int, int, const int (&)[QPT], int,
+                                              uint32_t*, bool) {}
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 // block-level exact select + sort of `n` keys produced by a loader; one CTA (256 threads) per query
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int FIN_THREADS = 256;
@@ -517,31 +596,65 @@ __device__ __forceinline__ void write_result(const uint64_t* skeys, int k_out, i
   }
 }
 
-// sort one query's final T list (<= k keys) and emit (score, id)
-__global__ void __launch_bounds__(FIN_THREADS)
-topk_sort_kernel(const uint64_t* __restrict__ tlists, const QMeta* __restrict__ meta, int k, int P, int64_t row_offset,
-                 float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
-  extern __shared__ uint64_t fin_smem[];
-  const int q = blockIdx.x;
-  const int tc = (int)meta[q].tcount;
-  const uint64_t* t = tlists + (size_t)q * 2 * k + (size_t)meta[q].tsel * k;
-  for (int i = threadIdx.x; i < P; i += FIN_THREADS) fin_smem[i] = (i < tc) ? __ldcg(t + i) : 0ull;
-  __syncthreads();
-  for (int size = 2; size <= P; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = threadIdx.x; i < P / 2; i += FIN_THREADS) {
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = ((lo & size) == 0);
-        const uint64_t x = fin_smem[lo], y = fin_smem[hi];
-        if ((x < y) == desc) {
-          fin_smem[lo] = y;
-          fin_smem[hi] = x;
-        }
-      }
-      __syncthreads();
+// Final per-query kernel: candidates = the query's shared list T  u  the leftovers published by every CTA whose last
+// segment scanned this query's supertile; exact select of the k best + bitonic sort (score desc, row asc).
+constexpr int FIN_MAX_SRC = 160;
+struct MultiLoader {
+  const uint64_t* const* ptr;  // shared memory
+  const int* off;              // shared memory, nsrc + 1 prefix offsets
+  int nsrc;
+  __device__ __forceinline__ uint64_t operator()(int i) const {
+    int lo = 0, hi = nsrc - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (off[mid] <= i)
+        lo = mid;
+      else
+        hi = mid - 1;
     }
+    return __ldcg(ptr[lo] + (i - off[lo]));
   }
+};
+
+template <int NQ>
+__global__ void __launch_bounds__(FIN_THREADS)
+topk_final_kernel(const StreamGeom g, const uint64_t* __restrict__ tlists, const QMeta* __restrict__ meta,
+                  const uint64_t* __restrict__ lists, const uint32_t* __restrict__ left, int cap, int k, int P,
+                  int64_t row_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+  extern __shared__ uint64_t fin_smem[];
+  __shared__ uint32_t hist[256];
+  __shared__ int s_misc[8];
+  __shared__ const uint64_t* s_ptr[FIN_MAX_SRC];
+  __shared__ int s_off[FIN_MAX_SRC + 1];
+  constexpr int QS = 128 * NQ;
+  const int q = blockIdx.x;
+  const int s = q / QS, slot = q - s * QS;
+  if (threadIdx.x == 0) {
+    int n = 0, ns = 0;
+    s_ptr[ns] = tlists + (size_t)q * 2 * k + (size_t)meta[q].tsel * k;
+    s_off[ns++] = n;
+    n += (int)meta[q].tcount;
+    const int c0 = geom_first_cta(g, s), c1 = geom_last_cta(g, s);
+    for (int c = c0; c <= c1 && ns < FIN_MAX_SRC; ++c) {
+      long long wend = (long long)(c + 1) * g.W;
+      if (wend > g.total) wend = g.total;
+      if ((int)((wend - 1) / g.T) != s) continue;  // that CTA's last segment belongs to another supertile
+      const uint32_t l = left[(size_t)c * QS + slot];
+      const int cnt = (int)(l & 0x7FFFFFFFu);
+      if (cnt == 0) continue;
+      s_ptr[ns] = lists + ((size_t)c * QS + slot) * (2 * (size_t)cap) + ((l >> 31) ? cap : 0);
+      s_off[ns++] = n;
+      n += cnt;
+    }
+    s_off[ns] = n;
+    s_misc[5] = ns;
+    s_misc[6] = n;
+  }
+  __syncthreads();
+  MultiLoader ld{s_ptr, s_off, s_misc[5]};
+  const int n = s_misc[6];
+  __syncthreads();
+  block_select_sort(ld, n, k, fin_smem, P, hist, s_misc);
   write_result(fin_smem, k, row_offset, out_scores + (size_t)q * k, out_ids + (size_t)q * k);
 }
 
@@ -653,9 +766,11 @@ struct TopkPlan {
   int nq, bn;
   StreamGeom g;
   int cap;
-  size_t lists_bytes, tlists_bytes, meta_bytes, sample_bytes;
+  size_t lists_bytes, tlists_bytes, meta_bytes, left_bytes, sample_bytes;
   int64_t sample_m, sample_stride;  // 0 = no sampling pass
-  size_t total() const { return lists_bytes + tlists_bytes + meta_bytes + sample_bytes; }
+  int sample_gw;
+  StreamGeom gs;                    // geometry of the sampling pass
+  size_t total() const { return lists_bytes + tlists_bytes + meta_bytes + left_bytes + sample_bytes; }
 };
 
 static int cap_for(int k, int bn) {
@@ -692,18 +807,31 @@ static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k) {
   p.lists_bytes = (size_t)p.g.grid * 128 * p.nq * 2 * (size_t)p.cap * sizeof(uint64_t);
   p.tlists_bytes = (size_t)Q * 2 * (size_t)k * sizeof(uint64_t);
   p.meta_bytes = (((size_t)Q * sizeof(QMeta)) + 255) / 256 * 256;
-  // sampling pass: m strided rows, m*Q scores materialised once (<= 256 MB), only when it is a small fraction of N
-  int64_t m = (64ll << 20) / Q;
-  if (m > 65536) m = 65536;
-  m = m / 128 * 128;
+  p.left_bytes = (((size_t)p.g.grid * 128 * p.nq * sizeof(uint32_t)) + 255) / 256 * 256;
+  if (p.g.max_parts + 1 > FIN_MAX_SRC) return fail("topk: too many catalogue slices per query (%d)", p.g.max_parts);
+  // sampling pass: group maxima over m = N/32 strided rows (fast path only; see SampleMaxEpi)
+  p.sample_m = p.sample_stride = 0;
+  p.sample_bytes = 0;
+  p.sample_gw = 32;
   const char* ns = getenv("B200REC_TOPK_NOSAMPLE");
-  if (m >= 4 * (int64_t)k && m >= 1024 && N >= 8 * m && !(ns && atoi(ns))) {
-    p.sample_m = m;
-    p.sample_stride = N / m;
-    p.sample_bytes = (size_t)Q * m * sizeof(float);
-  } else {
-    p.sample_m = p.sample_stride = 0;
-    p.sample_bytes = 0;
+  const char* sf = getenv("B200REC_TOPK_SAMPLE_FRAC");
+  int64_t frac = N >= (4ll << 20) ? 32 : (N >= (256ll << 10) ? 16 : 8);
+  if (sf && atoi(sf) > 0) frac = atoi(sf);
+  int64_t m = (N / frac) / 256 * 256;
+  if (!(ns && atoi(ns)) && m >= 2048) {
+    int gw = 32;
+    while (gw < 128 && gw < p.bn && m / gw > 8192) gw *= 2;
+    if (m / gw >= 2 * (int64_t)k) {
+      p.sample_m = m;
+      p.sample_stride = N / m;
+      p.sample_gw = gw;
+      p.sample_bytes = (size_t)Q * (m / gw) * sizeof(float);
+      bool sok;
+      if (p.nq == 2) sok = stream_geom<2, 128>(p.gs, m, (int)Q, KB, sms, SampleMaxEpi::SCRATCH_BYTES);
+      else if (p.bn == 256) sok = stream_geom<1, 256>(p.gs, m, (int)Q, KB, sms, SampleMaxEpi::SCRATCH_BYTES);
+      else sok = stream_geom<1, 64>(p.gs, m, (int)Q, KB, sms, SampleMaxEpi::SCRATCH_BYTES);
+      if (!sok) p.sample_m = 0, p.sample_bytes = 0;
+    }
   }
   return 0;
 }
@@ -719,10 +847,13 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
   ea.lists = reinterpret_cast<uint64_t*>(workspace);
   ea.tlists = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(workspace) + p.lists_bytes);
   ea.meta = reinterpret_cast<QMeta*>(reinterpret_cast<uint8_t*>(workspace) + p.lists_bytes + p.tlists_bytes);
+  ea.left = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + p.lists_bytes + p.tlists_bytes + p.meta_bytes);
+  B200_CUDA_OK(cudaMemsetAsync(ea.left, 0, p.left_bytes, st));
   ea.excl_indptr = excl_indptr;
   ea.excl_rows = excl_rows;
   ea.k = k;
   ea.cap = p.cap;
+  ea.flush = getenv("B200REC_TOPK_FLUSH") ? atoi(getenv("B200REC_TOPK_FLUSH")) : 32;
   ea.debug = getenv("B200REC_TOPK_DEBUG") ? atoi(getenv("B200REC_TOPK_DEBUG")) : 0;
   auto kern = stream_scores_kernel<NQ, BN, TopkEpi>;
   static int smem_set = 0;
@@ -731,11 +862,22 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
     smem_set = ST_SMEM_LIMIT;
   }
   if (p.sample_m > 0 && excl_indptr == nullptr) {
-    float* S = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + p.lists_bytes + p.tlists_bytes + p.meta_bytes);
-    if (b200rec_gemm_bf16_tn(queries, ld, Q, catalogue, ld * p.sample_stride, p.sample_m, ld, S, p.sample_m, nullptr,
-                             1.0f, 1, st))
-      return 1;
-    sample_kth_kernel<<<(unsigned)Q, FIN_THREADS, 0, st>>>(S, (int)p.sample_m, k, ea.meta);
+    float* S = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + p.lists_bytes + p.tlists_bytes + p.meta_bytes + p.left_bytes);
+    CUtensorMap ts;  // row i of this map is catalogue row i * stride
+    if (make_tmap_bf16_2d(&ts, catalogue, (uint64_t)p.sample_m, (uint64_t)ld, (uint64_t)(ld * p.sample_stride), BN)) return 1;
+    SampleMaxEpi::Args sa;
+    sa.out = S;
+    sa.ngroups = (int)(p.sample_m / p.sample_gw);
+    sa.gw = p.sample_gw;
+    auto skern = stream_scores_kernel<NQ, BN, SampleMaxEpi>;
+    static bool sattr = false;
+    if (!sattr) {
+      B200_CUDA_OK(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_LIMIT));
+      sattr = true;
+    }
+    skern<<<p.gs.grid, ST_THREADS, p.gs.smem_bytes, st>>>(tq, ts, p.gs, sa);
+    B200_LAUNCH_OK("stream_scores_kernel<sample>");
+    sample_kth_kernel<<<(unsigned)Q, FIN_THREADS, 0, st>>>(S, sa.ngroups, k, ea.meta);
     B200_LAUNCH_OK("sample_kth_kernel");
   } else {
     // every finite score must be able to enter: start just above -FLT_MAX (faiss' heap neutral, never returned)
@@ -753,9 +895,9 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
   B200_LAUNCH_OK("stream_scores_kernel<topk>");
   if (g_time_kernel) B200_CUDA_OK(cudaEventRecord(g_ev1, st));
   const int P = next_pow2(k);
-  topk_sort_kernel<<<(unsigned)Q, FIN_THREADS, P * sizeof(uint64_t), st>>>(ea.tlists, ea.meta, k, P, row_offset,
-                                                                           out_scores, out_ids);
-  B200_LAUNCH_OK("topk_sort_kernel");
+  topk_final_kernel<NQ><<<(unsigned)Q, FIN_THREADS, P * sizeof(uint64_t), st>>>(
+      p.g, ea.tlists, ea.meta, ea.lists, ea.left, p.cap, k, P, row_offset, out_scores, out_ids);
+  B200_LAUNCH_OK("topk_final_kernel");
   return 0;
 }
 

@@ -15,9 +15,9 @@ def run(Nr, Q, D, k):
     e0.record(); KR.flat_ip_topk(cat, qry, k, workspace=ws); e1.record(); torch.cuda.synchronize()
     lib.b200rec_debug_topk_stats(buf, 1)
     ms = e0.elapsed_time(e1)
-    print(f"N={Nr} Q={Q} k={k} nq={os.environ.get('B200REC_TOPK_NQ')}: {ms:.2f} ms appends/query={buf[0]/Q:.0f} requests/query={buf[1]/Q:.1f} "
+    print(f"N={Nr} Q={Q} k={k}: {ms:.2f} ms appends/query={buf[0]/Q:.0f} requests/query={buf[1]/Q:.1f} "
           f"epi-wait Mcyc/CTA={buf[2]/148/1e6:.2f} helper-busy Mcyc/CTA={buf[3]/148/1e6:.2f} lock-miss={buf[4]} (kernel ~{ms*1.9:.1f} Mcyc)", flush=True)
-for nq in ("2", "1"):
-    os.environ["B200REC_TOPK_NQ"] = nq
-    run(1_000_000, 4096, 128, 100)
-    run(10_000_000, 4096, 128, 100)
+run(250_000, 4096, 128, 100)
+run(1_000_000, 4096, 128, 100)
+run(10_000_000, 4096, 128, 100)
+run(10_000_000, 64, 128, 100)
