@@ -21,16 +21,16 @@ struct LseEpi {
 
   static __device__ __forceinline__ void init_scratch(uint32_t*, int) {}
   static __device__ __forceinline__ void epilogue_exit(uint32_t*, int) {}
-  template <int NQ, int EPI_WARPS>
+  template <int SLOTS, int EPI_WARPS>
   static __device__ __forceinline__ void helper(const Args&, const StreamGeom&, int, int, uint32_t*) {}
 
-  template <int NQ, int QPT>
-  __device__ __forceinline__ void begin_segment(const Args&, const StreamGeom&, int, int, const int (&)[QPT], int,
-                                                uint32_t*) {
+  template <int SLOTS, int QPT>
+  __device__ __forceinline__ void begin_segment(const Args&, const StreamGeom&, int, int, const long long (&)[QPT],
+                                                const int (&)[QPT], int, uint32_t*) {
 #pragma unroll
     for (int a = 0; a < QPT; ++a) m[a] = -INFINITY, s[a] = 0.f;
   }
-  template <int NQ, int BN, int QPT>
+  template <int BN, int QPT>
   __device__ __forceinline__ void pre_tile(const Args&, const StreamGeom&, const int (&)[QPT], int, uint32_t*) {}
 
   template <int BN>
@@ -60,12 +60,12 @@ struct LseEpi {
     }
   }
 
-  template <int NQ, int QPT>
+  template <int SLOTS, int QPT>
   __device__ __forceinline__ void end_segment(const Args& ea, const StreamGeom& g, int sidx, int part,
                                               const int (&qslot)[QPT], int, uint32_t*, bool) {
 #pragma unroll
     for (int a = 0; a < QPT; ++a) {
-      const size_t o = ((size_t)sidx * g.max_parts + part) * (128 * NQ) + qslot[a];
+      const size_t o = ((size_t)sidx * g.max_parts + part) * SLOTS + qslot[a];
       ea.part_m[o] = m[a];
       ea.part_s[o] = s[a];
     }

@@ -8,6 +8,7 @@
 // Warp roles: 0 = TMA producer, 1 = tcgen05.mma issuer, 2 = TMEM allocator, 3 = idle, 4..11 = epilogue (consume TMEM),
 // 12..15 = helper warps owned by the epilogue policy (asynchronous candidate compaction for top-K; idle for LSE).
 #pragma once
+#include <cstdlib>
 #include "host_util.h"
 #include "tc_common.cuh"
 
@@ -34,6 +35,8 @@ struct StreamGeom {
   int max_parts;    // CTAs that can touch one supertile
   int stages;
   int smem_bytes;
+  int dbg_nofeed;   // development knob (2-CTA kernel): issue MMAs without waiting for / loading operands
+  int ks;           // 2-CTA kernel: 64-column atoms per ring stage
 };
 
 template <int NQ, int BN>
@@ -42,6 +45,8 @@ inline bool stream_geom(StreamGeom& g, long long N, int Q, int KB, int sms, int 
   g.N = N;
   g.Q = Q;
   g.KB = KB;
+  g.dbg_nofeed = 0;
+  g.ks = 1;
   const int rows_per_super = 128 * NQ;
   g.S = (Q + rows_per_super - 1) / rows_per_super;
   g.T = (N + BN - 1) / BN;
@@ -210,12 +215,17 @@ stream_scores_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       if (t1 > g.T) t1 = g.T;
       const int part = (int)blockIdx.x - geom_first_cta(g, s);
       int qslot[QPT];
+      long long qrow[QPT];
 #pragma unroll
-      for (int a = 0; a < QPT; ++a) qslot[a] = (half * QPT + a) * 128 + quarter * 32 + lane;
-      epi.template begin_segment<NQ, QPT>(ea, g, s, part, qslot, lane, scratch);
+      for (int a = 0; a < QPT; ++a) {
+        qslot[a] = (half * QPT + a) * 128 + quarter * 32 + lane;
+        const long long q = (long long)s * (128 * NQ) + qslot[a];
+        qrow[a] = q < g.Q ? q : -1;
+      }
+      epi.template begin_segment<128 * NQ, QPT>(ea, g, s, part, qrow, qslot, lane, scratch);
       for (long long t = t0; t < t1; ++t, ++tc) {
         const uint32_t buf = tc & 1;
-        epi.template pre_tile<NQ, BN, QPT>(ea, g, qslot, lane, scratch);
+        epi.template pre_tile<BN, QPT>(ea, g, qslot, lane, scratch);
         mbar_wait(&acc_full[buf], (tc >> 1) & 1);
         tc_fence_after();
 #pragma unroll
@@ -228,12 +238,12 @@ stream_scores_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
       }
-      epi.template end_segment<NQ, QPT>(ea, g, s, part, qslot, lane, scratch, /*last=*/(w + (t1 - t0)) >= w_end);
+      epi.template end_segment<128 * NQ, QPT>(ea, g, s, part, qslot, lane, scratch, /*last=*/(w + (t1 - t0)) >= w_end);
       w += t1 - t0;
     }
     Epi::epilogue_exit(scratch, lane);
   } else if (warp >= ST_HELP_WARP0) {
-    Epi::template helper<NQ, EPI_WARPS>(ea, g, warp - ST_HELP_WARP0, lane, scratch);
+    Epi::template helper<128 * NQ, EPI_WARPS>(ea, g, warp - ST_HELP_WARP0, lane, scratch);
   }
   tc_fence_before();
   __syncthreads();

@@ -1,0 +1,295 @@
+// 2-CTA variant of the streaming score kernel: a thread-block cluster of two CTAs (one SM pair) computes a
+// 256-query x 256-row score tile per step with tcgen05.mma.cta_group::2 (M = 256: each CTA supplies its 128 query
+// rows; N = 256: each CTA supplies 128 catalogue rows), so every operand byte staged in shared memory is used by two
+// SMs — the single-CTA 128x128 form is bound by shared-memory operand bandwidth (128 B/cycle at the nominal MMA rate),
+// this form needs 64 B/cycle.  Each CTA ends up with its 128 queries x 256 columns in its own TMEM (double buffered,
+// 2 x 256 = 512 columns) and runs the same epilogue policies as stream_scores.cuh.
+//
+// Roles per CTA: warp 0 TMA producer (its half of every tile), warp 1 MMA issuer (leader CTA only), warp 2 TMEM
+// allocator, warps 4..11 epilogue (thread = TMEM lane x 128-column half), warps 12..15 policy helper warps.
+// Barriers: TMA of both CTAs completes on the LEADER's full barrier; tcgen05.commit multicasts to both CTAs' empty /
+// accumulator-full barriers; epilogue warps of both CTAs arrive on the leader's accumulator-empty barrier.
+#pragma once
+#include "stream_scores.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load of this CTA's half; completion bytes are credited to the barrier at `bar_cluster_addr` (leader's)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// arrive (once all prior MMAs of this thread are complete) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+
+// Two shapes of the pair tile (NQ2 = query tiles per CTA):
+//   NQ2 = 1: 256 queries x 256 rows per step; an epilogue thread owns (TMEM lane, 128-column half)
+//   NQ2 = 2: 512 queries x 128 rows per step (two M=256,N=128 MMAs share every catalogue tile: half the L2 -> SM
+//            traffic per score, which is what bounds the NQ2 = 1 form at ~4.4 TB/s); a thread owns (lane, query tile)
+constexpr int S2_SLOTS = 256;  // epilogue slots per CTA in both shapes
+template <int NQ2> struct S2Shape {
+  static constexpr int ROWS = NQ2 == 1 ? 256 : 128;      // catalogue rows per step for the pair
+  static constexpr int QUERIES = 256 * NQ2;              // queries per supertile
+  static constexpr int STAGE_BYTES = (ROWS / 2) * 128;   // this CTA's half of one 64-column k-block
+  static constexpr int UMMA_N = ROWS;
+};
+
+// A ring stage holds g.ks 64-column atoms (ks = 2 when the row length allows it): one full-barrier wait and one
+// commit per 8 MMAs instead of per 4 — the barrier handshake on the single MMA-issuing thread is what separates the
+// fed pipeline (~1000 TFLOP/s) from the unfed issue rate (~1500 TFLOP/s).
+template <int NQ2>
+inline bool stream_geom2(StreamGeom& g, long long N, int Q, int KB, int sms, int scratch_bytes) {
+  constexpr int S2_QUERIES = S2Shape<NQ2>::QUERIES, S2_ROWS = S2Shape<NQ2>::ROWS, S2_STAGE_BYTES = S2Shape<NQ2>::STAGE_BYTES;
+  g.N = N;
+  g.Q = Q;
+  g.KB = KB;
+  g.dbg_nofeed = 0;
+  g.S = (Q + S2_QUERIES - 1) / S2_QUERIES;
+  g.T = (N + S2_ROWS - 1) / S2_ROWS;
+  g.total = g.S * g.T;
+  long long units = sms / 2;
+  if (units > g.total) units = g.total;
+  g.W = (g.total + units - 1) / units;
+  const long long used = (g.total + g.W - 1) / g.W;
+  g.grid = (int)(2 * used);
+  long long mp = (g.T + g.W - 1) / g.W + 1;
+  g.max_parts = (int)(mp < used ? mp : used);
+  const int q_bytes = NQ2 * KB * ST_QTILE_BYTES;
+  const int avail = ST_SMEM_LIMIT - 1024 - ST_BAR_BYTES - scratch_bytes - q_bytes;
+  const char* kse = getenv("B200REC_KS");
+  g.ks = (KB % 2 == 0) ? 2 : 1;
+  if (kse && atoi(kse) == 1) g.ks = 1;
+  int stages = avail / (S2_STAGE_BYTES * g.ks);
+  if (stages > ST_MAX_STAGES) stages = ST_MAX_STAGES;
+  g.stages = stages;
+  g.smem_bytes = 1024 + q_bytes + stages * S2_STAGE_BYTES * g.ks + ST_BAR_BYTES + scratch_bytes;
+  return stages >= 3;
+}
+
+template <int NQ2, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ST_THREADS, 1)
+stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
+                      const StreamGeom g, const typename Epi::Args ea) {
+  constexpr int EPI_WARPS = 8;
+  constexpr int S2_ROWS = S2Shape<NQ2>::ROWS, S2_QUERIES = S2Shape<NQ2>::QUERIES;
+  constexpr int S2_STAGE_BYTES = S2Shape<NQ2>::STAGE_BYTES, UMMA_N = S2Shape<NQ2>::UMMA_N;
+  constexpr int COLS = 128;  // accumulator columns one epilogue thread consumes per step
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_smem = smem;
+  uint8_t* ring = smem + NQ2 * g.KB * ST_QTILE_BYTES;
+  const int ks = g.ks;                       // 64-column atoms per ring stage
+  const int stage_bytes = S2_STAGE_BYTES * ks;
+  const int nsteps = g.KB / ks;              // ring stages per catalogue tile
+  uint8_t* tail = ring + g.stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + ST_MAX_STAGES;
+  uint64_t* acc_full = empty_bar + ST_MAX_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* q_full = acc_empty + 2;
+  uint64_t* q_empty = q_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 1);
+  uint32_t* scratch = reinterpret_cast<uint32_t*>(tail + ST_BAR_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const long long unit = blockIdx.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_x);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(&full_bar[s], 1);    // leader's: one arrive.expect_tx by the leader's producer, bytes from both CTAs
+      mbar_init(&empty_bar[s], 1);   // one multicast commit
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);                 // one multicast commit
+      mbar_init(&acc_empty[b], 2 * EPI_WARPS);    // leader's: epilogue warps of both CTAs
+    }
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc2(tmem_slot, 512);
+  if (warp == 3) Epi::init_scratch(scratch, lane);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA completion can target them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long w_begin = unit * g.W;
+  long long w_end = w_begin + g.W;
+  if (w_end > g.total) w_end = g.total;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (this CTA's halves)
+    if (lane == 0) {
+      const uint32_t q_full_leader = mapa_u32(smem_u32(q_full), 0);
+      uint32_t it = 0, seg = 0;
+      for (long long w = w_begin; w < w_end; ++seg) {
+        const int s = (int)(w / g.T);
+        const long long t0 = w - (long long)s * g.T;
+        long long t1 = t0 + (w_end - w);
+        if (t1 > g.T) t1 = g.T;
+        mbar_wait(q_empty, (seg & 1) ^ 1);
+        if (leader) mbar_arrive_expect_tx(q_full, 2 * NQ2 * g.KB * ST_QTILE_BYTES);
+        for (int qt = 0; qt < NQ2; ++qt)
+          for (int kb = 0; kb < g.KB; ++kb)
+            tma_load_2d_2sm(q_smem + (qt * g.KB + kb) * ST_QTILE_BYTES, &tmap_q, q_full_leader, kb * 64,
+                            s * S2_QUERIES + qt * 256 + (int)rank * 128);
+        for (long long t = t0; t < t1; ++t) {
+          for (int step = 0; step < nsteps; ++step, ++it) {
+            const int st = it % g.stages;
+            const uint32_t ph = (it / g.stages) & 1;
+            if (g.dbg_nofeed) continue;  // development knob: MMA issue rate without any operand traffic
+            mbar_wait(&empty_bar[st], ph ^ 1);
+            if (leader) mbar_arrive_expect_tx(&full_bar[st], 2 * stage_bytes);
+            const uint32_t bar = mapa_u32(smem_u32(&full_bar[st]), 0);
+            for (int a = 0; a < ks; ++a)
+              tma_load_2d_2sm(ring + st * stage_bytes + a * S2_STAGE_BYTES, &tmap_x, bar, (step * ks + a) * 64,
+                              (int)(t * S2_ROWS + rank * (S2_ROWS / 2)));
+          }
+        }
+        w += t1 - t0;
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    if (leader && lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(256, UMMA_N);
+      const uint32_t q_addr = smem_u32(q_smem);
+      const uint32_t ring_addr = smem_u32(ring);
+      uint32_t it = 0, seg = 0, tc = 0;
+      for (long long w = w_begin; w < w_end; ++seg) {
+        const int s = (int)(w / g.T);
+        const long long t0 = w - (long long)s * g.T;
+        long long t1 = t0 + (w_end - w);
+        if (t1 > g.T) t1 = g.T;
+        mbar_wait(q_full, seg & 1);
+        tc_fence_after();
+        for (long long t = t0; t < t1; ++t, ++tc) {
+          const uint32_t buf = tc & 1;
+          mbar_wait(&acc_empty[buf], ((tc >> 1) & 1) ^ 1);
+          tc_fence_after();
+          for (int step = 0; step < nsteps; ++step, ++it) {
+            const int st = it % g.stages;
+            const uint32_t ph = (it / g.stages) & 1;
+            if (!g.dbg_nofeed) {
+              mbar_wait(&full_bar[st], ph);
+              tc_fence_after();
+            }
+            for (int a = 0; a < ks; ++a) {
+              const int kb = step * ks + a;
+              const uint32_t b_addr = ring_addr + st * stage_bytes + a * S2_STAGE_BYTES;
+#pragma unroll
+              for (int qt = 0; qt < NQ2; ++qt) {
+                const uint32_t a_addr = q_addr + (qt * g.KB + kb) * ST_QTILE_BYTES;
+                const uint32_t d_addr = tmem_base + buf * 256 + qt * 128;  // NQ2 = 1: one 256-column accumulator
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_2sm(d_addr, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
+                                (kb | k) != 0);
+              }
+            }
+            if (!g.dbg_nofeed) umma_commit_2sm(&empty_bar[st]);
+          }
+          umma_commit_2sm(&acc_full[buf]);
+        }
+        umma_commit_2sm(q_empty);
+        w += t1 - t0;
+      }
+    }
+  } else if (warp >= ST_EPI_WARP0 && warp < ST_EPI_WARP0 + EPI_WARPS) {
+    // ------------------------------------------------------------------ epilogue: lane x 128-column half
+    const int ew = warp - ST_EPI_WARP0;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    Epi epi;
+    uint32_t tc = 0;
+    const uint32_t acc_empty_leader[2] = {mapa_u32(smem_u32(&acc_empty[0]), 0), mapa_u32(smem_u32(&acc_empty[1]), 0)};
+    for (long long w = w_begin; w < w_end;) {
+      const int s = (int)(w / g.T);
+      const long long t0 = w - (long long)s * g.T;
+      long long t1 = t0 + (w_end - w);
+      if (t1 > g.T) t1 = g.T;
+      const int part = (int)(unit - (s * g.T) / g.W);
+      // `half` selects the 128-column half of the one accumulator (NQ2 = 1) or the query tile (NQ2 = 2)
+      int qslot[1] = {half * 128 + quarter * 32 + lane};
+      const long long q = (long long)s * S2_QUERIES + (NQ2 == 2 ? half * 256 : 0) + rank * 128 + quarter * 32 + lane;
+      long long qrow[1] = {q < g.Q ? q : -1};
+      epi.template begin_segment<S2_SLOTS, 1>(ea, g, s, part, qrow, qslot, lane, scratch);
+      for (long long t = t0; t < t1; ++t, ++tc) {
+        const uint32_t buf = tc & 1;
+        epi.template pre_tile<COLS, 1>(ea, g, qslot, lane, scratch);
+        mbar_wait(&acc_full[buf], (tc >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * 256 + half * 128;
+        epi.template tile<COLS>(ea, g, 0, taddr, (unsigned long long)t * S2_ROWS + (NQ2 == 1 ? half * 128 : 0));
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_leader[buf]);
+      }
+      epi.template end_segment<S2_SLOTS, 1>(ea, g, s, part, qslot, lane, scratch, /*last=*/(w + (t1 - t0)) >= w_end);
+      w += t1 - t0;
+    }
+    Epi::epilogue_exit(scratch, lane);
+  } else if (warp >= ST_HELP_WARP0) {
+    Epi::template helper<S2_SLOTS, EPI_WARPS>(ea, g, warp - ST_HELP_WARP0, lane, scratch);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still signal it or read its operands
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+}  // namespace b200

@@ -15,6 +15,7 @@
 #include <cfloat>
 #include <cstdlib>
 #include "stream_scores.cuh"
+#include "stream_scores2.cuh"
 #include "../../include/b200rec.h"
 
 namespace b200 {
@@ -167,18 +168,19 @@ struct TopkEpi {
     while (*req != 0u) __nanosleep(40);
   }
 
-  template <int NQ, int QPT>
+  template <int SLOTS, int QPT>
   __device__ __forceinline__ void begin_segment(const Args& ea, const StreamGeom& g, int s, int part,
-                                                const int (&qslot)[QPT], int lane, uint32_t* scratch) {
+                                                const long long (&qrow)[QPT], const int (&qslot)[QPT], int lane,
+                                                uint32_t* scratch) {
 #pragma unroll
     for (int a = 0; a < QPT; ++a) {
-      const long long q = (long long)s * 128 * NQ + qslot[a];
-      const bool valid = (q < g.Q) && ea.debug != 1;
+      const long long q = qrow[a];
+      const bool valid = (q >= 0) && ea.debug != 1 && ea.debug != 3 && ea.debug != 5;
       qid[a] = valid ? (uint32_t)q : NO_QUERY;
       tau[a] = valid ? __ldcg(&ea.meta[q].tau) : INFINITY;
       cnt[a] = 0;
       active[a] = 0;
-      buf[a] = ea.lists + ((size_t)blockIdx.x * (128 * NQ) + qslot[a]) * (2 * (size_t)ea.cap);
+      buf[a] = ea.lists + ((size_t)blockIdx.x * SLOTS + qslot[a]) * (2 * (size_t)ea.cap);
       ex_lo[a] = nullptr;
       ex_n[a] = 0;
       if (ea.excl_indptr != nullptr && valid) {
@@ -192,7 +194,7 @@ struct TopkEpi {
   }
 
   // pick up thresholds raised by any feeder of this query; hand over a list that could overflow during the next tile
-  template <int NQ, int BN, int QPT>
+  template <int BN, int QPT>
   __device__ __forceinline__ void pre_tile(const Args& ea, const StreamGeom& g, const int (&qslot)[QPT], int lane,
                                            uint32_t* scratch) {
 #pragma unroll
@@ -236,6 +238,7 @@ struct TopkEpi {
   __device__ __forceinline__ void tile(const Args& ea, const StreamGeom& g, int a, uint32_t taddr,
                                        unsigned long long row0_ll) {
     const uint32_t row0 = (uint32_t)row0_ll;
+    if (ea.debug == 3) return;  // development knob: MMA + TMA pipeline only (TMEM never read)
 #pragma unroll 1
     for (int c = 0; c < BN; c += 64) {
       uint32_t gbits;
@@ -244,6 +247,10 @@ struct TopkEpi {
         tmem_ld_32x32(taddr + c, v0);
         tmem_ld_32x32(taddr + c + 32, v1);
         tmem_ld_wait();
+        if (ea.debug == 5) {  // development knob: TMEM read cost only
+          asm volatile("" ::"r"(v0[0]), "r"(v1[31]));
+          continue;
+        }
         gbits = group_bits(v0, tau[a]) | (group_bits(v1, tau[a]) << 4);
       }
       // rare path (warp-uniform loop because tcgen05.ld is warp-collective): re-read only the flagged 8-column groups
@@ -282,14 +289,14 @@ struct TopkEpi {
   // left in the active list (id << 31 | count); the final per-query kernel selects over T u leftovers with one CTA per
   // query, which replaces a serialised tail of ~38 K locked merges.  Earlier segments (CTAs spanning a supertile
   // boundary) hand the list to the helper warps as usual because their buffers are reused by the next segment.
-  template <int NQ, int QPT>
+  template <int SLOTS, int QPT>
   __device__ __forceinline__ void end_segment(const Args& ea, const StreamGeom& g, int s, int part,
                                               const int (&qslot)[QPT], int lane, uint32_t* scratch, bool last) {
     if (last) {
 #pragma unroll
       for (int a = 0; a < QPT; ++a) {
         wait_idle(scratch + 1536 + qslot[a]);
-        ea.left[(size_t)blockIdx.x * (128 * NQ) + qslot[a]] =
+        ea.left[(size_t)blockIdx.x * SLOTS + qslot[a]] =
             (qid[a] != NO_QUERY) ? ((active[a] << 31) | (uint32_t)cnt[a]) : 0u;
       }
       return;
@@ -346,10 +353,10 @@ struct TopkEpi {
     return ord_f32((uint32_t)(minkey >> 32));
   }
 
-  template <int NQ, int EPI_WARPS>
+  template <int SLOTS, int EPI_WARPS>
   static __device__ void helper(const Args& ea, const StreamGeom& g, int hw, int lane, uint32_t* scratch) {
-    constexpr int QS = 128 * NQ;
-    constexpr int PER_LANE = NQ;  // QS / (4 warps * 32 lanes)
+    constexpr int QS = SLOTS;
+    constexpr int PER_LANE = SLOTS / 128;  // SLOTS / (4 warps * 32 lanes)
     uint32_t* hist = scratch + hw * 256;
     volatile uint64_t* tau_pub = reinterpret_cast<volatile uint64_t*>(scratch + 1024);
     volatile uint32_t* reqs = scratch + 1536;
@@ -458,19 +465,16 @@ struct SampleMaxEpi {
 
   static __device__ __forceinline__ void init_scratch(uint32_t*, int) {}
   static __device__ __forceinline__ void epilogue_exit(uint32_t*, int) {}
-  template <int NQ, int EPI_WARPS>
+  template <int SLOTS, int EPI_WARPS>
   static __device__ __forceinline__ void helper(const Args&, const StreamGeom&, int, int, uint32_t*) {}
 
-  template <int NQ, int QPT>
-  __device__ __forceinline__ void begin_segment(const Args&, const StreamGeom& g, int s, int, const int (&qslot)[QPT],
-                                                int, uint32_t*) {
+  template <int SLOTS, int QPT>
+  __device__ __forceinline__ void begin_segment(const Args&, const StreamGeom&, int, int, const long long (&q)[QPT],
+                                                const int (&)[QPT], int, uint32_t*) {
 #pragma unroll
-    for (int a = 0; a < QPT; ++a) {
-      const long long q = (long long)s * 128 * NQ + qslot[a];
-      qrow[a] = q < g.Q ? q : -1;
-    }
+    for (int a = 0; a < QPT; ++a) qrow[a] = q[a];
   }
-  template <int NQ, int BN, int QPT>
+  template <int BN, int QPT>
   __device__ __forceinline__ void pre_tile(const Args&, const StreamGeom&, const int (&)[QPT], int, uint32_t*) {}
 
   template <int BN>
@@ -497,7 +501,7 @@ struct SampleMaxEpi {
     }
   }
 
-  template <int NQ, int QPT>
+  template <int SLOTS, int QPT>
   __device__ __forceinline__ void end_segment(const Args&, const StreamGeom&, int, int, const int (&)[QPT], int,
                                               uint32_t*, bool) {}
 };
@@ -616,9 +620,9 @@ struct MultiLoader {
   }
 };
 
-template <int NQ>
 __global__ void __launch_bounds__(FIN_THREADS)
-topk_final_kernel(const StreamGeom g, const uint64_t* __restrict__ tlists, const QMeta* __restrict__ meta,
+topk_final_kernel(const StreamGeom g, int v2, int qs /*queries per supertile*/, int slots /*per CTA*/,
+                  const uint64_t* __restrict__ tlists, const QMeta* __restrict__ meta,
                   const uint64_t* __restrict__ lists, const uint32_t* __restrict__ left, int cap, int k, int P,
                   int64_t row_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
   extern __shared__ uint64_t fin_smem[];
@@ -626,25 +630,29 @@ topk_final_kernel(const StreamGeom g, const uint64_t* __restrict__ tlists, const
   __shared__ int s_misc[8];
   __shared__ const uint64_t* s_ptr[FIN_MAX_SRC];
   __shared__ int s_off[FIN_MAX_SRC + 1];
-  constexpr int QS = 128 * NQ;
   const int q = blockIdx.x;
-  const int s = q / QS, slot = q - s * QS;
+  const int s = q / qs, inq = q - s * qs;
   if (threadIdx.x == 0) {
     int n = 0, ns = 0;
     s_ptr[ns] = tlists + (size_t)q * 2 * k + (size_t)meta[q].tsel * k;
     s_off[ns++] = n;
     n += (int)meta[q].tcount;
-    const int c0 = geom_first_cta(g, s), c1 = geom_last_cta(g, s);
-    for (int c = c0; c <= c1 && ns < FIN_MAX_SRC; ++c) {
-      long long wend = (long long)(c + 1) * g.W;
+    const int u0 = geom_first_cta(g, s), u1 = geom_last_cta(g, s);  // work units (CTAs, or CTA pairs when v2)
+    for (int u = u0; u <= u1; ++u) {
+      long long wend = (long long)(u + 1) * g.W;
       if (wend > g.total) wend = g.total;
-      if ((int)((wend - 1) / g.T) != s) continue;  // that CTA's last segment belongs to another supertile
-      const uint32_t l = left[(size_t)c * QS + slot];
-      const int cnt = (int)(l & 0x7FFFFFFFu);
-      if (cnt == 0) continue;
-      s_ptr[ns] = lists + ((size_t)c * QS + slot) * (2 * (size_t)cap) + ((l >> 31) ? cap : 0);
-      s_off[ns++] = n;
-      n += cnt;
+      if ((int)((wend - 1) / g.T) != s) continue;  // that unit's last segment belongs to another supertile
+      const int cta = v2 ? 2 * u + ((inq >> 7) & 1) : u;
+      const int nslot = v2 == 1 ? 2 : 1;
+      for (int h = 0; h < nslot && ns < FIN_MAX_SRC; ++h) {
+        const int slot = v2 == 1 ? h * 128 + (inq & 127) : (v2 == 2 ? (inq >> 8) * 128 + (inq & 127) : inq);
+        const uint32_t l = left[(size_t)cta * slots + slot];
+        const int cnt = (int)(l & 0x7FFFFFFFu);
+        if (cnt == 0) continue;
+        s_ptr[ns] = lists + ((size_t)cta * slots + slot) * (2 * (size_t)cap) + ((l >> 31) ? cap : 0);
+        s_off[ns++] = n;
+        n += cnt;
+      }
     }
     s_off[ns] = n;
     s_misc[5] = ns;
@@ -763,6 +771,7 @@ static int g_time_kernel = 0;
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 
 struct TopkPlan {
+  int v2;      // 1: CTA-pair kernel (stream_scores2.cuh), 0: single-CTA kernel
   int nq, bn;
   StreamGeom g;
   int cap;
@@ -789,9 +798,21 @@ static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k) {
   const int sms = num_sms();
   const int q128 = (int)((Q + 127) / 128);
   bool ok = false;
+  p.v2 = 0;
+  const char* v2e = getenv("B200REC_TOPK_V2");
+  const bool want_v2 = v2e ? atoi(v2e) != 0 : true;
+  const int v2shape = v2e ? atoi(v2e) : (q128 >= 3 ? 2 : 1);
+  if (want_v2 && q128 >= 2 && (sms % 2) == 0) {
+    if (v2shape == 2 && stream_geom2<2>(p.g, N, (int)Q, KB, sms, TopkEpi::SCRATCH_BYTES) && p.g.max_parts + 1 <= FIN_MAX_SRC) {
+      p.v2 = 2, p.nq = 2, p.bn = 128, ok = true;  // nq/bn describe one CTA's share: 256 slots, 128 columns per thread
+    } else if (stream_geom2<1>(p.g, N, (int)Q, KB, sms, TopkEpi::SCRATCH_BYTES) && 2 * p.g.max_parts + 1 <= FIN_MAX_SRC) {
+      p.v2 = 1, p.nq = 2, p.bn = 128, ok = true;
+    }
+  }
   const char* force = getenv("B200REC_TOPK_NQ");
   const int fnq = force ? atoi(force) : 0;
-  if (fnq == 2 && stream_geom<2, 128>(p.g, N, (int)Q, KB, sms, TopkEpi::SCRATCH_BYTES)) {
+  if (ok) {
+  } else if (fnq == 2 && stream_geom<2, 128>(p.g, N, (int)Q, KB, sms, TopkEpi::SCRATCH_BYTES)) {
     p.nq = 2, p.bn = 128, ok = true;
   } else if (fnq == 1 && stream_geom<1, 256>(p.g, N, (int)Q, KB, sms, TopkEpi::SCRATCH_BYTES)) {
     p.nq = 1, p.bn = 256, ok = true;
@@ -808,7 +829,7 @@ static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k) {
   p.tlists_bytes = (size_t)Q * 2 * (size_t)k * sizeof(uint64_t);
   p.meta_bytes = (((size_t)Q * sizeof(QMeta)) + 255) / 256 * 256;
   p.left_bytes = (((size_t)p.g.grid * 128 * p.nq * sizeof(uint32_t)) + 255) / 256 * 256;
-  if (p.g.max_parts + 1 > FIN_MAX_SRC) return fail("topk: too many catalogue slices per query (%d)", p.g.max_parts);
+  if (!p.v2 && p.g.max_parts + 1 > FIN_MAX_SRC) return fail("topk: too many catalogue slices per query (%d)", p.g.max_parts);
   // sampling pass: group maxima over m = N/32 strided rows (fast path only; see SampleMaxEpi)
   p.sample_m = p.sample_stride = 0;
   p.sample_bytes = 0;
@@ -827,7 +848,9 @@ static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k) {
       p.sample_gw = gw;
       p.sample_bytes = (size_t)Q * (m / gw) * sizeof(float);
       bool sok;
-      if (p.nq == 2) sok = stream_geom<2, 128>(p.gs, m, (int)Q, KB, sms, SampleMaxEpi::SCRATCH_BYTES);
+      if (p.v2 == 2) sok = stream_geom2<2>(p.gs, m, (int)Q, KB, sms, SampleMaxEpi::SCRATCH_BYTES);
+      else if (p.v2 == 1) sok = stream_geom2<1>(p.gs, m, (int)Q, KB, sms, SampleMaxEpi::SCRATCH_BYTES);
+      else if (p.nq == 2) sok = stream_geom<2, 128>(p.gs, m, (int)Q, KB, sms, SampleMaxEpi::SCRATCH_BYTES);
       else if (p.bn == 256) sok = stream_geom<1, 256>(p.gs, m, (int)Q, KB, sms, SampleMaxEpi::SCRATCH_BYTES);
       else sok = stream_geom<1, 64>(p.gs, m, (int)Q, KB, sms, SampleMaxEpi::SCRATCH_BYTES);
       if (!sok) p.sample_m = 0, p.sample_bytes = 0;
@@ -836,13 +859,14 @@ static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k) {
   return 0;
 }
 
-template <int NQ, int BN>
+template <int NQ, int BN, int V2>
 static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q,
                        int k, int64_t row_offset, const int64_t* excl_indptr, const int32_t* excl_rows,
                        float* out_scores, int64_t* out_ids, void* workspace, cudaStream_t st) {
   CUtensorMap tq, tx;
   if (make_tmap_bf16_2d(&tq, queries, (uint64_t)Q, (uint64_t)ld, (uint64_t)ld, 128)) return 1;
-  if (make_tmap_bf16_2d(&tx, catalogue, (uint64_t)N, (uint64_t)ld, (uint64_t)ld, BN)) return 1;
+  constexpr int XBOX = V2 == 1 ? 128 : (V2 == 2 ? 64 : BN);  // rows per TMA box (a CTA of a pair loads its half)
+  if (make_tmap_bf16_2d(&tx, catalogue, (uint64_t)N, (uint64_t)ld, (uint64_t)ld, XBOX)) return 1;
   TopkEpi::Args ea;
   ea.lists = reinterpret_cast<uint64_t*>(workspace);
   ea.tlists = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(workspace) + p.lists_bytes);
@@ -855,7 +879,9 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
   ea.cap = p.cap;
   ea.flush = getenv("B200REC_TOPK_FLUSH") ? atoi(getenv("B200REC_TOPK_FLUSH")) : 32;
   ea.debug = getenv("B200REC_TOPK_DEBUG") ? atoi(getenv("B200REC_TOPK_DEBUG")) : 0;
-  auto kern = stream_scores_kernel<NQ, BN, TopkEpi>;
+  void (*kern)(const CUtensorMap, const CUtensorMap, const StreamGeom, const TopkEpi::Args);
+  if constexpr (V2 != 0) kern = stream_scores2_kernel<(V2 == 2 ? 2 : 1), TopkEpi>;
+  else kern = stream_scores_kernel<NQ, BN, TopkEpi>;
   static int smem_set = 0;
   if (smem_set < p.g.smem_bytes) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_LIMIT));
@@ -864,12 +890,14 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
   if (p.sample_m > 0 && excl_indptr == nullptr) {
     float* S = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + p.lists_bytes + p.tlists_bytes + p.meta_bytes + p.left_bytes);
     CUtensorMap ts;  // row i of this map is catalogue row i * stride
-    if (make_tmap_bf16_2d(&ts, catalogue, (uint64_t)p.sample_m, (uint64_t)ld, (uint64_t)(ld * p.sample_stride), BN)) return 1;
+    if (make_tmap_bf16_2d(&ts, catalogue, (uint64_t)p.sample_m, (uint64_t)ld, (uint64_t)(ld * p.sample_stride), XBOX)) return 1;
     SampleMaxEpi::Args sa;
     sa.out = S;
     sa.ngroups = (int)(p.sample_m / p.sample_gw);
     sa.gw = p.sample_gw;
-    auto skern = stream_scores_kernel<NQ, BN, SampleMaxEpi>;
+    void (*skern)(const CUtensorMap, const CUtensorMap, const StreamGeom, const SampleMaxEpi::Args);
+    if constexpr (V2 != 0) skern = stream_scores2_kernel<(V2 == 2 ? 2 : 1), SampleMaxEpi>;
+    else skern = stream_scores_kernel<NQ, BN, SampleMaxEpi>;
     static bool sattr = false;
     if (!sattr) {
       B200_CUDA_OK(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_LIMIT));
@@ -891,12 +919,16 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
     }
     B200_CUDA_OK(cudaEventRecord(g_ev0, st));
   }
-  kern<<<p.g.grid, ST_THREADS, p.g.smem_bytes, st>>>(tq, tx, p.g, ea);
+  StreamGeom gl = p.g;
+  gl.dbg_nofeed = (ea.debug == 4) ? 1 : 0;
+  if (ea.debug == 4) ea.debug = 3;
+  kern<<<gl.grid, ST_THREADS, gl.smem_bytes, st>>>(tq, tx, gl, ea);
   B200_LAUNCH_OK("stream_scores_kernel<topk>");
   if (g_time_kernel) B200_CUDA_OK(cudaEventRecord(g_ev1, st));
   const int P = next_pow2(k);
-  topk_final_kernel<NQ><<<(unsigned)Q, FIN_THREADS, P * sizeof(uint64_t), st>>>(
-      p.g, ea.tlists, ea.meta, ea.lists, ea.left, p.cap, k, P, row_offset, out_scores, out_ids);
+  topk_final_kernel<<<(unsigned)Q, FIN_THREADS, P * sizeof(uint64_t), st>>>(
+      p.g, V2, V2 == 2 ? 512 : (V2 == 1 ? 256 : 128 * NQ), V2 ? S2_SLOTS : 128 * NQ, ea.tlists, ea.meta, ea.lists, ea.left, p.cap,
+      k, P, row_offset, out_scores, out_ids);
   B200_LAUNCH_OK("topk_final_kernel");
   return 0;
 }
@@ -943,9 +975,11 @@ extern "C" int b200rec_flat_ip_topk(const void* catalogue, int64_t N, int64_t ld
   if (workspace_bytes < p.total()) return fail("topk: workspace too small (%zu < %zu)", workspace_bytes, p.total());
   if ((exclude_indptr == nullptr) != (exclude_rows == nullptr)) return fail("topk: exclusion CSR needs both arrays");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (p.nq == 2) return launch_topk<2, 128>(p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st);
-  if (p.bn == 256) return launch_topk<1, 256>(p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st);
-  return launch_topk<1, 64>(p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st);
+  if (p.v2 == 2) return launch_topk<2, 128, 2>(p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st);
+  if (p.v2 == 1) return launch_topk<2, 128, 1>(p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st);
+  if (p.nq == 2) return launch_topk<2, 128, 0>(p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st);
+  if (p.bn == 256) return launch_topk<1, 256, 0>(p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st);
+  return launch_topk<1, 64, 0>(p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st);
 }
 
 extern "C" int b200rec_topk_merge(const float* scores, const int64_t* ids, int parts, int64_t Q, int k_in, int k_out,
