@@ -60,13 +60,24 @@ int b200rec_gemm_bf16_tn(const void* A, int64_t lda, int64_t M, const void* B, i
  * exclude_* (nullable): CSR of per-query LOCAL rows (ascending) that must never be returned (the -inf mask of
  * evaluate_model.py:225-228).  k <= 2048, N < 2^32 - 1 per shard. */
 size_t b200rec_topk_workspace_bytes(int64_t N, int64_t ld, int64_t Q, int k);
+/* tau_init (nullable, device float[Q]): caller-supplied lower bounds of each query's FINAL k-th score; candidates below
+ * them are never considered (a shard may then return fewer than k rows), and the internal sampling pass is skipped. */
 int b200rec_flat_ip_topk(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k,
                          int64_t row_offset, const int64_t* exclude_indptr, const int32_t* exclude_rows,
-                         float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes, void* stream);
-/* k-way merge of `parts` candidate lists laid out [parts][Q][k_in] (id < 0 = empty, ids < 2^32) into the global top
- * k_out under the same order: the exchange step after the all-gather of per-GPU results. */
+                         const float* tau_init, float* out_scores, int64_t* out_ids, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* Sampling pass alone: out_vals [Q,k] = the k largest group maxima (distinct sampled rows) of every query, descending.
+ * Row-sharded search exchanges these (all-gather) and starts every shard from the k-th best of the union.
+ * b200rec_topk_has_sample says whether this shape runs a sampling pass at all (small shards do not). */
+int b200rec_topk_sample(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k,
+                        float* out_vals, void* workspace, size_t workspace_bytes, void* stream);
+int b200rec_topk_has_sample(int64_t N, int64_t ld, int64_t Q, int k);
+/* k-way merge of `parts` candidate lists [parts][Q][k_in] (id < 0 = empty, ids < 2^32) into the global top k_out under
+ * the same order: the exchange step after the all-gather of per-GPU results.  *_part_stride = element distance
+ * between consecutive parts (0 = dense, Q*k_in); non-dense strides let one all-gather carry scores and ids together. */
 int b200rec_topk_merge(const float* scores, const int64_t* ids, int parts, int64_t Q, int k_in, int k_out,
-                       float* out_scores, int64_t* out_ids, void* stream);
+                       int64_t scores_part_stride, int64_t ids_part_stride, float* out_scores, int64_t* out_ids,
+                       void* stream);
 
 /* ---------------------------------------------------------------- embedding bags (csrc/embedding.cu)
  * out[b, 0:num_cols] = numerical[b, :]; out[b, col_off[f] : +width[f]] = table_f[idx_f[b], :width[f]].

@@ -666,6 +666,43 @@ topk_final_kernel(const StreamGeom g, int v2, int qs /*queries per supertile*/, 
   write_result(fin_smem, k, row_offset, out_scores + (size_t)q * k, out_ids + (size_t)q * k);
 }
 
+// per-query k largest group maxima of the sampling pass (descending; -FLT_MAX padding): what shards exchange so that
+// every GPU starts from the k-th best of the UNION of all samples
+struct FloatRowLoader {
+  const float* row;
+  __device__ __forceinline__ uint64_t operator()(int i) const {
+    return (static_cast<uint64_t>(f32_ord(__ldcg(row + i))) << 32) | static_cast<uint64_t>(~(uint32_t)i);
+  }
+};
+__global__ void __launch_bounds__(FIN_THREADS)
+sample_topk_kernel(const float* __restrict__ S, int m, int k, int P, float* __restrict__ out_vals) {
+  extern __shared__ uint64_t fin_smem[];
+  __shared__ uint32_t hist[256];
+  __shared__ int s_misc[8];
+  const int q = blockIdx.x;
+  FloatRowLoader ld{S + (size_t)q * m};
+  block_select_sort(ld, m, k, fin_smem, P, hist, s_misc);
+  for (int i = threadIdx.x; i < k; i += FIN_THREADS) {
+    const uint64_t key = fin_smem[i];
+    out_vals[(size_t)q * k + i] = key == 0ull ? -FLT_MAX : ord_f32((uint32_t)(key >> 32));
+  }
+}
+
+// thresholds supplied by the caller (a valid lower bound of each query's final k-th score), with the same 64-ulp slack
+__global__ void topk_init_from_kernel(QMeta* meta, int Q, const float* __restrict__ tau_init) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < Q) {
+    uint32_t key = f32_ord(tau_init[q]);
+    key = key > 64u ? key - 64u : 0u;
+    QMeta m;
+    m.lock = 0u;
+    m.tcount = 0u;
+    m.tsel = 0u;
+    m.tau = fmaxf(ord_f32(key), nextafterf(-FLT_MAX, 0.f));
+    meta[q] = m;
+  }
+}
+
 __global__ void topk_init_kernel(QMeta* meta, int Q, float tau0) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q < Q) {
@@ -681,19 +718,19 @@ __global__ void topk_init_kernel(QMeta* meta, int Q, float tau0) {
 struct ListLoader {
   const float* scores;
   const int64_t* ids;
-  size_t part_stride;  // Q * k_in
+  size_t s_stride, i_stride;  // element distance between consecutive parts (Q * k_in when the arrays are dense)
   int k_in;
   __device__ __forceinline__ uint64_t operator()(int i) const {
     const int p = i / k_in, j = i - p * k_in;
-    const size_t off = (size_t)p * part_stride + j;
-    const int64_t id = ids[off];
-    return id < 0 ? 0ull : make_key(scores[off], (uint32_t)id);
+    const int64_t id = ids[(size_t)p * i_stride + j];
+    return id < 0 ? 0ull : make_key(scores[(size_t)p * s_stride + j], (uint32_t)id);
   }
 };
 
 __global__ void __launch_bounds__(FIN_THREADS)
 topk_merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids, int parts, long long Q, int k_in,
-                  int k_out, int P, float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+                  int k_out, int P, long long s_stride, long long i_stride, float* __restrict__ out_scores,
+                  int64_t* __restrict__ out_ids) {
   extern __shared__ uint64_t fin_smem[];
   __shared__ uint32_t hist[256];
   __shared__ int s_misc[8];
@@ -701,7 +738,8 @@ topk_merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
   ListLoader ld;
   ld.scores = scores + (size_t)q * k_in;
   ld.ids = ids + (size_t)q * k_in;
-  ld.part_stride = (size_t)Q * k_in;
+  ld.s_stride = (size_t)s_stride;
+  ld.i_stride = (size_t)i_stride;
   ld.k_in = k_in;
   block_select_sort(ld, parts * k_in, k_out, fin_smem, P, hist, s_misc);
   write_result(fin_smem, k_out, 0, out_scores + (size_t)q * k_out, out_ids + (size_t)q * k_out);
@@ -862,7 +900,8 @@ static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k) {
 template <int NQ, int BN, int V2>
 static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q,
                        int k, int64_t row_offset, const int64_t* excl_indptr, const int32_t* excl_rows,
-                       float* out_scores, int64_t* out_ids, void* workspace, cudaStream_t st) {
+                       float* out_scores, int64_t* out_ids, void* workspace, cudaStream_t st,
+                       const float* tau_init, float* sample_vals_out) {
   CUtensorMap tq, tx;
   if (make_tmap_bf16_2d(&tq, queries, (uint64_t)Q, (uint64_t)ld, (uint64_t)ld, 128)) return 1;
   constexpr int XBOX = V2 == 1 ? 128 : (V2 == 2 ? 64 : BN);  // rows per TMA box (a CTA of a pair loads its half)
@@ -887,7 +926,10 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_LIMIT));
     smem_set = ST_SMEM_LIMIT;
   }
-  if (p.sample_m > 0 && excl_indptr == nullptr) {
+  if (tau_init != nullptr) {
+    topk_init_from_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(ea.meta, (int)Q, tau_init);
+    B200_LAUNCH_OK("topk_init_from_kernel");
+  } else if (p.sample_m > 0 && excl_indptr == nullptr) {
     float* S = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + p.lists_bytes + p.tlists_bytes + p.meta_bytes + p.left_bytes);
     CUtensorMap ts;  // row i of this map is catalogue row i * stride
     if (make_tmap_bf16_2d(&ts, catalogue, (uint64_t)p.sample_m, (uint64_t)ld, (uint64_t)(ld * p.sample_stride), XBOX)) return 1;
@@ -905,8 +947,16 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
     }
     skern<<<p.gs.grid, ST_THREADS, p.gs.smem_bytes, st>>>(tq, ts, p.gs, sa);
     B200_LAUNCH_OK("stream_scores_kernel<sample>");
+    if (sample_vals_out != nullptr) {  // sampling only: hand the k best group maxima per query to the caller
+      const int P = next_pow2(k);
+      sample_topk_kernel<<<(unsigned)Q, FIN_THREADS, P * sizeof(uint64_t), st>>>(S, sa.ngroups, k, P, sample_vals_out);
+      B200_LAUNCH_OK("sample_topk_kernel");
+      return 0;
+    }
     sample_kth_kernel<<<(unsigned)Q, FIN_THREADS, 0, st>>>(S, sa.ngroups, k, ea.meta);
     B200_LAUNCH_OK("sample_kth_kernel");
+  } else if (sample_vals_out != nullptr) {
+    return fail("topk_sample: no sampling pass for this shape (catalogue too small or exclusion lists given)");
   } else {
     // every finite score must be able to enter: start just above -FLT_MAX (faiss' heap neutral, never returned)
     topk_init_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(ea.meta, (int)Q, nextafterf(-FLT_MAX, 0.f));
@@ -964,26 +1014,51 @@ extern "C" size_t b200rec_topk_workspace_bytes(int64_t N, int64_t ld, int64_t Q,
   return p.total();
 }
 
-extern "C" int b200rec_flat_ip_topk(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k,
-                                    int64_t row_offset, const int64_t* exclude_indptr, const int32_t* exclude_rows,
-                                    float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes,
-                                    void* stream) {
+static int topk_dispatch(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k,
+                         int64_t row_offset, const int64_t* exclude_indptr, const int32_t* exclude_rows,
+                         const float* tau_init, float* out_scores, int64_t* out_ids, float* sample_vals_out,
+                         void* workspace, size_t workspace_bytes, void* stream) {
   using namespace b200;
-  if (!catalogue || !queries || !out_scores || !out_ids || !workspace) return fail("topk: null pointer");
   TopkPlan p;
   if (plan_topk(p, N, ld, Q, k)) return 1;
   if (workspace_bytes < p.total()) return fail("topk: workspace too small (%zu < %zu)", workspace_bytes, p.total());
   if ((exclude_indptr == nullptr) != (exclude_rows == nullptr)) return fail("topk: exclusion CSR needs both arrays");
+  if (sample_vals_out != nullptr && p.sample_m == 0) return fail("topk_sample: catalogue too small for a sampling pass");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (p.v2 == 2) return launch_topk<2, 128, 2>(p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st);
-  if (p.v2 == 1) return launch_topk<2, 128, 1>(p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st);
-  if (p.nq == 2) return launch_topk<2, 128, 0>(p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st);
-  if (p.bn == 256) return launch_topk<1, 256, 0>(p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st);
-  return launch_topk<1, 64, 0>(p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st);
+#define B200_TOPK_ARGS p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st, tau_init, sample_vals_out
+  if (p.v2 == 2) return launch_topk<2, 128, 2>(B200_TOPK_ARGS);
+  if (p.v2 == 1) return launch_topk<2, 128, 1>(B200_TOPK_ARGS);
+  if (p.nq == 2) return launch_topk<2, 128, 0>(B200_TOPK_ARGS);
+  if (p.bn == 256) return launch_topk<1, 256, 0>(B200_TOPK_ARGS);
+  return launch_topk<1, 64, 0>(B200_TOPK_ARGS);
+#undef B200_TOPK_ARGS
+}
+
+extern "C" int b200rec_flat_ip_topk(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k,
+                                    int64_t row_offset, const int64_t* exclude_indptr, const int32_t* exclude_rows,
+                                    const float* tau_init, float* out_scores, int64_t* out_ids, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  if (!catalogue || !queries || !out_scores || !out_ids || !workspace) return b200::fail("topk: null pointer");
+  return topk_dispatch(catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, tau_init, out_scores,
+                       out_ids, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int b200rec_topk_sample(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k,
+                                   float* out_vals, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!catalogue || !queries || !out_vals || !workspace) return b200::fail("topk_sample: null pointer");
+  return topk_dispatch(catalogue, N, ld, queries, Q, k, 0, nullptr, nullptr, nullptr, nullptr, nullptr, out_vals, workspace,
+                       workspace_bytes, stream);
+}
+
+extern "C" int b200rec_topk_has_sample(int64_t N, int64_t ld, int64_t Q, int k) {
+  b200::TopkPlan p;
+  if (b200::plan_topk(p, N, ld, Q, k)) return 0;
+  return p.sample_m > 0 ? 1 : 0;
 }
 
 extern "C" int b200rec_topk_merge(const float* scores, const int64_t* ids, int parts, int64_t Q, int k_in, int k_out,
-                                  float* out_scores, int64_t* out_ids, void* stream) {
+                                  int64_t scores_part_stride, int64_t ids_part_stride, float* out_scores,
+                                  int64_t* out_ids, void* stream) {
   using namespace b200;
   if (!scores || !ids || !out_scores || !out_ids) return fail("topk_merge: null pointer");
   if (parts < 1 || Q < 1 || k_in < 1) return fail("topk_merge: empty input");
@@ -991,7 +1066,9 @@ extern "C" int b200rec_topk_merge(const float* scores, const int64_t* ids, int p
   if ((int64_t)parts * k_in > INT32_MAX) return fail("topk_merge: too many candidates per query");
   const int P = next_pow2(k_out);
   topk_merge_kernel<<<(unsigned)Q, FIN_THREADS, P * sizeof(uint64_t), reinterpret_cast<cudaStream_t>(stream)>>>(
-      scores, ids, parts, (long long)Q, k_in, k_out, P, out_scores, out_ids);
+      scores, ids, parts, (long long)Q, k_in, k_out, P,
+      (long long)(scores_part_stride > 0 ? scores_part_stride : Q * k_in),
+      (long long)(ids_part_stride > 0 ? ids_part_stride : Q * k_in), out_scores, out_ids);
   B200_LAUNCH_OK("topk_merge_kernel");
   return 0;
 }

@@ -31,33 +31,83 @@ def _world() -> Tuple[int, int]:
 class ShardedFlatIndex:
     """Row-sharded exact inner-product index: `search` returns the GLOBAL top-k on every rank.
 
-    local_search(q, k) -> (scores [Q,k] fp32, ids [Q,k] int64 with GLOBAL row ids, -1 padding)
+    local_search(q, k, tau=None) -> (scores [Q,k] fp32, ids [Q,k] int64 with GLOBAL row ids, -1 padding)
     merge(scores [P,Q,k], ids [P,Q,k], k) -> (scores [Q,k], ids [Q,k])   order: score desc, id asc
+    local_sample(q, k) -> [Q,k] scores of k DISTINCT local rows per query, or None (optional).  When given, shards
+        all-gather these and every shard starts from the k-th best of the union: a lower bound of the GLOBAL k-th
+        score, so each GPU only collects candidates that can still reach the global top-k.
     """
 
-    def __init__(self, local_search: Callable, merge: Callable, group=None):
+    def __init__(self, local_search: Callable, merge: Callable, group=None, local_sample: Optional[Callable] = None):
         self.local_search = local_search
         self.merge = merge
         self.group = group
+        self.local_sample = local_sample
+        self.packed_exchange = False   # set by from_device_index: needs a local_search that writes into `out`
+        self._ids_cache = {}
 
     @classmethod
     def from_device_index(cls, index, group=None) -> "ShardedFlatIndex":
         from . import kernels as K
 
-        def local(q_op, k):
-            return index.search_device(q_op, k)
+        def local(q_op, k, tau=None, out=None):
+            return index.search_device(q_op, k, tau_init=tau, out=out)
 
         def merge(s, i, k):
             return K.topk_merge(s, i, k)
 
-        return cls(local, merge, group)
+        def sample(q_op, k):
+            return index.sample_device(q_op, k) if index.has_sample_pass(q_op.shape[0], k) else None
+
+        obj = cls(local, merge, group, sample)
+        obj.packed_exchange = True
+        return obj
+
+    def _shared_thresholds(self, queries, k: int, world: int):
+        """k-th best of the union of every shard's sample: [Q] lower bounds of the global k-th score (or None)."""
+        vals = self.local_sample(queries, k)
+        shape_key = ("use", int(queries.shape[0]), k)
+        if shape_key not in self._ids_cache:
+            # every shard must take the same branch: agree once per (batch, k) shape (one host sync, then cached)
+            flag = torch.tensor([0 if vals is None else 1], dtype=torch.int32)
+            if dist.get_backend(self.group) == "nccl":
+                flag = flag.cuda()
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            self._ids_cache[shape_key] = int(flag.item()) == 1
+        if not self._ids_cache[shape_key] or vals is None:
+            return None
+        q = vals.shape[0]
+        allv = torch.empty((world * q, k), dtype=vals.dtype, device=vals.device)
+        dist.all_gather_into_tensor(allv, vals.contiguous(), group=self.group)
+        key = (world, q, k, str(vals.device))
+        if key not in self._ids_cache:  # any distinct ids will do: only the merged scores are used
+            self._ids_cache[key] = torch.arange(world * q * k, dtype=torch.int64, device=vals.device).view(world, q, k)
+        top, _ = self.merge(allv.view(world, q, k), self._ids_cache[key], k)
+        return top[:, k - 1].contiguous()
 
     def search(self, queries, k: int):
         world, _ = _world()
-        s, i = self.local_search(queries, k)
         if world == 1:
-            return s, i
-        q = s.shape[0]
+            return self.local_search(queries, k)
+        tau = self._shared_thresholds(queries, k, world) if self.local_sample is not None else None
+        q = int(queries.shape[0])
+        if self.packed_exchange and (q * k) % 2 == 0:
+            # one all-gather carries scores and ids: each rank's chunk is [q*k fp32 | q*k int64]
+            dev = queries.device
+            key = ("buf", q, k, str(dev))
+            if key not in self._ids_cache:
+                self._ids_cache[key] = (torch.empty((12 * q * k,), dtype=torch.uint8, device=dev),
+                                        torch.empty((world * 12 * q * k,), dtype=torch.uint8, device=dev))
+            mine, everyone = self._ids_cache[key]
+            s_view = mine[: 4 * q * k].view(torch.float32).view(q, k)
+            i_view = mine[4 * q * k:].view(torch.int64).view(q, k)
+            self.local_search(queries, k, tau, (s_view, i_view))
+            dist.all_gather_into_tensor(everyone, mine, group=self.group)
+            chunks = everyone.view(world, 12 * q * k)
+            gs = chunks[:, : 4 * q * k].view(torch.float32).view(world, q, k)
+            gi = chunks[:, 4 * q * k:].view(torch.int64).view(world, q, k)
+            return self.merge(gs, gi, k)
+        s, i = self.local_search(queries, k, tau) if tau is not None else self.local_search(queries, k)
         gs = torch.empty((world * q, s.shape[1]), dtype=s.dtype, device=s.device)
         gi = torch.empty((world * q, i.shape[1]), dtype=i.dtype, device=i.device)
         dist.all_gather_into_tensor(gs, s.contiguous(), group=self.group)

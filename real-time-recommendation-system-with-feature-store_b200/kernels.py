@@ -81,7 +81,8 @@ def topk_workspace_bytes(n: int, ld: int, q: int, k: int) -> int:
 
 def flat_ip_topk(catalogue: torch.Tensor, queries: torch.Tensor, k: int, row_offset: int = 0,
                  exclude_indptr: Optional[torch.Tensor] = None, exclude_rows: Optional[torch.Tensor] = None,
-                 workspace: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                 workspace: Optional[torch.Tensor] = None, tau_init: Optional[torch.Tensor] = None,
+                 out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """catalogue bf16 [N, ld], queries bf16 [Q, ld] (ld multiple of 64) -> (scores fp32 [Q,k] desc, ids int64 [Q,k])."""
     assert catalogue.dtype == BF16 and queries.dtype == BF16
     assert catalogue.stride(1) == 1 and queries.stride(1) == 1 and catalogue.stride(0) == queries.stride(0)
@@ -92,22 +93,40 @@ def flat_ip_topk(catalogue: torch.Tensor, queries: torch.Tensor, k: int, row_off
         raise RuntimeError(f"b200rec flat_ip_topk: {N.last_error()}")
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty((need,), dtype=torch.uint8, device=catalogue.device)
-    scores = torch.empty((q, k), dtype=torch.float32, device=catalogue.device)
-    ids = torch.empty((q, k), dtype=torch.int64, device=catalogue.device)
+    if out is None:
+        scores = torch.empty((q, k), dtype=torch.float32, device=catalogue.device)
+        ids = torch.empty((q, k), dtype=torch.int64, device=catalogue.device)
+    else:
+        scores, ids = out
     N.check(N.lib().b200rec_flat_ip_topk(N.ptr(catalogue), n, ld, N.ptr(queries), q, k, row_offset,
-                                         N.ptr(exclude_indptr), N.ptr(exclude_rows), N.ptr(scores), N.ptr(ids),
-                                         N.ptr(workspace), workspace.numel(), N.stream()), "flat_ip_topk")
+                                         N.ptr(exclude_indptr), N.ptr(exclude_rows), N.ptr(tau_init), N.ptr(scores),
+                                         N.ptr(ids), N.ptr(workspace), workspace.numel(), N.stream()), "flat_ip_topk")
     return scores, ids
 
 
+def topk_has_sample(n: int, ld: int, q: int, k: int) -> bool:
+    return bool(N.lib().b200rec_topk_has_sample(n, ld, q, k))
+
+
+def topk_sample(catalogue: torch.Tensor, queries: torch.Tensor, k: int, workspace: torch.Tensor) -> torch.Tensor:
+    """Sampling pass only: [Q,k] largest group maxima per query (what row shards exchange before the main pass)."""
+    n, ld, q = catalogue.shape[0], catalogue.stride(0), queries.shape[0]
+    vals = torch.empty((q, k), dtype=torch.float32, device=catalogue.device)
+    N.check(N.lib().b200rec_topk_sample(N.ptr(catalogue), n, ld, N.ptr(queries), q, k, N.ptr(vals), N.ptr(workspace),
+                                        workspace.numel(), N.stream()), "topk_sample")
+    return vals
+
+
 def topk_merge(scores: torch.Tensor, ids: torch.Tensor, k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """scores/ids [parts, Q, k_in] -> global top k_out per query (score desc, id asc; id < 0 = padding)."""
-    assert scores.dim() == 3 and scores.shape == ids.shape and scores.is_contiguous() and ids.is_contiguous()
+    """scores/ids [parts, Q, k_in] -> global top k_out per query (score desc, id asc; id < 0 = padding).  The part
+    dimension may be strided (scores and ids interleaved in one all-gathered buffer)."""
+    assert scores.dim() == 3 and scores.shape == ids.shape
     parts, q, k_in = scores.shape
+    assert scores.stride(2) == 1 and scores.stride(1) == k_in and ids.stride(2) == 1 and ids.stride(1) == k_in
     out_s = torch.empty((q, k_out), dtype=torch.float32, device=scores.device)
     out_i = torch.empty((q, k_out), dtype=torch.int64, device=scores.device)
-    N.check(N.lib().b200rec_topk_merge(N.ptr(scores), N.ptr(ids), parts, q, k_in, k_out, N.ptr(out_s), N.ptr(out_i),
-                                       N.stream()), "topk_merge")
+    N.check(N.lib().b200rec_topk_merge(N.ptr(scores), N.ptr(ids), parts, q, k_in, k_out, scores.stride(0),
+                                       ids.stride(0), N.ptr(out_s), N.ptr(out_i), N.stream()), "topk_merge")
     return out_s, out_i
 
 

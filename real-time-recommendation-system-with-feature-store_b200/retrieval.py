@@ -138,19 +138,34 @@ class FlatIPDeviceIndex:
                                      terms=self.terms, side=0)
         return qop
 
-    def search_device(self, q_op: torch.Tensor, k: int, exclude_indptr=None, exclude_rows=None):
-        """q_op: bf16 operand [nq, ld] on the device -> (D, I) device tensors."""
-        nq = q_op.shape[0]
-        if self.ntotal == 0:
-            return (torch.full((nq, k), -FLT_MAX, dtype=torch.float32, device=self.device),
-                    torch.full((nq, k), -1, dtype=torch.int64, device=self.device))
+    def _workspace(self, nq: int, k: int) -> torch.Tensor:
         need = K.topk_workspace_bytes(self.ntotal, self.ld, nq, k)
         if need == 0:
             raise RuntimeError(f"b200rec flat_ip_topk: {K.N.last_error()}")
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def has_sample_pass(self, nq: int, k: int) -> bool:
+        return self.ntotal > 0 and K.topk_has_sample(self.ntotal, self.ld, nq, k)
+
+    def sample_device(self, q_op: torch.Tensor, k: int) -> torch.Tensor:
+        """Sampling pass only: the k largest group maxima per query [nq, k] (exchanged between row shards)."""
+        return K.topk_sample(self._cat[: self.ntotal], q_op, k, self._workspace(q_op.shape[0], k))
+
+    def search_device(self, q_op: torch.Tensor, k: int, exclude_indptr=None, exclude_rows=None, tau_init=None,
+                      out=None):
+        """q_op: bf16 operand [nq, ld] on the device -> (D, I) device tensors (written into `out` when given)."""
+        nq = q_op.shape[0]
+        if self.ntotal == 0:
+            if out is not None:
+                out[0].fill_(-FLT_MAX)
+                out[1].fill_(-1)
+                return out
+            return (torch.full((nq, k), -FLT_MAX, dtype=torch.float32, device=self.device),
+                    torch.full((nq, k), -1, dtype=torch.int64, device=self.device))
         return K.flat_ip_topk(self._cat[: self.ntotal], q_op, k, self.row_offset, exclude_indptr, exclude_rows,
-                              self._ws)
+                              self._workspace(nq, k), tau_init, out)
 
     def search(self, q, k: int, normalize: bool = False) -> Tuple[np.ndarray, np.ndarray]:
         """faiss contract: (D float32 [nq,k] descending, I int64 [nq,k]) as numpy arrays."""

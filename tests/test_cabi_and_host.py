@@ -41,7 +41,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert "empty" in _native.last_error()
     assert lib.b200rec_topk_workspace_bytes(1000, 100, 4, 10) == 0
     assert "multiple of 64" in _native.last_error()
-    assert lib.b200rec_topk_merge(None, None, 1, 1, 1, 1, None, None, None) != 0
+    assert lib.b200rec_topk_merge(None, None, 1, 1, 1, 1, 0, 0, None, None, None) != 0
     assert "null" in _native.last_error()
 
 
@@ -130,16 +130,24 @@ def _gloo_worker(rank, world, port, tmp):
     ix = IndexFlatIP(D)
     ix.add(cat[lo:hi])
 
-    def local(q, kk):  # the oracle stands in for the CUDA kernel: same contract, global ids via the row offset
+    def local(q, kk, tau=None):  # the oracle stands in for the CUDA kernel: same contract, global ids via the offset
         s, i = ix.search(q, kk)
         i = np.where(i >= 0, i + lo, -1)
-        return torch.from_numpy(s), torch.from_numpy(i)
+        if tau is not None:  # shared thresholds: a shard drops what cannot reach the global top-k
+            drop = s < tau.numpy()[:, None]
+            s, i = np.where(drop, -np.finfo(np.float32).max, s), np.where(drop, -1, i)
+        return torch.from_numpy(s.astype(np.float32)), torch.from_numpy(i)
+
+    def sample(q, kk):  # any k distinct local rows per query: here the best of the first 400 rows of the shard
+        sub = IndexFlatIP(D)
+        sub.add(cat[lo:lo + 400])
+        return torch.from_numpy(sub.search(q, kk)[0])
 
     def merge(s, i, kk):
         ms, mi = merge_topk([s[p].numpy() for p in range(s.shape[0])], [i[p].numpy() for p in range(i.shape[0])], kk)
         return torch.from_numpy(ms), torch.from_numpy(mi)
 
-    s, i = ShardedFlatIndex(local, merge).search(qry, k)
+    s, i = ShardedFlatIndex(local, merge, local_sample=sample).search(qry, k)
     full = IndexFlatIP(D)
     full.add(cat)
     rs, ri = full.search(qry, k)

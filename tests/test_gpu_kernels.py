@@ -136,3 +136,32 @@ def test_topk_merge_matches_oracle():
     gs, gi = KR.topk_merge(torch.from_numpy(s).cuda(), torch.from_numpy(ids).cuda(), kout)
     assert np.array_equal(gs.cpu().numpy(), rs)
     assert np.array_equal(gi.cpu().numpy(), ri)
+
+
+def test_sharded_search_with_shared_thresholds_single_gpu():
+    """Two row shards emulated on one GPU: sample -> union k-th -> tau_init -> local top-K -> merge == oracle."""
+    from b200rec import kernels as KR
+    from b200rec.retrieval import FlatIPDeviceIndex
+    from oracle.flat_ip import bf16_round, normalize_L2
+    rng = np.random.default_rng(21)
+    N, Q, D, k = 600_000, 300, 64, 50
+    cat = bf16_round(normalize_L2(rng.standard_normal((N, D)).astype(np.float32)))
+    qry = bf16_round(normalize_L2(rng.standard_normal((Q, D)).astype(np.float32)))
+    rD, rI = _oracle_topk(cat, qry, k)
+    shards = []
+    for lo, hi in ((0, 250_000), (250_000, N)):
+        ix = FlatIPDeviceIndex(D, storage="bf16", row_offset=lo)
+        ix.add(cat[lo:hi])
+        shards.append(ix)
+    q_op = shards[0].prepare_queries(qry)
+    assert all(ix.has_sample_pass(Q, k) for ix in shards)
+    vals = torch.stack([ix.sample_device(q_op, k) for ix in shards])            # [2, Q, k]
+    ids = torch.arange(vals.numel(), device="cuda").view_as(vals)
+    tau = KR.topk_merge(vals.contiguous(), ids.contiguous(), k)[0][:, k - 1].contiguous()
+    assert (tau.cpu().numpy() <= rD[:, k - 1] + 1e-6).all(), "shared threshold must be a lower bound of the k-th score"
+    parts = [ix.search_device(q_op, k, tau_init=tau) for ix in shards]
+    s = torch.stack([p[0] for p in parts]).contiguous()
+    i = torch.stack([p[1] for p in parts]).contiguous()
+    Dg, Ig = KR.topk_merge(s, i, k)
+    torch.cuda.synchronize()
+    _check_topk(Dg, Ig, rD, rI, cat, qry)
