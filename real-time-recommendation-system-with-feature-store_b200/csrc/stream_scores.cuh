@@ -37,7 +37,13 @@ struct StreamGeom {
   int smem_bytes;
   int dbg_nofeed;   // development knob (2-CTA kernel): issue MMAs without waiting for / loading operands
   int ks;           // 2-CTA kernel: 64-column atoms per ring stage
+  int dbg_stats;    // development knob (2-CTA kernel): accumulate pipeline wait cycles in g_stream_stats
+  int mma_order;    // development knob (2-CTA kernel): MMA issue order / accumulator hand-off variant
 };
+
+// development counters of the 2-CTA kernel (one copy per translation unit): [0] MMA warp cycles waiting for a free
+// accumulator, [1] waiting for operands, [2] epilogue-warp cycles waiting for an accumulator, [3] consuming it, [4] tiles
+static __device__ unsigned long long g_stream_stats[8];
 
 template <int NQ, int BN>
 inline bool stream_geom(StreamGeom& g, long long N, int Q, int KB, int sms, int scratch_bytes) {
@@ -46,6 +52,8 @@ inline bool stream_geom(StreamGeom& g, long long N, int Q, int KB, int sms, int 
   g.Q = Q;
   g.KB = KB;
   g.dbg_nofeed = 0;
+  g.dbg_stats = 0;
+  g.mma_order = 0;
   g.ks = 1;
   const int rows_per_super = 128 * NQ;
   g.S = (Q + rows_per_super - 1) / rows_per_super;
@@ -134,7 +142,10 @@ stream_scores_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // Producer and MMA issuer walk their loops with the whole warp (uniform control flow) and let one ELECTED lane
+    // issue: under a `lane == 0` branch ptxas wraps each TMA / tcgen05 instruction in an ELECT + R2UR waterfall loop
+    // (~19 SASS instructions per MMA), which makes the single issuing thread the bottleneck of the pipeline.
+    {
       const uint64_t pol_q = l2_policy_evict_last();
       uint32_t it = 0, seg = 0;
       for (long long w = w_begin; w < w_end; ++seg) {
@@ -143,18 +154,24 @@ stream_scores_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         long long t1 = t0 + (w_end - w);
         if (t1 > g.T) t1 = g.T;
         mbar_wait(q_empty, (seg & 1) ^ 1);
-        mbar_arrive_expect_tx(q_full, NQ * g.KB * ST_QTILE_BYTES);
-        for (int qs = 0; qs < NQ; ++qs)
-          for (int kb = 0; kb < g.KB; ++kb)
-            tma_load_2d_hint(q_smem + (qs * g.KB + kb) * ST_QTILE_BYTES, &tmap_q, q_full, kb * 64,
-                             (s * NQ + qs) * 128, pol_q);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(q_full, NQ * g.KB * ST_QTILE_BYTES);
+          for (int qs = 0; qs < NQ; ++qs)
+            for (int kb = 0; kb < g.KB; ++kb)
+              tma_load_2d_hint(q_smem + (qs * g.KB + kb) * ST_QTILE_BYTES, &tmap_q, q_full, kb * 64,
+                               (s * NQ + qs) * 128, pol_q);
+        }
+        __syncwarp();
         for (long long t = t0; t < t1; ++t) {
           for (int kb = 0; kb < g.KB; ++kb, ++it) {
             const int st = it % g.stages;
             const uint32_t ph = (it / g.stages) & 1;
             mbar_wait(&empty_bar[st], ph ^ 1);
-            mbar_arrive_expect_tx(&full_bar[st], STAGE_BYTES);
-            tma_load_2d(ring + st * STAGE_BYTES, &tmap_x, &full_bar[st], kb * 64, (int)(t * BN));
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&full_bar[st], STAGE_BYTES);
+              tma_load_2d(ring + st * STAGE_BYTES, &tmap_x, &full_bar[st], kb * 64, (int)(t * BN));
+            }
+            __syncwarp();
           }
         }
         w += t1 - t0;
@@ -162,10 +179,11 @@ stream_scores_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {
       const uint32_t idesc = umma_idesc_bf16(128, BN);
-      const uint32_t q_addr = smem_u32(q_smem);
-      const uint32_t ring_addr = smem_u32(ring);
+      const uint64_t desc_base = umma_desc_k_sw128(0);
+      const uint32_t q_lo = (smem_u32(q_smem) & 0x3FFFFu) >> 4;
+      const uint32_t ring_lo = (smem_u32(ring) & 0x3FFFFu) >> 4;
       uint32_t it = 0, seg = 0, tc = 0;
       for (long long w = w_begin; w < w_end; ++seg) {
         const int s = (int)(w / g.T);
@@ -183,21 +201,23 @@ stream_scores_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const uint32_t ph = (it / g.stages) & 1;
             mbar_wait(&full_bar[st], ph);
             tc_fence_after();
-            const uint32_t b_addr = ring_addr + st * STAGE_BYTES;
+            if (elect_one()) {
+              const uint64_t b_desc = desc_base + (ring_lo + ((st * STAGE_BYTES) >> 4));
 #pragma unroll
-            for (int qs = 0; qs < NQ; ++qs) {
-              const uint32_t a_addr = q_addr + (qs * g.KB + kb) * ST_QTILE_BYTES;
-              const uint32_t d_addr = tmem_base + (buf * NQ + qs) * BN;
+              for (int qs = 0; qs < NQ; ++qs) {
+                const uint64_t a_desc = desc_base + (q_lo + (((qs * g.KB + kb) * ST_QTILE_BYTES) >> 4));
+                const uint32_t d_addr = tmem_base + (buf * NQ + qs) * BN;
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d_addr, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
-                          (kb | k) != 0);
+                for (int k = 0; k < 4; ++k) umma_bf16(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+              }
+              umma_commit(&empty_bar[st]);
+              if (kb == g.KB - 1) umma_commit(&acc_full[buf]);
             }
-            umma_commit(&empty_bar[st]);
+            __syncwarp();
           }
-          umma_commit(&acc_full[buf]);
         }
-        umma_commit(q_empty);
+        if (elect_one()) umma_commit(q_empty);
+        __syncwarp();
         w += t1 - t0;
       }
     }

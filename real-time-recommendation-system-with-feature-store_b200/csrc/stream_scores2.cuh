@@ -86,6 +86,8 @@ inline bool stream_geom2(StreamGeom& g, long long N, int Q, int KB, int sms, int
   g.Q = Q;
   g.KB = KB;
   g.dbg_nofeed = 0;
+  g.dbg_stats = 0;
+  g.mma_order = getenv("B200REC_MMA_ORDER") ? atoi(getenv("B200REC_MMA_ORDER")) : 0;
   g.S = (Q + S2_QUERIES - 1) / S2_QUERIES;
   g.T = (N + S2_ROWS - 1) / S2_ROWS;
   g.total = g.S * g.T;
@@ -116,6 +118,11 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   constexpr int S2_ROWS = S2Shape<NQ2>::ROWS, S2_QUERIES = S2Shape<NQ2>::QUERIES;
   constexpr int S2_STAGE_BYTES = S2Shape<NQ2>::STAGE_BYTES, UMMA_N = S2Shape<NQ2>::UMMA_N;
   constexpr int COLS = 128;  // accumulator columns one epilogue thread consumes per step
+  // Accumulator hand-off granularity.  NQ2 = 2: the two query tiles of a step are separate accumulators; with one
+  // ring stage per catalogue tile the MMAs are issued query-tile-major and each accumulator has its own full/empty
+  // barrier pair (4 epilogue warps per CTA each), so the MMA of (tile t+2, query tile 0) only waits for the 8 warps
+  // that read (t, 0) and the epilogue of (t, 0) starts half a tile earlier.  NQ2 = 1: one 256-column accumulator.
+  constexpr int NSUB = NQ2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_smem = smem;
@@ -127,8 +134,8 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + ST_MAX_STAGES;
   uint64_t* acc_full = empty_bar + ST_MAX_STAGES;
-  uint64_t* acc_empty = acc_full + 2;
-  uint64_t* q_full = acc_empty + 2;
+  uint64_t* acc_empty = acc_full + 4;   // [buffer][sub]: NQ2 = 2 hands each query tile's accumulator over separately
+  uint64_t* q_full = acc_empty + 4;
   uint64_t* q_empty = q_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 1);
   uint32_t* scratch = reinterpret_cast<uint32_t*>(tail + ST_BAR_BYTES);
@@ -148,9 +155,9 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       mbar_init(&full_bar[s], 1);    // leader's: one arrive.expect_tx by the leader's producer, bytes from both CTAs
       mbar_init(&empty_bar[s], 1);   // one multicast commit
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&acc_full[b], 1);                 // one multicast commit
-      mbar_init(&acc_empty[b], 2 * EPI_WARPS);    // leader's: epilogue warps of both CTAs
+    for (int b = 0; b < 4; ++b) {
+      mbar_init(&acc_full[b], 1);                       // one multicast commit
+      mbar_init(&acc_empty[b], 2 * EPI_WARPS / NSUB);   // leader's: the sub-buffer's epilogue warps of both CTAs
     }
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
@@ -170,7 +177,8 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (this CTA's halves)
-    if (lane == 0) {
+    // warp-uniform loop, one elected lane issues (same reason as the MMA issuer below)
+    {
       const uint32_t q_full_leader = mapa_u32(smem_u32(q_full), 0);
       uint32_t it = 0, seg = 0;
       for (long long w = w_begin; w < w_end; ++seg) {
@@ -179,34 +187,47 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         long long t1 = t0 + (w_end - w);
         if (t1 > g.T) t1 = g.T;
         mbar_wait(q_empty, (seg & 1) ^ 1);
-        if (leader) mbar_arrive_expect_tx(q_full, 2 * NQ2 * g.KB * ST_QTILE_BYTES);
-        for (int qt = 0; qt < NQ2; ++qt)
-          for (int kb = 0; kb < g.KB; ++kb)
-            tma_load_2d_2sm(q_smem + (qt * g.KB + kb) * ST_QTILE_BYTES, &tmap_q, q_full_leader, kb * 64,
-                            s * S2_QUERIES + qt * 256 + (int)rank * 128);
-        for (long long t = t0; t < t1; ++t) {
-          for (int step = 0; step < nsteps; ++step, ++it) {
-            const int st = it % g.stages;
-            const uint32_t ph = (it / g.stages) & 1;
-            if (g.dbg_nofeed) continue;  // development knob: MMA issue rate without any operand traffic
-            mbar_wait(&empty_bar[st], ph ^ 1);
-            if (leader) mbar_arrive_expect_tx(&full_bar[st], 2 * stage_bytes);
-            const uint32_t bar = mapa_u32(smem_u32(&full_bar[st]), 0);
-            for (int a = 0; a < ks; ++a)
-              tma_load_2d_2sm(ring + st * stage_bytes + a * S2_STAGE_BYTES, &tmap_x, bar, (step * ks + a) * 64,
-                              (int)(t * S2_ROWS + rank * (S2_ROWS / 2)));
+        if (elect_one()) {
+          if (leader) mbar_arrive_expect_tx(q_full, 2 * NQ2 * g.KB * ST_QTILE_BYTES);
+          for (int qt = 0; qt < NQ2; ++qt)
+            for (int kb = 0; kb < g.KB; ++kb)
+              tma_load_2d_2sm(q_smem + (qt * g.KB + kb) * ST_QTILE_BYTES, &tmap_q, q_full_leader, kb * 64,
+                              s * S2_QUERIES + qt * 256 + (int)rank * 128);
+        }
+        __syncwarp();
+        if (!g.dbg_nofeed) {  // development knob off: MMA issue rate without any operand traffic
+          for (long long t = t0; t < t1; ++t) {
+            for (int step = 0; step < nsteps; ++step, ++it) {
+              const int st = it % g.stages;
+              const uint32_t ph = (it / g.stages) & 1;
+              mbar_wait(&empty_bar[st], ph ^ 1);
+              if (elect_one()) {
+                if (leader) mbar_arrive_expect_tx(&full_bar[st], 2 * stage_bytes);
+                const uint32_t bar = mapa_u32(smem_u32(&full_bar[st]), 0);
+                for (int a = 0; a < ks; ++a)
+                  tma_load_2d_2sm(ring + st * stage_bytes + a * S2_STAGE_BYTES, &tmap_x, bar, (step * ks + a) * 64,
+                                  (int)(t * S2_ROWS + rank * (S2_ROWS / 2)));
+              }
+              __syncwarp();
+            }
           }
         }
         w += t1 - t0;
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
-    if (leader && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    // The whole warp walks the loop (warp-uniform control flow) and one ELECTED lane issues: with a `lane == 0`
+    // branch ptxas wraps every tcgen05 instruction in an ELECT / R2UR waterfall loop (~19 SASS instructions per MMA,
+    // more than the 64 cycles one M=256,N=128,K=16 MMA takes once the warp shares its scheduler with epilogue warps).
+    // Descriptors are a constant high word plus (smem address >> 4): one add per operand per MMA.
+    if (leader) {
       const uint32_t idesc = umma_idesc_bf16(256, UMMA_N);
-      const uint32_t q_addr = smem_u32(q_smem);
-      const uint32_t ring_addr = smem_u32(ring);
+      const uint64_t desc_base = umma_desc_k_sw128(0);
+      const uint32_t q_lo = (smem_u32(q_smem) & 0x3FFFFu) >> 4;
+      const uint32_t ring_lo = (smem_u32(ring) & 0x3FFFFu) >> 4;
       uint32_t it = 0, seg = 0, tc = 0;
+      long long c_acc = 0, c_full = 0;
       for (long long w = w_begin; w < w_end; ++seg) {
         const int s = (int)(w / g.T);
         const long long t0 = w - (long long)s * g.T;
@@ -216,34 +237,99 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         tc_fence_after();
         for (long long t = t0; t < t1; ++t, ++tc) {
           const uint32_t buf = tc & 1;
-          mbar_wait(&acc_empty[buf], ((tc >> 1) & 1) ^ 1);
+          const uint32_t acc_ph = ((tc >> 1) & 1) ^ 1;
+          if (NSUB == 2 && nsteps == 1 && g.mma_order != 1 && g.mma_order != 3) {
+            // query-tile-major: [wait operands] { wait acc(sub) ; 4*ks MMAs ; commit acc_full(sub) } x 2 ; release stage
+            const int st = it % g.stages;
+            const uint32_t ph = (it / g.stages) & 1;
+            ++it;
+            if (!g.dbg_nofeed) {
+              const long long c2 = g.dbg_stats ? clock64() : 0;
+              mbar_wait(&full_bar[st], ph);
+              if (g.dbg_stats) c_full += clock64() - c2;
+            }
+#pragma unroll
+            for (int qt = 0; qt < NSUB; ++qt) {
+              const long long c0 = g.dbg_stats ? clock64() : 0;
+              if (g.mma_order == 2) {
+                if (qt == 0) {
+                  mbar_wait(&acc_empty[buf * 2 + 0], acc_ph);
+                  mbar_wait(&acc_empty[buf * 2 + 1], acc_ph);
+                }
+              } else {
+                mbar_wait(&acc_empty[buf * 2 + qt], acc_ph);
+              }
+              tc_fence_after();
+              if (g.dbg_stats) c_acc += clock64() - c0;
+              if (elect_one()) {
+                const uint32_t d_addr = tmem_base + buf * 256 + qt * 128;
+                for (int a = 0; a < ks; ++a) {
+                  const uint64_t b_desc = desc_base + (ring_lo + ((st * stage_bytes + a * S2_STAGE_BYTES) >> 4));
+                  const uint64_t a_desc = desc_base + (q_lo + (((qt * g.KB + a) * ST_QTILE_BYTES) >> 4));
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16_2sm(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc, (a | k) != 0);
+                }
+                umma_commit_2sm(&acc_full[buf * 2 + qt]);
+                if (qt == NSUB - 1 && !g.dbg_nofeed) umma_commit_2sm(&empty_bar[st]);
+              }
+              __syncwarp();
+            }
+            continue;
+          }
+          const long long c0 = g.dbg_stats ? clock64() : 0;
+          for (int sub = 0; sub < NSUB; ++sub) mbar_wait(&acc_empty[buf * 2 + sub], acc_ph);
           tc_fence_after();
+          const long long c1 = g.dbg_stats ? clock64() : 0;
+          c_acc += c1 - c0;
           for (int step = 0; step < nsteps; ++step, ++it) {
             const int st = it % g.stages;
             const uint32_t ph = (it / g.stages) & 1;
             if (!g.dbg_nofeed) {
+              const long long c2 = g.dbg_stats ? clock64() : 0;
               mbar_wait(&full_bar[st], ph);
               tc_fence_after();
+              if (g.dbg_stats) c_full += clock64() - c2;
             }
-            for (int a = 0; a < ks; ++a) {
-              const int kb = step * ks + a;
-              const uint32_t b_addr = ring_addr + st * stage_bytes + a * S2_STAGE_BYTES;
+            if (elect_one()) {
+              for (int a = 0; a < ks; ++a) {
+                const int kb = step * ks + a;
+                const uint64_t b_desc = desc_base + (ring_lo + ((st * stage_bytes + a * S2_STAGE_BYTES) >> 4));
+                if (g.mma_order == 3) {  // development variant: alternate the query tiles every MMA
 #pragma unroll
-              for (int qt = 0; qt < NQ2; ++qt) {
-                const uint32_t a_addr = q_addr + (qt * g.KB + kb) * ST_QTILE_BYTES;
-                const uint32_t d_addr = tmem_base + buf * 256 + qt * 128;  // NQ2 = 1: one 256-column accumulator
+                  for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16_2sm(d_addr, umma_desc_k_sw128(a_addr + k * 32), umma_desc_k_sw128(b_addr + k * 32), idesc,
-                                (kb | k) != 0);
+                    for (int qt = 0; qt < NQ2; ++qt) {
+                      const uint64_t a_desc = desc_base + (q_lo + (((qt * g.KB + kb) * ST_QTILE_BYTES) >> 4));
+                      umma_bf16_2sm(tmem_base + buf * 256 + qt * 128, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                  }
+                  continue;
+                }
+#pragma unroll
+                for (int qt = 0; qt < NQ2; ++qt) {
+                  const uint64_t a_desc = desc_base + (q_lo + (((qt * g.KB + kb) * ST_QTILE_BYTES) >> 4));
+                  const uint32_t d_addr = tmem_base + buf * 256 + qt * 128;  // NQ2 = 1: one 256-column accumulator
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16_2sm(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                }
+              }
+              if (!g.dbg_nofeed) umma_commit_2sm(&empty_bar[st]);
+              if (step == nsteps - 1) {
+                for (int sub = 0; sub < NSUB; ++sub) umma_commit_2sm(&acc_full[buf * 2 + sub]);
               }
             }
-            if (!g.dbg_nofeed) umma_commit_2sm(&empty_bar[st]);
+            __syncwarp();
           }
-          umma_commit_2sm(&acc_full[buf]);
         }
-        umma_commit_2sm(q_empty);
+        if (elect_one()) umma_commit_2sm(q_empty);
+        __syncwarp();
         w += t1 - t0;
+      }
+      if (g.dbg_stats && lane == 0) {
+        atomicAdd(&g_stream_stats[0], (unsigned long long)c_acc);
+        atomicAdd(&g_stream_stats[1], (unsigned long long)c_full);
       }
     }
   } else if (warp >= ST_EPI_WARP0 && warp < ST_EPI_WARP0 + EPI_WARPS) {
@@ -253,7 +339,9 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const int half = ew >> 2;
     Epi epi;
     uint32_t tc = 0;
-    const uint32_t acc_empty_leader[2] = {mapa_u32(smem_u32(&acc_empty[0]), 0), mapa_u32(smem_u32(&acc_empty[1]), 0)};
+    long long c_wait = 0, c_proc = 0;
+    const int sub = NSUB == 2 ? half : 0;
+    const uint32_t acc_empty_leader[2] = {mapa_u32(smem_u32(&acc_empty[sub]), 0), mapa_u32(smem_u32(&acc_empty[2 + sub]), 0)};
     for (long long w = w_begin; w < w_end;) {
       const int s = (int)(w / g.T);
       const long long t0 = w - (long long)s * g.T;
@@ -268,16 +356,27 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       for (long long t = t0; t < t1; ++t, ++tc) {
         const uint32_t buf = tc & 1;
         epi.template pre_tile<COLS, 1>(ea, g, qslot, lane, scratch);
-        mbar_wait(&acc_full[buf], (tc >> 1) & 1);
+        const long long c0 = g.dbg_stats ? clock64() : 0;
+        mbar_wait(&acc_full[buf * 2 + sub], (tc >> 1) & 1);
         tc_fence_after();
+        const long long c1 = g.dbg_stats ? clock64() : 0;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * 256 + half * 128;
         epi.template tile<COLS>(ea, g, 0, taddr, (unsigned long long)t * S2_ROWS + (NQ2 == 1 ? half * 128 : 0));
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(acc_empty_leader[buf]);
+        if (g.dbg_stats) {
+          c_wait += c1 - c0;
+          c_proc += clock64() - c1;
+        }
       }
       epi.template end_segment<S2_SLOTS, 1>(ea, g, s, part, qslot, lane, scratch, /*last=*/(w + (t1 - t0)) >= w_end);
       w += t1 - t0;
+    }
+    if (g.dbg_stats && lane == 0) {
+      atomicAdd(&g_stream_stats[2], (unsigned long long)c_wait);
+      atomicAdd(&g_stream_stats[3], (unsigned long long)c_proc);
+      atomicAdd(&g_stream_stats[4], (unsigned long long)tc);
     }
     Epi::epilogue_exit(scratch, lane);
   } else if (warp >= ST_HELP_WARP0) {

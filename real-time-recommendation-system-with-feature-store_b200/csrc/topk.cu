@@ -112,7 +112,7 @@ __device__ __noinline__ bool row_excluded(const int32_t* rows, int n, uint32_t r
 }
 
 // development counters (B200REC_TOPK_DEBUG=2): appends, requests, epilogue wait cycles, helper busy cycles, lock misses
-__device__ unsigned long long g_topk_stats[8];
+__device__ unsigned long long g_topk_stats[16];  // [8] slow-path cycles, [9] slow-path entries, [10] group re-reads (per warp)
 
 struct QMeta {        // one per query, global memory
   uint32_t lock;      // 0 free, 1 held by a helper warp
@@ -143,6 +143,7 @@ struct TopkEpi {
     int cap;
     int flush;  // hand a list to the helper warps once it holds this many candidates (keeps tau fresh)
     int debug;  // development knob: 1 = reject everything (MMA + fast-path ceiling), 2 = count events
+    int hsleep; // nanoseconds an idle helper warp sleeps between mailbox polls
   };
   float tau[2];
   int cnt[2];
@@ -203,7 +204,9 @@ struct TopkEpi {
       if ((uint32_t)(pub >> 32) == qid[a] && qid[a] != NO_QUERY) tau[a] = fmaxf(tau[a], __uint_as_float((uint32_t)pub));
       const bool must = cnt[a] + BN > ea.cap;   // the list could overflow during the next tile
       volatile uint32_t* reqp = scratch + 1536 + qslot[a];
-      if (must || (cnt[a] >= ea.flush && *reqp == 0u)) {
+      if (ea.debug == 6) {  // development knob: candidates are found and appended but never merged
+        if (must || cnt[a] >= ea.flush) cnt[a] = 0;
+      } else if (must || (cnt[a] >= ea.flush && *reqp == 0u)) {
         volatile uint32_t* req = reqp;
         if (ea.debug == 2) {
           const long long t0 = clock64();
@@ -221,19 +224,25 @@ struct TopkEpi {
     }
   }
 
-  // Candidate test + append for one score.  Kept tiny on purpose: the whole epilogue loop must stay inside the
-  // instruction cache (a fully unrolled 64-column scan with an inlined exclusion search was 70 KB of SASS and
-  // spent 80% of its issue slots waiting for instruction fetch).
-  __device__ __forceinline__ void consider(const Args& ea, int a, float x, uint32_t row, const StreamGeom& g) {
-    if (x >= tau[a] && row < (uint32_t)g.N) {
-      if (ex_n[a] == 0 || !row_excluded(ex_lo[a], ex_n[a], row)) {
-        __stcg(buf[a] + (active[a] ? ea.cap : 0) + cnt[a], make_key(x, row));
-        ++cnt[a];
-        if (ea.debug == 2) atomicAdd(&g_topk_stats[0], 1ull);
-      }
+  // Append one candidate (rare).  Kept out of the scan on purpose: the whole epilogue loop must stay inside the
+  // instruction cache and free of branches (a fully unrolled 64-column scan with an inlined exclusion search was
+  // 70 KB of SASS and spent 80% of its issue slots waiting for instruction fetch).
+  __device__ __forceinline__ void append(const Args& ea, int a, float x, uint32_t row) {
+    if (ea.debug == 7) return;  // development knob: candidates are located but not recorded
+    if (ex_n[a] == 0 || !row_excluded(ex_lo[a], ex_n[a], row)) {
+      __stcg(buf[a] + (active[a] ? ea.cap : 0) + cnt[a], make_key(x, row));
+      ++cnt[a];
+      if (ea.debug == 2) atomicAdd(&g_topk_stats[0], 1ull);
     }
   }
 
+  // One accumulator buffer: BN columns of this thread's TMEM lane (= one query), 64 at a time.
+  //   common case  : one maximum over the 64 scores (31 three-input max + 1), one compare, one vote -> next chunk
+  //   rare case    : some lane saw a score >= tau.  The flagged 8-column groups are found from the registers (group
+  //                  maxima + one REDUX.OR over the warp); each flagged group is re-read from TMEM (warp-uniform loop,
+  //                  tcgen05.ld is warp-collective), eight compares build a hit mask without per-score branches, and only
+  //                  lanes with a non-empty mask (typically one lane, one score) run the append.  This path gates the
+  //                  MMA pipe: an accumulator is only released when every epilogue warp that reads it is done.
   template <int BN>
   __device__ __forceinline__ void tile(const Args& ea, const StreamGeom& g, int a, uint32_t taddr,
                                        unsigned long long row0_ll) {
@@ -241,35 +250,83 @@ struct TopkEpi {
     if (ea.debug == 3) return;  // development knob: MMA + TMA pipeline only (TMEM never read)
 #pragma unroll 1
     for (int c = 0; c < BN; c += 64) {
-      uint32_t gbits;
-      {
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32(taddr + c, v0);
-        tmem_ld_32x32(taddr + c + 32, v1);
-        tmem_ld_wait();
-        if (ea.debug == 5) {  // development knob: TMEM read cost only
-          asm volatile("" ::"r"(v0[0]), "r"(v1[31]));
-          continue;
-        }
-        gbits = group_bits(v0, tau[a]) | (group_bits(v1, tau[a]) << 4);
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(taddr + c, v0);
+      tmem_ld_32x32(taddr + c + 32, v1);
+      tmem_ld_wait();
+      if (ea.debug == 5) {  // development knob: TMEM read cost only
+        asm volatile("" ::"r"(v0[0]), "r"(v1[31]));
+        continue;
       }
-      // rare path (warp-uniform loop because tcgen05.ld is warp-collective): re-read only the flagged 8-column groups
-      uint32_t pending = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) pending |= (__ballot_sync(FULL_MASK, (gbits >> j) & 1u) != 0u) ? (1u << j) : 0u;
+      const float m64 = fmaxf(max32(v0), max32(v1));
+      if (!__any_sync(FULL_MASK, m64 >= tau[a])) continue;
+      long long sp0 = 0;
+      if (ea.debug == 2) sp0 = clock64();
+      const uint32_t gbits = (m64 >= tau[a]) ? (group_bits(v0, tau[a]) | (group_bits(v1, tau[a]) << 4)) : 0u;
+      uint32_t pending = __reduce_or_sync(FULL_MASK, gbits);
+      const uint32_t base = row0 + c;
+      const uint32_t nvalid = base < (uint32_t)g.N ? (uint32_t)g.N - base : 0u;  // rows [base, base + nvalid) exist
 #pragma unroll 1
       while (pending) {
         const int j = __ffs(pending) - 1;
         pending &= pending - 1;
-        uint32_t w[8];
-        tmem_ld_32x8(taddr + c + 8 * j, w);
-        tmem_ld_wait();
-        if ((gbits >> j) & 1u) {
+        float w[8];
+#ifndef B200_RARE_SWITCH  // re-read the flagged group from TMEM (measured 5% faster end to end than the register switch below)
+        {
+          uint32_t wr[8];
+          tmem_ld_32x8(taddr + c + 8 * j, wr);
+          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) consider(ea, a, __uint_as_float(w[i]), row0 + c + 8 * j + i, g);
+          for (int i = 0; i < 8; ++i) w[i] = __uint_as_float(wr[i]);
         }
+#else
+        switch (j) {  // warp-uniform
+#define B200_GRP(J, V, O)                                                     \
+  case J:                                                                     \
+    _Pragma("unroll") for (int i = 0; i < 8; ++i) w[i] = __uint_as_float(V[O + i]); \
+    break;
+          B200_GRP(0, v0, 0)
+          B200_GRP(1, v0, 8)
+          B200_GRP(2, v0, 16)
+          B200_GRP(3, v0, 24)
+          B200_GRP(4, v1, 0)
+          B200_GRP(5, v1, 8)
+          B200_GRP(6, v1, 16)
+          default:
+          B200_GRP(7, v1, 24)
+#undef B200_GRP
+        }
+#endif
+        uint32_t hits = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hits |= (w[i] >= tau[a]) ? (1u << i) : 0u;
+        const uint32_t col = 8u * (uint32_t)j;
+        if (col + 8u > nvalid) hits &= col < nvalid ? (1u << (nvalid - col)) - 1u : 0u;  // rows past the end of the shard
+        while (hits) {  // divergent: lanes that really hold a candidate (typically one lane, one score)
+          const int i = __ffs(hits) - 1;
+          hits &= hits - 1;
+          float x = w[0];
+#pragma unroll
+          for (int u = 1; u < 8; ++u) x = (i == u) ? w[u] : x;
+          append(ea, a, x, base + col + (uint32_t)i);
+        }
+        if (ea.debug == 2 && (threadIdx.x & 31) == 0) atomicAdd(&g_topk_stats[10], 1ull);
+      }
+      if (ea.debug == 2 && (threadIdx.x & 31) == 0) {
+        atomicAdd(&g_topk_stats[8], (unsigned long long)(clock64() - sp0));
+        atomicAdd(&g_topk_stats[9], 1ull);
       }
     }
+  }
+
+  static __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
+    float t[11];
+#pragma unroll
+    for (int j = 0; j < 10; ++j)
+      t[j] = fmax3(__uint_as_float(v[3 * j]), __uint_as_float(v[3 * j + 1]), __uint_as_float(v[3 * j + 2]));
+    t[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+    const float a = fmax3(t[0], t[1], t[2]), b = fmax3(t[3], t[4], t[5]), c = fmax3(t[6], t[7], t[8]);
+    return fmax3(fmax3(a, b, c), t[9], t[10]);
   }
 
   // bit j set when the maximum of columns [8j, 8j+8) reaches tau
@@ -364,6 +421,14 @@ struct TopkEpi {
     volatile uint32_t* done = scratch + 2048;
     uint64_t* stage = reinterpret_cast<uint64_t*>(scratch + 2112) + hw * TOPK_STG;
     const int k = ea.k;
+    // SM cycles and wall nanoseconds of this launch as seen by CTA 0 (=> the SM clock the kernel really ran at)
+    const bool stamp = hw == 0 && lane == 0;
+    long long c_begin = 0;
+    unsigned long long ns_begin = 0;
+    if (stamp) {
+      c_begin = clock64();
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
+    }
     for (;;) {
       const bool finished = (*done == (uint32_t)EPI_WARPS);
       bool any = false;
@@ -441,8 +506,15 @@ struct TopkEpi {
       }
       if (!any) {
         if (finished) break;
-        __nanosleep(64);
+        __nanosleep(ea.hsleep);  // idle helper warps must not burn issue slots (the kernel is power-limited)
       }
+    }
+    if (stamp) {
+      unsigned long long ns_end;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_end));
+      if (blockIdx.x == 0) g_topk_stats[6] = (unsigned long long)(clock64() - c_begin) * 1000ull / (ns_end - ns_begin + 1);  // MHz
+      atomicMax(&g_topk_stats[5], ~ns_begin);  // ~(earliest CTA start)
+      atomicMax(&g_topk_stats[7], ns_end);     // latest CTA end
     }
   }
 };
@@ -918,6 +990,7 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
   ea.cap = p.cap;
   ea.flush = getenv("B200REC_TOPK_FLUSH") ? atoi(getenv("B200REC_TOPK_FLUSH")) : 32;
   ea.debug = getenv("B200REC_TOPK_DEBUG") ? atoi(getenv("B200REC_TOPK_DEBUG")) : 0;
+  ea.hsleep = getenv("B200REC_TOPK_HSLEEP") ? atoi(getenv("B200REC_TOPK_HSLEEP")) : 400;
   void (*kern)(const CUtensorMap, const CUtensorMap, const StreamGeom, const TopkEpi::Args);
   if constexpr (V2 != 0) kern = stream_scores2_kernel<(V2 == 2 ? 2 : 1), TopkEpi>;
   else kern = stream_scores_kernel<NQ, BN, TopkEpi>;
@@ -971,6 +1044,7 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
   }
   StreamGeom gl = p.g;
   gl.dbg_nofeed = (ea.debug == 4) ? 1 : 0;
+  gl.dbg_stats = (ea.debug == 2 || getenv("B200REC_STREAM_STATS") != nullptr) ? 1 : 0;
   if (ea.debug == 4) ea.debug = 3;
   kern<<<gl.grid, ST_THREADS, gl.smem_bytes, st>>>(tq, tx, gl, ea);
   B200_LAUNCH_OK("stream_scores_kernel<topk>");
@@ -991,6 +1065,18 @@ extern "C" int b200rec_debug_topk_stats(unsigned long long* out8_host, int reset
   if (reset) {
     unsigned long long z[8] = {0};
     B200_CUDA_OK(cudaMemcpyToSymbol(g_topk_stats, z, sizeof(z)));
+  }
+  return 0;
+}
+
+extern "C" int b200rec_debug_topk_stats16(unsigned long long* out24_host, int reset) {
+  using namespace b200;
+  B200_CUDA_OK(cudaMemcpyFromSymbol(out24_host, g_topk_stats, sizeof(unsigned long long) * 16));
+  B200_CUDA_OK(cudaMemcpyFromSymbol(out24_host + 16, g_stream_stats, sizeof(unsigned long long) * 8));
+  if (reset) {
+    unsigned long long z[16] = {0};
+    B200_CUDA_OK(cudaMemcpyToSymbol(g_topk_stats, z, sizeof(z)));
+    B200_CUDA_OK(cudaMemcpyToSymbol(g_stream_stats, z, sizeof(unsigned long long) * 8));
   }
   return 0;
 }
