@@ -39,6 +39,10 @@ struct StreamGeom {
   int ks;           // 2-CTA kernel: 64-column atoms per ring stage
   int dbg_stats;    // development knob (2-CTA kernel): accumulate pipeline wait cycles in g_stream_stats
   int mma_order;    // development knob (2-CTA kernel): MMA issue order / accumulator hand-off variant
+  // 2-CTA kernel work decomposition (see geom2_segment): units [0, n_main) sweep tiles r, r+R, r+2R, ... < Tmain of ONE
+  // supertile each; the remaining units share the tail tiles [Tmain, T) of all supertiles as contiguous ranges.
+  int n_main, R;
+  long long Tmain, Tt, We;
 };
 
 // development counters of the 2-CTA kernel (one copy per translation unit): [0] MMA warp cycles waiting for a free

@@ -94,10 +94,38 @@ inline bool stream_geom2(StreamGeom& g, long long N, int Q, int KB, int sms, int
   long long units = sms / 2;
   if (units > g.total) units = g.total;
   g.W = (g.total + units - 1) / units;
-  const long long used = (g.total + g.W - 1) / g.W;
+  // Time-aligned schedule: with S supertiles and U units, R = U / S units sweep each supertile with stride R, so at any
+  // moment all units read the same few catalogue tiles (one per stride slot) for different queries and every tile
+  // comes from HBM once instead of once per supertile (ncu: 11.3 GB of DRAM reads per launch for a 2.56 GB catalogue
+  // with the contiguous split).  The U - R*S leftover units share the last Tt tiles of every supertile so that all
+  // units still do W tiles.  Falls back to the contiguous split when there are more supertiles than units.
+  const char* sch = getenv("B200REC_SCHED");
+  const bool aligned = !(sch && atoi(sch) == 0) && g.S <= units && g.T >= 4 * (units / g.S);
+  long long used;
+  if (aligned) {
+    g.R = (int)(units / g.S);
+    long long extra = units - (long long)g.R * g.S;
+    // A unit that changes supertile hands 256 candidate lists to its helper warps at once (hundreds of microseconds of
+    // merge backlog), so when only a few units are left over they stay idle rather than become stragglers.
+    if (extra * 16 <= units && !(sch && atoi(sch) == 3)) extra = 0;
+    g.n_main = g.R * g.S;
+    g.Tmain = extra == 0 ? g.T : (g.R * g.W < g.T ? g.R * g.W : g.T);
+    g.Tt = g.T - g.Tmain;
+    g.We = (extra > 0 && g.Tt > 0) ? ((long long)g.S * g.Tt + extra - 1) / extra : 1;
+    used = g.n_main + (g.Tt > 0 ? ((long long)g.S * g.Tt + g.We - 1) / g.We : 0);
+  } else {
+    g.R = 0;
+    g.n_main = 0;
+    g.Tmain = 0;
+    g.Tt = g.T;
+    g.We = g.W;
+    used = (g.total + g.W - 1) / g.W;
+  }
   g.grid = (int)(2 * used);
-  long long mp = (g.T + g.W - 1) / g.W + 1;
-  g.max_parts = (int)(mp < used ? mp : used);
+  {
+    const long long lin = (g.T + g.W - 1) / g.W + 1;
+    g.max_parts = (int)(aligned ? g.R + (units - g.n_main) + 1 : (lin < used ? lin : used));
+  }
   const int q_bytes = NQ2 * KB * ST_QTILE_BYTES;
   const int avail = ST_SMEM_LIMIT - 1024 - ST_BAR_BYTES - scratch_bytes - q_bytes;
   const char* kse = getenv("B200REC_KS");
@@ -108,6 +136,43 @@ inline bool stream_geom2(StreamGeom& g, long long N, int Q, int KB, int sms, int
   g.stages = stages;
   g.smem_bytes = 1024 + q_bytes + stages * S2_STAGE_BYTES * g.ks + ST_BAR_BYTES + scratch_bytes;
   return stages >= 3;
+}
+
+// k-th segment (one supertile `s`, tiles t0, t0 + stride, ... (cnt of them)) of a work unit; false when there is none
+__device__ __forceinline__ bool geom2_segment(const StreamGeom& g, long long unit, int k, int& s, long long& t0,
+                                              long long& cnt, long long& stride, bool& last) {
+  if (unit < g.n_main) {
+    if (k > 0) return false;
+    s = (int)(unit % g.S);
+    const long long r = unit / g.S;
+    t0 = r;
+    stride = g.R;
+    cnt = r < g.Tmain ? (g.Tmain - r + g.R - 1) / g.R : 0;
+    last = true;
+    return cnt > 0;
+  }
+  const long long x0 = (unit - g.n_main) * g.We, xt = (long long)g.S * g.Tt;
+  long long x1 = x0 + g.We;
+  if (x1 > xt) x1 = xt;
+  if (x0 >= x1) return false;
+  const long long sk = x0 / g.Tt + k;
+  const long long a = x0 > sk * g.Tt ? x0 : sk * g.Tt;
+  const long long b = x1 < (sk + 1) * g.Tt ? x1 : (sk + 1) * g.Tt;
+  if (a >= b) return false;
+  s = (int)sk;
+  t0 = g.Tmain + (a - sk * g.Tt);
+  cnt = b - a;
+  stride = 1;
+  last = b >= x1;
+  return true;
+}
+// supertile of a unit's LAST segment (-1: the unit has no work); the final per-query kernel collects leftovers with it
+__device__ __forceinline__ int geom2_last_super(const StreamGeom& g, long long unit) {
+  if (unit < g.n_main) return unit / g.S < g.Tmain ? (int)(unit % g.S) : -1;
+  const long long x0 = (unit - g.n_main) * g.We, xt = (long long)g.S * g.Tt;
+  long long x1 = x0 + g.We;
+  if (x1 > xt) x1 = xt;
+  return x0 < x1 ? (int)((x1 - 1) / g.Tt) : -1;
 }
 
 template <int NQ2, class Epi>
@@ -171,21 +236,18 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long w_begin = unit * g.W;
-  long long w_end = w_begin + g.W;
-  if (w_end > g.total) w_end = g.total;
+  const bool dbg_st = g.dbg_stats == 1 || g.dbg_stats == 2 + (int)unit;  // development counters: all units or one
+  int s;                       // segment: supertile, first tile, tile count, tile stride, last segment of the unit
+  long long t0, ntile, tstep;
+  bool last_seg;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (this CTA's halves)
     // warp-uniform loop, one elected lane issues (same reason as the MMA issuer below)
     {
       const uint32_t q_full_leader = mapa_u32(smem_u32(q_full), 0);
-      uint32_t it = 0, seg = 0;
-      for (long long w = w_begin; w < w_end; ++seg) {
-        const int s = (int)(w / g.T);
-        const long long t0 = w - (long long)s * g.T;
-        long long t1 = t0 + (w_end - w);
-        if (t1 > g.T) t1 = g.T;
+      uint32_t it = 0;
+      for (int seg = 0; geom2_segment(g, unit, seg, s, t0, ntile, tstep, last_seg); ++seg) {
         mbar_wait(q_empty, (seg & 1) ^ 1);
         if (elect_one()) {
           if (leader) mbar_arrive_expect_tx(q_full, 2 * NQ2 * g.KB * ST_QTILE_BYTES);
@@ -196,7 +258,7 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         }
         __syncwarp();
         if (!g.dbg_nofeed) {  // development knob off: MMA issue rate without any operand traffic
-          for (long long t = t0; t < t1; ++t) {
+          for (long long ti = 0, t = t0; ti < ntile; ++ti, t += tstep) {
             for (int step = 0; step < nsteps; ++step, ++it) {
               const int st = it % g.stages;
               const uint32_t ph = (it / g.stages) & 1;
@@ -212,7 +274,6 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             }
           }
         }
-        w += t1 - t0;
       }
     }
   } else if (warp == 1) {
@@ -226,16 +287,12 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       const uint64_t desc_base = umma_desc_k_sw128(0);
       const uint32_t q_lo = (smem_u32(q_smem) & 0x3FFFFu) >> 4;
       const uint32_t ring_lo = (smem_u32(ring) & 0x3FFFFu) >> 4;
-      uint32_t it = 0, seg = 0, tc = 0;
+      uint32_t it = 0, tc = 0;
       long long c_acc = 0, c_full = 0;
-      for (long long w = w_begin; w < w_end; ++seg) {
-        const int s = (int)(w / g.T);
-        const long long t0 = w - (long long)s * g.T;
-        long long t1 = t0 + (w_end - w);
-        if (t1 > g.T) t1 = g.T;
+      for (int seg = 0; geom2_segment(g, unit, seg, s, t0, ntile, tstep, last_seg); ++seg) {
         mbar_wait(q_full, seg & 1);
         tc_fence_after();
-        for (long long t = t0; t < t1; ++t, ++tc) {
+        for (long long ti = 0; ti < ntile; ++ti, ++tc) {
           const uint32_t buf = tc & 1;
           const uint32_t acc_ph = ((tc >> 1) & 1) ^ 1;
           if (NSUB == 2 && nsteps == 1 && g.mma_order != 1 && g.mma_order != 3) {
@@ -244,13 +301,13 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             const uint32_t ph = (it / g.stages) & 1;
             ++it;
             if (!g.dbg_nofeed) {
-              const long long c2 = g.dbg_stats ? clock64() : 0;
+              const long long c2 = dbg_st ? clock64() : 0;
               mbar_wait(&full_bar[st], ph);
-              if (g.dbg_stats) c_full += clock64() - c2;
+              if (dbg_st) c_full += clock64() - c2;
             }
 #pragma unroll
             for (int qt = 0; qt < NSUB; ++qt) {
-              const long long c0 = g.dbg_stats ? clock64() : 0;
+              const long long c0 = dbg_st ? clock64() : 0;
               if (g.mma_order == 2) {
                 if (qt == 0) {
                   mbar_wait(&acc_empty[buf * 2 + 0], acc_ph);
@@ -260,7 +317,7 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 mbar_wait(&acc_empty[buf * 2 + qt], acc_ph);
               }
               tc_fence_after();
-              if (g.dbg_stats) c_acc += clock64() - c0;
+              if (dbg_st) c_acc += clock64() - c0;
               if (elect_one()) {
                 const uint32_t d_addr = tmem_base + buf * 256 + qt * 128;
                 for (int a = 0; a < ks; ++a) {
@@ -277,19 +334,19 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             }
             continue;
           }
-          const long long c0 = g.dbg_stats ? clock64() : 0;
+          const long long c0 = dbg_st ? clock64() : 0;
           for (int sub = 0; sub < NSUB; ++sub) mbar_wait(&acc_empty[buf * 2 + sub], acc_ph);
           tc_fence_after();
-          const long long c1 = g.dbg_stats ? clock64() : 0;
+          const long long c1 = dbg_st ? clock64() : 0;
           c_acc += c1 - c0;
           for (int step = 0; step < nsteps; ++step, ++it) {
             const int st = it % g.stages;
             const uint32_t ph = (it / g.stages) & 1;
             if (!g.dbg_nofeed) {
-              const long long c2 = g.dbg_stats ? clock64() : 0;
+              const long long c2 = dbg_st ? clock64() : 0;
               mbar_wait(&full_bar[st], ph);
               tc_fence_after();
-              if (g.dbg_stats) c_full += clock64() - c2;
+              if (dbg_st) c_full += clock64() - c2;
             }
             if (elect_one()) {
               for (int a = 0; a < ks; ++a) {
@@ -325,9 +382,8 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         }
         if (elect_one()) umma_commit_2sm(q_empty);
         __syncwarp();
-        w += t1 - t0;
       }
-      if (g.dbg_stats && lane == 0) {
+      if (dbg_st && lane == 0) {
         atomicAdd(&g_stream_stats[0], (unsigned long long)c_acc);
         atomicAdd(&g_stream_stats[1], (unsigned long long)c_full);
       }
@@ -342,38 +398,33 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     long long c_wait = 0, c_proc = 0;
     const int sub = NSUB == 2 ? half : 0;
     const uint32_t acc_empty_leader[2] = {mapa_u32(smem_u32(&acc_empty[sub]), 0), mapa_u32(smem_u32(&acc_empty[2 + sub]), 0)};
-    for (long long w = w_begin; w < w_end;) {
-      const int s = (int)(w / g.T);
-      const long long t0 = w - (long long)s * g.T;
-      long long t1 = t0 + (w_end - w);
-      if (t1 > g.T) t1 = g.T;
-      const int part = (int)(unit - (s * g.T) / g.W);
+    for (int seg = 0; geom2_segment(g, unit, seg, s, t0, ntile, tstep, last_seg); ++seg) {
+      const int part = 0;
       // `half` selects the 128-column half of the one accumulator (NQ2 = 1) or the query tile (NQ2 = 2)
       int qslot[1] = {half * 128 + quarter * 32 + lane};
       const long long q = (long long)s * S2_QUERIES + (NQ2 == 2 ? half * 256 : 0) + rank * 128 + quarter * 32 + lane;
       long long qrow[1] = {q < g.Q ? q : -1};
       epi.template begin_segment<S2_SLOTS, 1>(ea, g, s, part, qrow, qslot, lane, scratch);
-      for (long long t = t0; t < t1; ++t, ++tc) {
+      for (long long ti = 0, t = t0; ti < ntile; ++ti, t += tstep, ++tc) {
         const uint32_t buf = tc & 1;
         epi.template pre_tile<COLS, 1>(ea, g, qslot, lane, scratch);
-        const long long c0 = g.dbg_stats ? clock64() : 0;
+        const long long c0 = dbg_st ? clock64() : 0;
         mbar_wait(&acc_full[buf * 2 + sub], (tc >> 1) & 1);
         tc_fence_after();
-        const long long c1 = g.dbg_stats ? clock64() : 0;
+        const long long c1 = dbg_st ? clock64() : 0;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * 256 + half * 128;
         epi.template tile<COLS>(ea, g, 0, taddr, (unsigned long long)t * S2_ROWS + (NQ2 == 1 ? half * 128 : 0));
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(acc_empty_leader[buf]);
-        if (g.dbg_stats) {
+        if (dbg_st) {
           c_wait += c1 - c0;
           c_proc += clock64() - c1;
         }
       }
-      epi.template end_segment<S2_SLOTS, 1>(ea, g, s, part, qslot, lane, scratch, /*last=*/(w + (t1 - t0)) >= w_end);
-      w += t1 - t0;
+      epi.template end_segment<S2_SLOTS, 1>(ea, g, s, part, qslot, lane, scratch, last_seg);
     }
-    if (g.dbg_stats && lane == 0) {
+    if (dbg_st && lane == 0) {
       atomicAdd(&g_stream_stats[2], (unsigned long long)c_wait);
       atomicAdd(&g_stream_stats[3], (unsigned long long)c_proc);
       atomicAdd(&g_stream_stats[4], (unsigned long long)tc);

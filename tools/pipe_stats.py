@@ -26,12 +26,9 @@ def run(tag):
     print(f"   MMA warp (74 leaders): wait-acc {buf[16]/74/tiles_cta:.0f} cyc/tile, wait-operands {buf[17]/74/tiles_cta:.0f} cyc/tile", flush=True)
     print(f"   epilogue warp: wait-acc {buf[18]/tiles:.0f} cyc/tile, consume {buf[19]/tiles:.0f} cyc/tile", flush=True)
     print(f"   appends/query {buf[0]/Q:.0f}, requests/query {buf[1]/Q:.1f}, slow-path entries/warp-tile {buf[9]/tiles:.3f}, "
-          f"cycles/entry {buf[8]/max(buf[9],1):.0f}, group re-reads/entry {buf[10]/max(buf[9],1):.2f}, helper busy {buf[3]/148/4/1e6:.2f} Mcyc/warp, lock-miss {buf[4]}", flush=True)
+          f"cycles/entry {buf[8]/max(buf[9],1):.0f}, group re-reads/entry {buf[10]/max(buf[9],1):.2f}, helper busy {buf[3]/148/4/1e6:.3f} Mcyc/warp, lock-miss {buf[4]}, epi mailbox wait {buf[2]/148/8/1e6:.3f} Mcyc/warp", flush=True)
+    print(f"   rare path per entry: find groups {buf[11]/max(buf[9],1):.0f} cyc, TMEM re-read {buf[12]/max(buf[9],1):.0f} cyc, tests+append {buf[13]/max(buf[9],1):.0f} cyc", flush=True)
 os.environ["B200REC_TOPK_DEBUG"] = "2"
 run("full+stats")
 os.environ["B200REC_TOPK_DEBUG"] = "1"; os.environ["B200REC_STREAM_STATS"] = "1"
 run("reject-all+stats")
-os.environ["B200REC_TOPK_DEBUG"] = "5"
-run("tmem-read-only+stats")
-os.environ["B200REC_TOPK_DEBUG"] = "3"
-run("noepi+stats")
