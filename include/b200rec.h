@@ -66,11 +66,12 @@ int b200rec_flat_ip_topk(const void* catalogue, int64_t N, int64_t ld, const voi
                          int64_t row_offset, const int64_t* exclude_indptr, const int32_t* exclude_rows,
                          const float* tau_init, float* out_scores, int64_t* out_ids, void* workspace,
                          size_t workspace_bytes, void* stream);
-/* Sampling pass alone: out_vals [Q,k] = the k largest group maxima (distinct sampled rows) of every query, descending.
- * Row-sharded search exchanges these (all-gather) and starts every shard from the k-th best of the union.
+/* Sampling pass alone: out_vals [Q,k_out] = the k_out (<= k) largest group maxima (distinct sampled rows) of every
+ * query, descending.  Row-sharded search exchanges these (all-gather) and starts every shard from the k-th best of the
+ * union; `shards` (>= 1) says how many shards pool their samples, so each one samples 1/shards as densely.
  * b200rec_topk_has_sample says whether this shape runs a sampling pass at all (small shards do not). */
-int b200rec_topk_sample(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k,
-                        float* out_vals, void* workspace, size_t workspace_bytes, void* stream);
+int b200rec_topk_sample(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k, int k_out,
+                        int shards, float* out_vals, void* workspace, size_t workspace_bytes, void* stream);
 int b200rec_topk_has_sample(int64_t N, int64_t ld, int64_t Q, int k);
 /* k-way merge of `parts` candidate lists [parts][Q][k_in] (id < 0 = empty, ids < 2^32) into the global top k_out under
  * the same order: the exchange step after the all-gather of per-GPU results.  *_part_stride = element distance

@@ -689,8 +689,8 @@ struct SampleMaxEpi {
 constexpr int FIN_THREADS = 256;
 
 template <class Loader>
-__device__ void block_select_sort(const Loader& load, int n, int k_out, uint64_t* skeys /*[pow2 >= k_out]*/, int P,
-                                  uint32_t* hist /*[256]*/, int* s_misc /*[8]*/) {
+__device__ void block_select_sort_core(const Loader& load, int n, int k_out, uint64_t* skeys /*[pow2 >= k_out]*/, int P,
+                                       uint32_t* hist /*[256]*/, int* s_misc /*[8]*/) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // count valid keys
   if (tid == 0) s_misc[0] = 0;
@@ -763,6 +763,24 @@ __device__ void block_select_sort(const Loader& load, int n, int k_out, uint64_t
   }
 }
 
+struct StagedKeys {
+  const uint64_t* keys;
+  __device__ __forceinline__ uint64_t operator()(int i) const { return keys[i]; }
+};
+// The select makes up to ten passes over the candidates: stage them in shared memory once when they fit (the loaders
+// read global memory through index arithmetic or a binary search over source lists).
+template <class Loader>
+__device__ __forceinline__ void block_select_sort(const Loader& load, int n, int k_out, uint64_t* skeys, int P,
+                                                  uint32_t* hist, int* s_misc, uint64_t* stage, int stage_cap) {
+  if (n <= stage_cap) {
+    for (int i = threadIdx.x; i < n; i += FIN_THREADS) stage[i] = load(i);
+    __syncthreads();
+    block_select_sort_core(StagedKeys{stage}, n, k_out, skeys, P, hist, s_misc);
+  } else {
+    block_select_sort_core(load, n, k_out, skeys, P, hist, s_misc);
+  }
+}
+
 __device__ __forceinline__ void write_result(const uint64_t* skeys, int k_out, int64_t row_offset, float* out_s,
                                              int64_t* out_i) {
   for (int i = threadIdx.x; i < k_out; i += FIN_THREADS) {
@@ -801,14 +819,19 @@ __global__ void __launch_bounds__(FIN_THREADS)
 topk_final_kernel(const StreamGeom g, int v2, int qs /*queries per supertile*/, int slots /*per CTA*/,
                   const uint64_t* __restrict__ tlists, const QMeta* __restrict__ meta,
                   const uint64_t* __restrict__ lists, const uint32_t* __restrict__ left, int cap, int k, int P,
-                  int64_t row_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+                  int stage_cap, int64_t row_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
   extern __shared__ uint64_t fin_smem[];
   __shared__ uint32_t hist[256];
   __shared__ int s_misc[8];
   __shared__ const uint64_t* s_ptr[FIN_MAX_SRC];
   __shared__ int s_off[FIN_MAX_SRC + 1];
+  __shared__ int s_last[FIN_MAX_SRC];  // 2-CTA kernel: supertile of every unit's last segment (64-bit divisions: in parallel)
   const int q = blockIdx.x;
   const int s = q / qs, inq = q - s * qs;
+  if (v2) {
+    for (int u = threadIdx.x; u < g.grid / 2 && u < FIN_MAX_SRC; u += FIN_THREADS) s_last[u] = geom2_last_super(g, u);
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
     int n = 0, ns = 0;
     s_ptr[ns] = tlists + (size_t)q * 2 * k + (size_t)meta[q].tsel * k;
@@ -818,7 +841,7 @@ topk_final_kernel(const StreamGeom g, int v2, int qs /*queries per supertile*/, 
     const int u0 = v2 ? 0 : geom_first_cta(g, s), u1 = v2 ? g.grid / 2 - 1 : geom_last_cta(g, s);
     for (int u = u0; u <= u1; ++u) {
       if (v2) {
-        if (geom2_last_super(g, u) != s) continue;
+        if (u >= FIN_MAX_SRC || s_last[u] != s) continue;
       } else {
         long long wend = (long long)(u + 1) * g.W;
         if (wend > g.total) wend = g.total;
@@ -844,7 +867,7 @@ topk_final_kernel(const StreamGeom g, int v2, int qs /*queries per supertile*/, 
   MultiLoader ld{s_ptr, s_off, s_misc[5]};
   const int n = s_misc[6];
   __syncthreads();
-  block_select_sort(ld, n, k, fin_smem, P, hist, s_misc);
+  block_select_sort(ld, n, k, fin_smem, P, hist, s_misc, fin_smem + P, stage_cap);
   write_result(fin_smem, k, row_offset, out_scores + (size_t)q * k, out_ids + (size_t)q * k);
 }
 
@@ -857,13 +880,13 @@ struct FloatRowLoader {
   }
 };
 __global__ void __launch_bounds__(FIN_THREADS)
-sample_topk_kernel(const float* __restrict__ S, int m, int k, int P, float* __restrict__ out_vals) {
+sample_topk_kernel(const float* __restrict__ S, int m, int k, int P, int stage_cap, float* __restrict__ out_vals) {
   extern __shared__ uint64_t fin_smem[];
   __shared__ uint32_t hist[256];
   __shared__ int s_misc[8];
   const int q = blockIdx.x;
   FloatRowLoader ld{S + (size_t)q * m};
-  block_select_sort(ld, m, k, fin_smem, P, hist, s_misc);
+  block_select_sort(ld, m, k, fin_smem, P, hist, s_misc, fin_smem + P, stage_cap);
   for (int i = threadIdx.x; i < k; i += FIN_THREADS) {
     const uint64_t key = fin_smem[i];
     out_vals[(size_t)q * k + i] = key == 0ull ? -FLT_MAX : ord_f32((uint32_t)(key >> 32));
@@ -911,8 +934,8 @@ struct ListLoader {
 
 __global__ void __launch_bounds__(FIN_THREADS)
 topk_merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids, int parts, long long Q, int k_in,
-                  int k_out, int P, long long s_stride, long long i_stride, float* __restrict__ out_scores,
-                  int64_t* __restrict__ out_ids) {
+                  int k_out, int P, int stage_cap, long long s_stride, long long i_stride,
+                  float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
   extern __shared__ uint64_t fin_smem[];
   __shared__ uint32_t hist[256];
   __shared__ int s_misc[8];
@@ -923,7 +946,7 @@ topk_merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
   ld.s_stride = (size_t)s_stride;
   ld.i_stride = (size_t)i_stride;
   ld.k_in = k_in;
-  block_select_sort(ld, parts * k_in, k_out, fin_smem, P, hist, s_misc);
+  block_select_sort(ld, parts * k_in, k_out, fin_smem, P, hist, s_misc, fin_smem + P, stage_cap);
   write_result(fin_smem, k_out, 0, out_scores + (size_t)q * k_out, out_ids + (size_t)q * k_out);
 }
 
@@ -998,6 +1021,7 @@ struct TopkPlan {
   size_t lists_bytes, tlists_bytes, meta_bytes, left_bytes, sample_bytes;
   int64_t sample_m, sample_stride;  // 0 = no sampling pass
   int sample_gw;
+  int sample_k_out;                 // b200rec_topk_sample: group maxima returned per query (<= k)
   StreamGeom gs;                    // geometry of the sampling pass
   size_t total() const { return lists_bytes + tlists_bytes + meta_bytes + left_bytes + sample_bytes; }
 };
@@ -1008,7 +1032,7 @@ static int cap_for(int k, int bn) {
   return ((mult * k + bn + 31) / 32) * 32;
 }
 
-static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k) {
+static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k, int shards = 1) {
   if (N <= 0 || Q <= 0) return fail("topk: empty catalogue or query set");
   if (N >= (1ll << 32) - 1) return fail("topk: a shard holds at most 2^32-2 rows");
   if (Q > INT32_MAX / 2) return fail("topk: too many queries");
@@ -1056,7 +1080,9 @@ static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k) {
   p.sample_gw = 32;
   const char* ns = getenv("B200REC_TOPK_NOSAMPLE");
   const char* sf = getenv("B200REC_TOPK_SAMPLE_FRAC");
-  int64_t frac = N >= (4ll << 20) ? 32 : (N >= (256ll << 10) ? 16 : 8);
+  // `shards` row shards pool their samples (b200rec_topk_sample): the density is chosen for the pooled catalogue
+  const int64_t n_pool = N * (shards > 1 ? shards : 1);
+  int64_t frac = n_pool >= (4ll << 20) ? 32 : (n_pool >= (256ll << 10) ? 16 : 8);
   if (sf && atoi(sf) > 0) frac = atoi(sf);
   int64_t m = (N / frac) / 256 * 256;
   if (!(ns && atoi(ns)) && m >= 2048) {
@@ -1132,7 +1158,8 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
     B200_LAUNCH_OK("stream_scores_kernel<sample>");
     if (sample_vals_out != nullptr) {  // sampling only: hand the k best group maxima per query to the caller
       const int P = next_pow2(k);
-      sample_topk_kernel<<<(unsigned)Q, FIN_THREADS, P * sizeof(uint64_t), st>>>(S, sa.ngroups, k, P, sample_vals_out);
+      const int sc = sa.ngroups <= 4096 ? sa.ngroups : 0;
+      sample_topk_kernel<<<(unsigned)Q, FIN_THREADS, (P + sc) * sizeof(uint64_t), st>>>(S, sa.ngroups, p.sample_k_out, P, sc, sample_vals_out);
       B200_LAUNCH_OK("sample_topk_kernel");
       return 0;
     }
@@ -1161,9 +1188,10 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
   B200_LAUNCH_OK("stream_scores_kernel<topk>");
   if (g_time_kernel) B200_CUDA_OK(cudaEventRecord(g_ev1, st));
   const int P = next_pow2(k);
-  topk_final_kernel<<<(unsigned)Q, FIN_THREADS, P * sizeof(uint64_t), st>>>(
+  const int fin_stage = P <= 1024 ? 1024 : 0;  // T + leftovers of a query usually are a few hundred keys
+  topk_final_kernel<<<(unsigned)Q, FIN_THREADS, (P + fin_stage) * sizeof(uint64_t), st>>>(
       p.g, V2, V2 == 2 ? 512 : (V2 == 1 ? 256 : 128 * NQ), V2 ? S2_SLOTS : 128 * NQ, ea.tlists, ea.meta, ea.lists, ea.left, p.cap,
-      k, P, row_offset, out_scores, out_ids);
+      k, P, fin_stage, row_offset, out_scores, out_ids);
   B200_LAUNCH_OK("topk_final_kernel");
   return 0;
 }
@@ -1220,10 +1248,13 @@ extern "C" size_t b200rec_topk_workspace_bytes(int64_t N, int64_t ld, int64_t Q,
 static int topk_dispatch(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k,
                          int64_t row_offset, const int64_t* exclude_indptr, const int32_t* exclude_rows,
                          const float* tau_init, float* out_scores, int64_t* out_ids, float* sample_vals_out,
+                         int sample_k_out, int shards,
                          void* workspace, size_t workspace_bytes, void* stream) {
   using namespace b200;
   TopkPlan p;
-  if (plan_topk(p, N, ld, Q, k)) return 1;
+  if (plan_topk(p, N, ld, Q, k, shards)) return 1;
+  if (shards > 1 && p.sample_m == 0 && plan_topk(p, N, ld, Q, k)) return 1;  // pooled density too thin for this shard
+  p.sample_k_out = sample_k_out;
   if (workspace_bytes < p.total()) return fail("topk: workspace too small (%zu < %zu)", workspace_bytes, p.total());
   if ((exclude_indptr == nullptr) != (exclude_rows == nullptr)) return fail("topk: exclusion CSR needs both arrays");
   if (sample_vals_out != nullptr && p.sample_m == 0) return fail("topk_sample: catalogue too small for a sampling pass");
@@ -1243,14 +1274,16 @@ extern "C" int b200rec_flat_ip_topk(const void* catalogue, int64_t N, int64_t ld
                                     size_t workspace_bytes, void* stream) {
   if (!catalogue || !queries || !out_scores || !out_ids || !workspace) return b200::fail("topk: null pointer");
   return topk_dispatch(catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, tau_init, out_scores,
-                       out_ids, nullptr, workspace, workspace_bytes, stream);
+                       out_ids, nullptr, k, 1, workspace, workspace_bytes, stream);
 }
 
 extern "C" int b200rec_topk_sample(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k,
-                                   float* out_vals, void* workspace, size_t workspace_bytes, void* stream) {
+                                   int k_out, int shards, float* out_vals, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
   if (!catalogue || !queries || !out_vals || !workspace) return b200::fail("topk_sample: null pointer");
-  return topk_dispatch(catalogue, N, ld, queries, Q, k, 0, nullptr, nullptr, nullptr, nullptr, nullptr, out_vals, workspace,
-                       workspace_bytes, stream);
+  if (k_out < 1 || k_out > k) return b200::fail("topk_sample: k_out must be in [1, k]");
+  return topk_dispatch(catalogue, N, ld, queries, Q, k, 0, nullptr, nullptr, nullptr, nullptr, nullptr, out_vals, k_out,
+                       shards < 1 ? 1 : shards, workspace, workspace_bytes, stream);
 }
 
 extern "C" int b200rec_topk_has_sample(int64_t N, int64_t ld, int64_t Q, int k) {
@@ -1268,8 +1301,10 @@ extern "C" int b200rec_topk_merge(const float* scores, const int64_t* ids, int p
   if (k_out < 1 || k_out > 2048) return fail("topk_merge: k_out must be in [1, 2048]");
   if ((int64_t)parts * k_in > INT32_MAX) return fail("topk_merge: too many candidates per query");
   const int P = next_pow2(k_out);
-  topk_merge_kernel<<<(unsigned)Q, FIN_THREADS, P * sizeof(uint64_t), reinterpret_cast<cudaStream_t>(stream)>>>(
-      scores, ids, parts, (long long)Q, k_in, k_out, P,
+  const int64_t n_in = (int64_t)parts * k_in;
+  const int sc = (n_in + P) * 8 <= 40960 ? (int)n_in : 0;
+  topk_merge_kernel<<<(unsigned)Q, FIN_THREADS, (P + sc) * sizeof(uint64_t), reinterpret_cast<cudaStream_t>(stream)>>>(
+      scores, ids, parts, (long long)Q, k_in, k_out, P, sc,
       (long long)(scores_part_stride > 0 ? scores_part_stride : Q * k_in),
       (long long)(ids_part_stride > 0 ? ids_part_stride : Q * k_in), out_scores, out_ids);
   B200_LAUNCH_OK("topk_merge_kernel");

@@ -9,6 +9,7 @@ the exchange on CPU with the oracle standing in for the CUDA kernels.
 """
 from __future__ import annotations
 
+import inspect
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -33,7 +34,7 @@ class ShardedFlatIndex:
 
     local_search(q, k, tau=None) -> (scores [Q,k] fp32, ids [Q,k] int64 with GLOBAL row ids, -1 padding)
     merge(scores [P,Q,k], ids [P,Q,k], k) -> (scores [Q,k], ids [Q,k])   order: score desc, id asc
-    local_sample(q, k) -> [Q,k] scores of k DISTINCT local rows per query, or None (optional).  When given, shards
+    local_sample(q, k[, k_out, shards]) -> [Q,k_out] scores of DISTINCT local rows per query, or None (optional).  When given, shards
         all-gather these and every shard starts from the k-th best of the union: a lower bound of the GLOBAL k-th
         score, so each GPU only collects candidates that can still reach the global top-k.
     """
@@ -43,6 +44,10 @@ class ShardedFlatIndex:
         self.merge = merge
         self.group = group
         self.local_sample = local_sample
+        # samplers may take (queries, k) or (queries, k, k_out, shards): the latter return k_out <= k values per query
+        # from a sample thinned for `shards` pooled shards
+        self._sample_takes_width = (local_sample is not None
+                                    and len(inspect.signature(local_sample).parameters) >= 4)
         self.packed_exchange = False   # set by from_device_index: needs a local_search that writes into `out`
         self._ids_cache = {}
 
@@ -56,16 +61,30 @@ class ShardedFlatIndex:
         def merge(s, i, k):
             return K.topk_merge(s, i, k)
 
-        def sample(q_op, k):
-            return index.sample_device(q_op, k) if index.has_sample_pass(q_op.shape[0], k) else None
+        def sample(q_op, k, k_out=None, shards=1):
+            if not index.has_sample_pass(q_op.shape[0], k):
+                return None
+            return index.sample_device(q_op, k, k_out, shards)
 
         obj = cls(local, merge, group, sample)
         obj.packed_exchange = True
         return obj
 
+    @staticmethod
+    def exchange_width(k: int, world: int) -> int:
+        """Sample maxima each shard contributes to the threshold exchange.  The union must hold >= k distinct rows for
+        its k-th best to bound the global k-th score from below; a shard owns about k/world of the union's top k
+        (binomial), so k/world + 4 sigma + 8 keeps the bound as tight as exchanging k per shard at a fraction of the
+        bytes (world 8, k 100: 32 instead of 100)."""
+        if world <= 1:
+            return k
+        mean = -(-k // world)
+        return min(k, mean + 4 * int(mean ** 0.5) + 8)
+
     def _shared_thresholds(self, queries, k: int, world: int):
         """k-th best of the union of every shard's sample: [Q] lower bounds of the global k-th score (or None)."""
-        vals = self.local_sample(queries, k)
+        kx = self.exchange_width(k, world)
+        vals = self.local_sample(queries, k, kx, world) if self._sample_takes_width else self.local_sample(queries, k)
         shape_key = ("use", int(queries.shape[0]), k)
         if shape_key not in self._ids_cache:
             # every shard must take the same branch: agree once per (batch, k) shape (one host sync, then cached)
@@ -76,13 +95,14 @@ class ShardedFlatIndex:
             self._ids_cache[shape_key] = int(flag.item()) == 1
         if not self._ids_cache[shape_key] or vals is None:
             return None
-        q = vals.shape[0]
-        allv = torch.empty((world * q, k), dtype=vals.dtype, device=vals.device)
-        dist.all_gather_into_tensor(allv, vals.contiguous(), group=self.group)
-        key = (world, q, k, str(vals.device))
+        q, kv = vals.shape
+        key = (world, q, kv, str(vals.device))
         if key not in self._ids_cache:  # any distinct ids will do: only the merged scores are used
-            self._ids_cache[key] = torch.arange(world * q * k, dtype=torch.int64, device=vals.device).view(world, q, k)
-        top, _ = self.merge(allv.view(world, q, k), self._ids_cache[key], k)
+            self._ids_cache[key] = (torch.arange(world * q * kv, dtype=torch.int64, device=vals.device).view(world, q, kv),
+                                    torch.empty((world * q, kv), dtype=vals.dtype, device=vals.device))
+        ids, allv = self._ids_cache[key]
+        dist.all_gather_into_tensor(allv, vals.contiguous(), group=self.group)
+        top, _ = self.merge(allv.view(world, q, kv), ids, k)
         return top[:, k - 1].contiguous()
 
     def search(self, queries, k: int):

@@ -108,12 +108,15 @@ def topk_has_sample(n: int, ld: int, q: int, k: int) -> bool:
     return bool(N.lib().b200rec_topk_has_sample(n, ld, q, k))
 
 
-def topk_sample(catalogue: torch.Tensor, queries: torch.Tensor, k: int, workspace: torch.Tensor) -> torch.Tensor:
-    """Sampling pass only: [Q,k] largest group maxima per query (what row shards exchange before the main pass)."""
+def topk_sample(catalogue: torch.Tensor, queries: torch.Tensor, k: int, workspace: torch.Tensor,
+                k_out: Optional[int] = None, shards: int = 1) -> torch.Tensor:
+    """Sampling pass only: [Q,k_out] largest group maxima per query (what row shards exchange before the main pass).
+    `shards` row shards pool their samples, so each samples 1/shards as densely."""
     n, ld, q = catalogue.shape[0], catalogue.stride(0), queries.shape[0]
-    vals = torch.empty((q, k), dtype=torch.float32, device=catalogue.device)
-    N.check(N.lib().b200rec_topk_sample(N.ptr(catalogue), n, ld, N.ptr(queries), q, k, N.ptr(vals), N.ptr(workspace),
-                                        workspace.numel(), N.stream()), "topk_sample")
+    k_out = k if k_out is None else k_out
+    vals = torch.empty((q, k_out), dtype=torch.float32, device=catalogue.device)
+    N.check(N.lib().b200rec_topk_sample(N.ptr(catalogue), n, ld, N.ptr(queries), q, k, k_out, shards, N.ptr(vals),
+                                        N.ptr(workspace), workspace.numel(), N.stream()), "topk_sample")
     return vals
 
 

@@ -149,9 +149,9 @@ class FlatIPDeviceIndex:
     def has_sample_pass(self, nq: int, k: int) -> bool:
         return self.ntotal > 0 and K.topk_has_sample(self.ntotal, self.ld, nq, k)
 
-    def sample_device(self, q_op: torch.Tensor, k: int) -> torch.Tensor:
-        """Sampling pass only: the k largest group maxima per query [nq, k] (exchanged between row shards)."""
-        return K.topk_sample(self._cat[: self.ntotal], q_op, k, self._workspace(q_op.shape[0], k))
+    def sample_device(self, q_op: torch.Tensor, k: int, k_out: Optional[int] = None, shards: int = 1) -> torch.Tensor:
+        """Sampling pass only: the k_out largest group maxima per query [nq, k_out] (exchanged between row shards)."""
+        return K.topk_sample(self._cat[: self.ntotal], q_op, k, self._workspace(q_op.shape[0], k), k_out, shards)
 
     def search_device(self, q_op: torch.Tensor, k: int, exclude_indptr=None, exclude_rows=None, tau_init=None,
                       out=None):

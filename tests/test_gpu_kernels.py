@@ -123,6 +123,57 @@ def test_flat_ip_topk_ties_and_exclusion():
     assert np.array_equal(Ig.cpu().numpy(), rI)
 
 
+@pytest.mark.parametrize("sched", ["default", "0", "3"])
+@pytest.mark.parametrize("N,Q,D,k", [(300_000, 1500, 64, 20), (150_000, 4500, 64, 10)])
+def test_flat_ip_topk_work_splits_bit_exact(monkeypatch, sched, N, Q, D, k):
+    """The 2-CTA kernel's three work decompositions (time-aligned strided sweep with idle leftover units, the same with
+    leftover units that change supertile and hand their lists over, contiguous split) on integer data: exact scores,
+    massive ties, so the total order (score desc, row asc) must come out bit for bit."""
+    from b200rec import kernels as KR
+    if sched != "default":
+        monkeypatch.setenv("B200REC_SCHED", sched)
+    rng = np.random.default_rng(N + Q)
+    base = rng.integers(-3, 4, size=(N, D)).astype(np.float32)
+    qry = rng.integers(-3, 4, size=(Q, D)).astype(np.float32)
+    rD, rI = _oracle_topk(base, qry, k)
+    Dg, Ig = KR.flat_ip_topk(torch.from_numpy(base).cuda().to(torch.bfloat16),
+                             torch.from_numpy(qry).cuda().to(torch.bfloat16), k)
+    torch.cuda.synchronize()
+    assert np.array_equal(Dg.cpu().numpy(), rD)
+    assert np.array_equal(Ig.cpu().numpy(), rI)
+
+
+def test_flat_ip_topk_more_supertiles_than_units():
+    """Q so large that there are more 512-query supertiles than CTA pairs: contiguous split, units that cross several
+    supertiles."""
+    from b200rec import kernels as KR
+    rng = np.random.default_rng(77)
+    N, Q, D, k = 12_000, 38_500, 64, 10
+    base = rng.integers(-3, 4, size=(N, D)).astype(np.float32)
+    qry = rng.integers(-3, 4, size=(Q, D)).astype(np.float32)
+    rD, rI = _oracle_topk(base, qry, k)
+    Dg, Ig = KR.flat_ip_topk(torch.from_numpy(base).cuda().to(torch.bfloat16),
+                             torch.from_numpy(qry).cuda().to(torch.bfloat16), k)
+    torch.cuda.synchronize()
+    assert np.array_equal(Dg.cpu().numpy(), rD)
+    assert np.array_equal(Ig.cpu().numpy(), rI)
+
+
+def test_flat_ip_topk_large_k_generic_merge():
+    """k + list > 256 keys: the helper warps take the shared-memory histogram select instead of the register one."""
+    from b200rec import kernels as KR
+    from oracle.flat_ip import bf16_round, normalize_L2
+    rng = np.random.default_rng(99)
+    N, Q, D, k = 120_000, 300, 64, 300
+    cat = bf16_round(normalize_L2(rng.standard_normal((N, D)).astype(np.float32)))
+    qry = bf16_round(normalize_L2(rng.standard_normal((Q, D)).astype(np.float32)))
+    rD, rI = _oracle_topk(cat, qry, k)
+    Dg, Ig = KR.flat_ip_topk(torch.from_numpy(cat).cuda().to(torch.bfloat16),
+                             torch.from_numpy(qry).cuda().to(torch.bfloat16), k)
+    torch.cuda.synchronize()
+    _check_topk(Dg, Ig, rD, rI, cat, qry)
+
+
 def test_topk_merge_matches_oracle():
     from b200rec import kernels as KR
     from oracle.flat_ip import merge_topk
@@ -155,7 +206,10 @@ def test_sharded_search_with_shared_thresholds_single_gpu():
         shards.append(ix)
     q_op = shards[0].prepare_queries(qry)
     assert all(ix.has_sample_pass(Q, k) for ix in shards)
-    vals = torch.stack([ix.sample_device(q_op, k) for ix in shards])            # [2, Q, k]
+    from b200rec.dist import ShardedFlatIndex
+    kx = ShardedFlatIndex.exchange_width(k, 2)
+    assert k // 2 < kx <= k
+    vals = torch.stack([ix.sample_device(q_op, k, kx, 2) for ix in shards])     # [2, Q, kx]: thinned sample, kx maxima each
     ids = torch.arange(vals.numel(), device="cuda").view_as(vals)
     tau = KR.topk_merge(vals.contiguous(), ids.contiguous(), k)[0][:, k - 1].contiguous()
     assert (tau.cpu().numpy() <= rD[:, k - 1] + 1e-6).all(), "shared threshold must be a lower bound of the k-th score"
