@@ -61,7 +61,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "25"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -141,7 +141,7 @@ def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    rows, queries = 1_000_000, 128
+    rows, queries = 1_000_000, 2048
     vals = []
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_retrieval_baseline(rows // 4, 32, threads)
@@ -264,7 +264,7 @@ def cpu_train_baseline(B: int, FD: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-train", action="store_true", help="skip the config-2 training block")
@@ -372,13 +372,19 @@ def main():
             train = run_train_block(device, max(steps, 10), warmup, not args.no_cpu_baseline)
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            rows, queries = 1_000_000, 128
+            rows, queries = 1_000_000, 2048
             v, dt = cpu_retrieval_baseline(rows, queries, threads)
             cpu = {"value": v, "unit": "queries/s", "cores": threads, "kind": "port",
                    "sample": f"{queries} queries x {rows} rows fp32 ({dt:.1f} s), oracle/flat_ip.py numpy sgemm + exact "
                              f"select (faiss-cpu restated), QPS scaled linearly to {N_ITEMS} rows"}
     if rank == 0:
         peaks = _peaks()
+        traffic = None  # DRAM bytes of one launch of the dominant kernel, from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "r01_topk_traffic.json")
+        if world == 1 and os.path.exists(tpath):
+            with open(tpath) as fh:
+                tj = json.load(fh)
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         n_local = (N_ITEMS + world - 1) // world
         flops = 2.0 * N_QUERIES * n_local * DIM
         achieved = flops / (kernel_ms * 1e-3) / 1e12
@@ -394,7 +400,8 @@ def main():
                 "clocks": clocks,
                 "roofline": {"kernel": "stream_scores_kernel<topk> (scoring GEMM fused with top-K select)",
                              "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                             "frac": achieved / peaks["tflops"], "traffic": None, "kernel_ms": kernel_ms,
+                             "frac": achieved / peaks["tflops"], "traffic": traffic, "kernel_ms": kernel_ms,
+                             "algorithmic_bytes": n_local * DIM * 2 + N_QUERIES * DIM * 2 + N_QUERIES * TOPK * 12,
                              "flops_per_launch": flops, "peak_source": peaks["source"],
                              "hbm_floor_ms": n_local * DIM * 2 / (peaks["hbm_gbs"] * 1e9) * 1e3},
                 "cpu_baseline": cpu, "train": train}
