@@ -73,6 +73,16 @@ int b200rec_flat_ip_topk(const void* catalogue, int64_t N, int64_t ld, const voi
 int b200rec_topk_sample(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k, int k_out,
                         int shards, float* out_vals, void* workspace, size_t workspace_bytes, void* stream);
 int b200rec_topk_has_sample(int64_t N, int64_t ld, int64_t Q, int k);
+/* Fan-out variants for row-sharded search over NVLink peer memory: the select kernels store every result row to n_dst
+ * (<= 16) destinations — dst_*[d] are device pointers to [Q,k] (resp. [Q,k_out]) arrays, typically this shard's slot in
+ * each GPU's gather buffer (peer-mapped symmetric memory) — so the kernel that produces the local top-k is also the
+ * all-gather.  The caller orders the exchange with a cross-GPU barrier on the same stream.  dst[0] may be local. */
+int b200rec_flat_ip_topk_fanout(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k,
+                                int64_t row_offset, const float* tau_init, int n_dst, void* const* dst_scores,
+                                void* const* dst_ids, void* workspace, size_t workspace_bytes, void* stream);
+int b200rec_topk_sample_fanout(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k,
+                               int k_out, int shards, int n_dst, void* const* dst_vals, void* workspace,
+                               size_t workspace_bytes, void* stream);
 /* k-way merge of `parts` candidate lists [parts][Q][k_in] (id < 0 = empty, ids < 2^32) into the global top k_out under
  * the same order: the exchange step after the all-gather of per-GPU results.  *_part_stride = element distance
  * between consecutive parts (0 = dense, Q*k_in); non-dense strides let one all-gather carry scores and ids together. */

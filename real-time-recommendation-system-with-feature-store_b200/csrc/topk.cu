@@ -781,6 +781,16 @@ __device__ __forceinline__ void block_select_sort(const Loader& load, int n, int
   }
 }
 
+// Result fan-out: the per-query result rows are stored to `n` destinations — the caller's own buffer and, in row-sharded
+// search, the slot of this shard in every peer GPU's gather buffer (peer-mapped NVLink addresses).  The select kernel
+// then IS the all-gather: no separate collective launch, the stores ride NVLink while other queries are still selected.
+constexpr int FAN_MAX = 16;
+struct OutFan {
+  int n;
+  float* s[FAN_MAX];
+  int64_t* i[FAN_MAX];
+};
+
 __device__ __forceinline__ void write_result(const uint64_t* skeys, int k_out, int64_t row_offset, float* out_s,
                                              int64_t* out_i) {
   for (int i = threadIdx.x; i < k_out; i += FIN_THREADS) {
@@ -819,7 +829,7 @@ __global__ void __launch_bounds__(FIN_THREADS)
 topk_final_kernel(const StreamGeom g, int v2, int qs /*queries per supertile*/, int slots /*per CTA*/,
                   const uint64_t* __restrict__ tlists, const QMeta* __restrict__ meta,
                   const uint64_t* __restrict__ lists, const uint32_t* __restrict__ left, int cap, int k, int P,
-                  int stage_cap, int64_t row_offset, float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+                  int stage_cap, int64_t row_offset, const OutFan fan) {
   extern __shared__ uint64_t fin_smem[];
   __shared__ uint32_t hist[256];
   __shared__ int s_misc[8];
@@ -868,7 +878,8 @@ topk_final_kernel(const StreamGeom g, int v2, int qs /*queries per supertile*/, 
   const int n = s_misc[6];
   __syncthreads();
   block_select_sort(ld, n, k, fin_smem, P, hist, s_misc, fin_smem + P, stage_cap);
-  write_result(fin_smem, k, row_offset, out_scores + (size_t)q * k, out_ids + (size_t)q * k);
+  for (int d = 0; d < fan.n; ++d)
+    write_result(fin_smem, k, row_offset, fan.s[d] + (size_t)q * k, fan.i[d] + (size_t)q * k);
 }
 
 // per-query k largest group maxima of the sampling pass (descending; -FLT_MAX padding): what shards exchange so that
@@ -880,7 +891,7 @@ struct FloatRowLoader {
   }
 };
 __global__ void __launch_bounds__(FIN_THREADS)
-sample_topk_kernel(const float* __restrict__ S, int m, int k, int P, int stage_cap, float* __restrict__ out_vals) {
+sample_topk_kernel(const float* __restrict__ S, int m, int k, int P, int stage_cap, const OutFan fan) {
   extern __shared__ uint64_t fin_smem[];
   __shared__ uint32_t hist[256];
   __shared__ int s_misc[8];
@@ -889,7 +900,8 @@ sample_topk_kernel(const float* __restrict__ S, int m, int k, int P, int stage_c
   block_select_sort(ld, m, k, fin_smem, P, hist, s_misc, fin_smem + P, stage_cap);
   for (int i = threadIdx.x; i < k; i += FIN_THREADS) {
     const uint64_t key = fin_smem[i];
-    out_vals[(size_t)q * k + i] = key == 0ull ? -FLT_MAX : ord_f32((uint32_t)(key >> 32));
+    const float v = key == 0ull ? -FLT_MAX : ord_f32((uint32_t)(key >> 32));
+    for (int d = 0; d < fan.n; ++d) fan.s[d][(size_t)q * k + i] = v;
   }
 }
 
@@ -1109,7 +1121,15 @@ template <int NQ, int BN, int V2>
 static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q,
                        int k, int64_t row_offset, const int64_t* excl_indptr, const int32_t* excl_rows,
                        float* out_scores, int64_t* out_ids, void* workspace, cudaStream_t st,
-                       const float* tau_init, float* sample_vals_out) {
+                       const float* tau_init, float* sample_vals_out, const OutFan* fan_in) {
+  OutFan fan;
+  if (fan_in != nullptr) {
+    fan = *fan_in;
+  } else {
+    fan.n = 1;
+    fan.s[0] = sample_vals_out != nullptr ? sample_vals_out : out_scores;
+    fan.i[0] = out_ids;
+  }
   CUtensorMap tq, tx;
   if (make_tmap_bf16_2d(&tq, queries, (uint64_t)Q, (uint64_t)ld, (uint64_t)ld, 128)) return 1;
   constexpr int XBOX = V2 == 1 ? 128 : (V2 == 2 ? 64 : BN);  // rows per TMA box (a CTA of a pair loads its half)
@@ -1159,7 +1179,7 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
     if (sample_vals_out != nullptr) {  // sampling only: hand the k best group maxima per query to the caller
       const int P = next_pow2(k);
       const int sc = sa.ngroups <= 4096 ? sa.ngroups : 0;
-      sample_topk_kernel<<<(unsigned)Q, FIN_THREADS, (P + sc) * sizeof(uint64_t), st>>>(S, sa.ngroups, p.sample_k_out, P, sc, sample_vals_out);
+      sample_topk_kernel<<<(unsigned)Q, FIN_THREADS, (P + sc) * sizeof(uint64_t), st>>>(S, sa.ngroups, p.sample_k_out, P, sc, fan);
       B200_LAUNCH_OK("sample_topk_kernel");
       return 0;
     }
@@ -1191,7 +1211,7 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
   const int fin_stage = P <= 1024 ? 1024 : 0;  // T + leftovers of a query usually are a few hundred keys
   topk_final_kernel<<<(unsigned)Q, FIN_THREADS, (P + fin_stage) * sizeof(uint64_t), st>>>(
       p.g, V2, V2 == 2 ? 512 : (V2 == 1 ? 256 : 128 * NQ), V2 ? S2_SLOTS : 128 * NQ, ea.tlists, ea.meta, ea.lists, ea.left, p.cap,
-      k, P, fin_stage, row_offset, out_scores, out_ids);
+      k, P, fin_stage, row_offset, fan);
   B200_LAUNCH_OK("topk_final_kernel");
   return 0;
 }
@@ -1248,7 +1268,7 @@ extern "C" size_t b200rec_topk_workspace_bytes(int64_t N, int64_t ld, int64_t Q,
 static int topk_dispatch(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k,
                          int64_t row_offset, const int64_t* exclude_indptr, const int32_t* exclude_rows,
                          const float* tau_init, float* out_scores, int64_t* out_ids, float* sample_vals_out,
-                         int sample_k_out, int shards,
+                         int sample_k_out, int shards, const b200::OutFan* fan,
                          void* workspace, size_t workspace_bytes, void* stream) {
   using namespace b200;
   TopkPlan p;
@@ -1259,7 +1279,7 @@ static int topk_dispatch(const void* catalogue, int64_t N, int64_t ld, const voi
   if ((exclude_indptr == nullptr) != (exclude_rows == nullptr)) return fail("topk: exclusion CSR needs both arrays");
   if (sample_vals_out != nullptr && p.sample_m == 0) return fail("topk_sample: catalogue too small for a sampling pass");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define B200_TOPK_ARGS p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st, tau_init, sample_vals_out
+#define B200_TOPK_ARGS p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st, tau_init, sample_vals_out, fan
   if (p.v2 == 2) return launch_topk<2, 128, 2>(B200_TOPK_ARGS);
   if (p.v2 == 1) return launch_topk<2, 128, 1>(B200_TOPK_ARGS);
   if (p.nq == 2) return launch_topk<2, 128, 0>(B200_TOPK_ARGS);
@@ -1274,7 +1294,7 @@ extern "C" int b200rec_flat_ip_topk(const void* catalogue, int64_t N, int64_t ld
                                     size_t workspace_bytes, void* stream) {
   if (!catalogue || !queries || !out_scores || !out_ids || !workspace) return b200::fail("topk: null pointer");
   return topk_dispatch(catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, tau_init, out_scores,
-                       out_ids, nullptr, k, 1, workspace, workspace_bytes, stream);
+                       out_ids, nullptr, k, 1, nullptr, workspace, workspace_bytes, stream);
 }
 
 extern "C" int b200rec_topk_sample(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k,
@@ -1283,7 +1303,41 @@ extern "C" int b200rec_topk_sample(const void* catalogue, int64_t N, int64_t ld,
   if (!catalogue || !queries || !out_vals || !workspace) return b200::fail("topk_sample: null pointer");
   if (k_out < 1 || k_out > k) return b200::fail("topk_sample: k_out must be in [1, k]");
   return topk_dispatch(catalogue, N, ld, queries, Q, k, 0, nullptr, nullptr, nullptr, nullptr, nullptr, out_vals, k_out,
-                       shards < 1 ? 1 : shards, workspace, workspace_bytes, stream);
+                       shards < 1 ? 1 : shards, nullptr, workspace, workspace_bytes, stream);
+}
+
+static int make_fan(b200::OutFan& fan, int n_dst, void* const* dst_scores, void* const* dst_ids, bool want_ids) {
+  if (n_dst < 1 || n_dst > b200::FAN_MAX) return b200::fail("topk fan-out: n_dst must be in [1, %d]", b200::FAN_MAX);
+  if (!dst_scores || (want_ids && !dst_ids)) return b200::fail("topk fan-out: null destination table");
+  fan.n = n_dst;
+  for (int d = 0; d < n_dst; ++d) {
+    fan.s[d] = reinterpret_cast<float*>(dst_scores[d]);
+    fan.i[d] = want_ids ? reinterpret_cast<int64_t*>(dst_ids[d]) : nullptr;
+    if (!fan.s[d] || (want_ids && !fan.i[d])) return b200::fail("topk fan-out: null destination %d", d);
+  }
+  return 0;
+}
+
+extern "C" int b200rec_flat_ip_topk_fanout(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q,
+                                           int k, int64_t row_offset, const float* tau_init, int n_dst,
+                                           void* const* dst_scores, void* const* dst_ids, void* workspace,
+                                           size_t workspace_bytes, void* stream) {
+  if (!catalogue || !queries || !workspace) return b200::fail("topk: null pointer");
+  b200::OutFan fan;
+  if (make_fan(fan, n_dst, dst_scores, dst_ids, true)) return 1;
+  return topk_dispatch(catalogue, N, ld, queries, Q, k, row_offset, nullptr, nullptr, tau_init, fan.s[0], fan.i[0], nullptr, k,
+                       1, &fan, workspace, workspace_bytes, stream);
+}
+
+extern "C" int b200rec_topk_sample_fanout(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q,
+                                          int k, int k_out, int shards, int n_dst, void* const* dst_vals, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+  if (!catalogue || !queries || !workspace) return b200::fail("topk_sample: null pointer");
+  if (k_out < 1 || k_out > k) return b200::fail("topk_sample: k_out must be in [1, k]");
+  b200::OutFan fan;
+  if (make_fan(fan, n_dst, dst_vals, nullptr, false)) return 1;
+  return topk_dispatch(catalogue, N, ld, queries, Q, k, 0, nullptr, nullptr, nullptr, nullptr, nullptr, fan.s[0], k_out,
+                       shards < 1 ? 1 : shards, &fan, workspace, workspace_bytes, stream);
 }
 
 extern "C" int b200rec_topk_has_sample(int64_t N, int64_t ld, int64_t Q, int k) {

@@ -29,6 +29,33 @@ def _world() -> Tuple[int, int]:
     return 1, 0
 
 
+class _PeerExchange:
+    """Symmetric (peer-mapped) gather buffers of one (batch, k) shape: every rank owns
+    [thresholds: world x q x kx fp32 | scores: world x q x k fp32 | ids: world x q x k int64] and knows the address of
+    its own slot inside every peer's copy, so the select kernels store their rows straight into all gather buffers over
+    NVLink (b200rec_*_fanout) and the only collective left is a device-side barrier."""
+
+    def __init__(self, group, q: int, k: int, kx: int, device):
+        import torch.distributed._symmetric_memory as symm
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        pad = lambda n: (n + 255) // 256 * 256
+        sec = [pad(world * q * kx * 4), pad(world * q * k * 4), pad(world * q * k * 8)]
+        off = [0, sec[0], sec[0] + sec[1]]
+        self.buf = symm.empty(sum(sec), dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        base = [int(p) for p in self.hdl.buffer_ptrs]
+        self.tau_dst = [base[p] + off[0] + rank * q * kx * 4 for p in range(world)]
+        self.s_dst = [base[p] + off[1] + rank * q * k * 4 for p in range(world)]
+        self.i_dst = [base[p] + off[2] + rank * q * k * 8 for p in range(world)]
+        self.tau_all = self.buf[off[0]: off[0] + world * q * kx * 4].view(torch.float32).view(world, q, kx)
+        self.s_all = self.buf[off[1]: off[1] + world * q * k * 4].view(torch.float32).view(world, q, k)
+        self.i_all = self.buf[off[2]: off[2] + world * q * k * 8].view(torch.int64).view(world, q, k)
+        self.tau_ids = torch.arange(world * q * kx, dtype=torch.int64, device=device).view(world, q, kx)
+
+    def barrier(self, channel: int) -> None:
+        self.hdl.barrier(channel=channel)
+
+
 class ShardedFlatIndex:
     """Row-sharded exact inner-product index: `search` returns the GLOBAL top-k on every rank.
 
@@ -49,10 +76,11 @@ class ShardedFlatIndex:
         self._sample_takes_width = (local_sample is not None
                                     and len(inspect.signature(local_sample).parameters) >= 4)
         self.packed_exchange = False   # set by from_device_index: needs a local_search that writes into `out`
+        self.peer_index = None         # set by from_device_index(peer_exchange=True): fan-out stores over NVLink
         self._ids_cache = {}
 
     @classmethod
-    def from_device_index(cls, index, group=None) -> "ShardedFlatIndex":
+    def from_device_index(cls, index, group=None, peer_exchange: bool = True) -> "ShardedFlatIndex":
         from . import kernels as K
 
         def local(q_op, k, tau=None, out=None):
@@ -68,7 +96,39 @@ class ShardedFlatIndex:
 
         obj = cls(local, merge, group, sample)
         obj.packed_exchange = True
+        obj.peer_index = index if peer_exchange else None
         return obj
+
+    def _peer(self, q: int, k: int, world: int, device):
+        """Peer gather buffers for this shape, or None when symmetric memory is unavailable / a shard has no sampling
+        pass (then the NCCL all-gather path below runs).  Every rank takes the same branch."""
+        key = ("peer", q, k)
+        if key not in self._ids_cache:
+            px = None
+            ok = 1 if self.peer_index.has_sample_pass(q, k) else 0
+            if dist.get_backend(self.group) != "nccl":
+                ok = 0
+            if ok:
+                try:
+                    px = _PeerExchange(self.group, q, k, self.exchange_width(k, world), device)
+                except Exception as exc:  # noqa: BLE001 - any setup failure just selects the NCCL path
+                    import logging
+                    logging.getLogger("b200rec").warning("peer-memory exchange unavailable (%s): using NCCL all-gather", exc)
+                    ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            self._ids_cache[key] = px if int(flag.item()) == 1 else None
+        return self._ids_cache[key]
+
+    def _search_peer(self, px: "_PeerExchange", queries, k: int, world: int):
+        ix = self.peer_index
+        ix.sample_fanout(queries, k, px.tau_all.shape[2], world, px.tau_dst)     # (1) sample -> every gather buffer
+        px.barrier(0)
+        top, _ = self.merge(px.tau_all, px.tau_ids, k)                           # (2) k-th best of the pooled sample
+        tau = top[:, k - 1].contiguous()
+        ix.search_fanout(queries, k, tau, px.s_dst, px.i_dst)                    # (3) local top-k -> every gather buffer
+        px.barrier(1)
+        return self.merge(px.s_all, px.i_all, k)                                 # (4) k-way select
 
     @staticmethod
     def exchange_width(k: int, world: int) -> int:
@@ -109,6 +169,10 @@ class ShardedFlatIndex:
         world, _ = _world()
         if world == 1:
             return self.local_search(queries, k)
+        if self.peer_index is not None:
+            px = self._peer(int(queries.shape[0]), k, world, queries.device)
+            if px is not None:
+                return self._search_peer(px, queries, k, world)
         tau = self._shared_thresholds(queries, k, world) if self.local_sample is not None else None
         q = int(queries.shape[0])
         if self.packed_exchange and (q * k) % 2 == 0:

@@ -104,6 +104,30 @@ def flat_ip_topk(catalogue: torch.Tensor, queries: torch.Tensor, k: int, row_off
     return scores, ids
 
 
+def _ptr_table(ptrs):
+    import ctypes
+    return (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
+def flat_ip_topk_fanout(catalogue: torch.Tensor, queries: torch.Tensor, k: int, row_offset: int,
+                        tau_init: Optional[torch.Tensor], dst_scores, dst_ids, workspace: torch.Tensor) -> None:
+    """flat_ip_topk whose [Q,k] result rows are stored to every (dst_scores[d], dst_ids[d]) device address — this shard's
+    slot in each GPU's gather buffer (peer-mapped symmetric memory): the select kernel doubles as the all-gather."""
+    n, ld, q = catalogue.shape[0], catalogue.stride(0), queries.shape[0]
+    N.check(N.lib().b200rec_flat_ip_topk_fanout(N.ptr(catalogue), n, ld, N.ptr(queries), q, k, row_offset,
+                                                N.ptr(tau_init), len(dst_scores), _ptr_table(dst_scores),
+                                                _ptr_table(dst_ids), N.ptr(workspace), workspace.numel(), N.stream()),
+            "flat_ip_topk_fanout")
+
+
+def topk_sample_fanout(catalogue: torch.Tensor, queries: torch.Tensor, k: int, k_out: int, shards: int, dst_vals,
+                       workspace: torch.Tensor) -> None:
+    n, ld, q = catalogue.shape[0], catalogue.stride(0), queries.shape[0]
+    N.check(N.lib().b200rec_topk_sample_fanout(N.ptr(catalogue), n, ld, N.ptr(queries), q, k, k_out, shards,
+                                               len(dst_vals), _ptr_table(dst_vals), N.ptr(workspace),
+                                               workspace.numel(), N.stream()), "topk_sample_fanout")
+
+
 def topk_has_sample(n: int, ld: int, q: int, k: int) -> bool:
     return bool(N.lib().b200rec_topk_has_sample(n, ld, q, k))
 

@@ -153,6 +153,15 @@ class FlatIPDeviceIndex:
         """Sampling pass only: the k_out largest group maxima per query [nq, k_out] (exchanged between row shards)."""
         return K.topk_sample(self._cat[: self.ntotal], q_op, k, self._workspace(q_op.shape[0], k), k_out, shards)
 
+    def sample_fanout(self, q_op: torch.Tensor, k: int, k_out: int, shards: int, dst_vals) -> None:
+        """Sampling pass whose [nq, k_out] maxima are stored to every address in dst_vals (peer gather buffers)."""
+        K.topk_sample_fanout(self._cat[: self.ntotal], q_op, k, k_out, shards, dst_vals, self._workspace(q_op.shape[0], k))
+
+    def search_fanout(self, q_op: torch.Tensor, k: int, tau_init, dst_scores, dst_ids) -> None:
+        """Local top-k (global row ids) stored to every (dst_scores[d], dst_ids[d]) address (peer gather buffers)."""
+        K.flat_ip_topk_fanout(self._cat[: self.ntotal], q_op, k, self.row_offset, tau_init, dst_scores, dst_ids,
+                              self._workspace(q_op.shape[0], k))
+
     def search_device(self, q_op: torch.Tensor, k: int, exclude_indptr=None, exclude_rows=None, tau_init=None,
                       out=None):
         """q_op: bf16 operand [nq, ld] on the device -> (D, I) device tensors (written into `out` when given)."""

@@ -12,7 +12,7 @@ cat = torch.nn.functional.normalize(torch.randn(N, D, device=dev, generator=g), 
 qry = torch.nn.functional.normalize(torch.randn(Q, D, device=dev, generator=g), dim=1)
 lo, hi = shard_bounds(N, world, rank)
 ix = FlatIPDeviceIndex(D, storage="bf16", device=dev, row_offset=lo); ix.add_bf16_rows(cat[lo:hi].contiguous())
-sh = ShardedFlatIndex.from_device_index(ix)
+sh = ShardedFlatIndex.from_device_index(ix, peer_exchange=os.environ.get("PEER", "1") == "1")
 qo = ix.prepare_queries(qry, normalize=False)
 s, i = sh.search(qo, k); torch.cuda.synchronize()
 full = FlatIPDeviceIndex(D, storage="bf16", device=dev); full.add_bf16_rows(cat)
@@ -25,6 +25,7 @@ for _ in range(5): sh.search(qo, k)
 torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
 for _ in range(20): sh.search(qo, k)
 torch.cuda.synchronize(); dist.barrier()
+if rank == 0: print(f"peer exchange active: {any(k_[0] == 'peer' and v is not None for k_, v in sh._ids_cache.items() if isinstance(k_, tuple))}")
 if rank == 0: print(f"sharded search N={N}: {(time.perf_counter()-t0)/20*1e3:.3f} ms/batch", flush=True)
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

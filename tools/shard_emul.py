@@ -36,3 +36,20 @@ for it in range(iters + 5):
     if it >= 5:
         for j in range(len(names)): acc[j] += ev[j].elapsed_time(ev[j + 1])
 print(f"{G}-way shard ({shards[0].ntotal} rows), exchange width {kx}: " + ", ".join(f"{n} {a/iters*1e3:.0f}us" for n, a in zip(names, acc)) + f" | total {sum(acc)/iters:.3f} ms (+2 all-gathers)", flush=True)
+import ctypes
+from b200rec import _native as NV
+lib = NV.lib()
+os.environ["B200REC_TOPK_DEBUG"] = "2"
+buf = (ctypes.c_ulonglong * 24)()
+ix.search_device(qo, k, tau_init=tau); torch.cuda.synchronize()
+lib.b200rec_debug_topk_stats16(buf, 1)
+ix.search_device(qo, k, tau_init=tau); torch.cuda.synchronize()
+lib.b200rec_debug_topk_stats16(buf, 0)
+ends = (ctypes.c_ulonglong * 512)(); lib.b200rec_debug_topk_cta_end(ends)
+start = (~buf[5]) & 0xFFFFFFFFFFFFFFFF
+span = (buf[7] - start) / 1e3
+tiles = max(buf[20], 1)
+d = sorted((ends[i] - start) / 1e3 for i in range(0, 144, 2))
+print(f"main kernel with pooled tau: span {span:.0f} us @ {buf[6]} MHz; unit end times us: min {d[0]:.0f} median {d[len(d)//2]:.0f} max {d[-1]:.0f}")
+print(f"  appends/query {buf[0]/Q:.0f}, requests/query {buf[1]/Q:.1f}, entries/warp-tile {buf[9]/tiles:.3f}, cycles/entry {buf[8]/max(buf[9],1):.0f}, "
+      f"MMA wait-acc {buf[16]/72/(tiles/(144*8)):.0f} cyc/tile, epilogue consume {buf[19]/tiles:.0f} cyc/tile, wait {buf[18]/tiles:.0f}")
