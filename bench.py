@@ -164,8 +164,11 @@ def run_reference(args, rank: int, world: int):
 
 
 # ------------------------------------------------------------------------------------------------ training block
-def run_train_block(device, steps: int, warmup: int, cpu_baseline: bool):
-    """BASELINE config 2: 1 M users x 100 K items, dim 64, batch 8192, in-batch negatives, one B200."""
+def run_train_block(device, steps: int, warmup: int, cpu_baseline: bool, world: int = 1, rank: int = 0):
+    """BASELINE config 2: 1 M users x 100 K items, dim 64, batch 8192 PER GPU, in-batch negatives.  world > 1: exact data
+    parallel (b200rec.dist.DataParallel: BatchNorm statistics and in-batch negatives over the global batch, summed
+    gradients) — the same numbers one process would produce on the world x 8192 batch."""
+    import torch.distributed as dist
     from b200rec import _native as N
     from b200rec.trainer import TwoTowerTrainer
     from b200rec.training_utils import create_two_tower_model_for_training
@@ -177,8 +180,12 @@ def run_train_block(device, steps: int, warmup: int, cpu_baseline: bool):
     model = create_two_tower_model_for_training(FD, FD, cfg)
     trainer = TwoTowerTrainer(model, [], [], {"learning_rate": 1e-3, "weight_decay": 1e-5,
                                               "checkpoint_dir": "/tmp/b200rec_bench_ckpt"}, device=str(device))
+    if world > 1:
+        from b200rec.dist import DataParallel
+        DataParallel(model)
     model.train()
-    rng = np.random.default_rng(SEED)
+    rng = np.random.default_rng(SEED + 1000 * rank)
+    torch.manual_seed(SEED + 1000 * rank)   # features differ per replica; parameters were initialised identically above
     pool = 8
 
     def zipf_ids(n, hi):
@@ -192,16 +199,21 @@ def run_train_block(device, steps: int, warmup: int, cpu_baseline: bool):
     def step_dev(b):
         return trainer.train_step(b["uf"], b["pf"], None, {"user_id": b["uid"]}, {"item_id": b["iid"]})
 
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for i in range(max(warmup, 3)):
         step_dev(dev[i % pool])
-    torch.cuda.synchronize()
+    sync()
     l0 = N.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
         step_dev(dev[i % pool])
     e1.record()
-    torch.cuda.synchronize()
+    sync()
     ms = e0.elapsed_time(e1) / steps
     launches = (N.launch_count() - l0) // steps
     # end to end: host batches (pinned) -> device every step, loss read back every step
@@ -209,13 +221,21 @@ def run_train_block(device, steps: int, warmup: int, cpu_baseline: bool):
     for i in range(steps):
         b = {k: v.to(device, non_blocking=True) for k, v in host[i % pool].items()}
         float(step_dev(b).item())
-    torch.cuda.synchronize()
+    sync()
     e2e_ms = (time.perf_counter() - t0) / steps * 1e3
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = [float(x) for x in t.tolist()]
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
-    out = {"metric": "train samples/s", "value": B / ms * 1e3, "unit": "samples/s", "ms_per_step": ms,
-           "config": {"workload": "synthetic 1M users x 100K items, dim 64, batch 8192, in-batch negatives, fp32-grade "
-                                  "split-bf16 GEMMs, dense Adam + clip (reference semantics)"},
-           "e2e": {"value": B / e2e_ms * 1e3, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+    out = {"metric": "train samples/s", "value": world * B / ms * 1e3, "unit": "samples/s", "ms_per_step": ms,
+           "n_gpus": world, "scaling": "weak",
+           "config": {"workload": f"synthetic 1M users x 100K items, dim 64, batch 8192 per GPU (global {world * B}), "
+                                  "in-batch negatives over the global batch, fp32-grade split-bf16 GEMMs, dense Adam + "
+                                  "clip (reference semantics)" + (", exact data parallel: synced BatchNorm statistics, "
+                                  "all-gathered negatives, summed gradients" if world > 1 else "")},
+           "e2e": {"value": world * B / e2e_ms * 1e3, "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
+                   "d2h_bytes_per_step": 4 * world},
            "gpu_launches_per_step": int(launches), "dtype": "f32 (bf16x6 split products, fp32 accumulate)"}
     if cpu_baseline:
         out["cpu_baseline"] = cpu_train_baseline(B, FD)
@@ -365,11 +385,12 @@ def main():
 
     train = None
     cpu = None
+    del sharded, index, q_op
+    torch.cuda.empty_cache()
+    if not args.no_train:
+        train = run_train_block(device, min(max(steps, 10), 30), warmup, (not args.no_cpu_baseline) and rank == 0 and world == 1,
+                                world, rank)
     if rank == 0 and world == 1:
-        del sharded, index, q_op
-        torch.cuda.empty_cache()
-        if not args.no_train:
-            train = run_train_block(device, max(steps, 10), warmup, not args.no_cpu_baseline)
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             rows, queries = 1_000_000, 2048

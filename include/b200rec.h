@@ -125,6 +125,18 @@ int b200rec_bn_backward(const float* dy, int64_t ld_dy, const float* z, int64_t 
                         int training, const float* mean, const float* invstd, const float* gamma, float drop_p,
                         uint64_t seed, float* dz, int64_t ld_dz, float* dgamma, float* dbeta, float* dbias,
                         double* scratch, void* stream);
+/* Data-parallel BatchNorm1d: batch statistics over the rows of ALL replicas (what a single process computes on the
+ * global batch, trainers/two_tower.py:98-151 under one-process-per-GPU training).  Two phases around the caller's
+ * all-reduce (sum) of the fp64 partial sums scratch[0, 2H): phase 0 accumulates the local sums (backward: also adds the
+ * LOCAL dbeta / dgamma), phase 1 finishes with B_total = rows over all replicas.  scratch: >= 3*H doubles. */
+int b200rec_bn_forward_dp(const float* z, int64_t B, int64_t H, int64_t ld, int act, float eps, float momentum,
+                          const float* gamma, const float* beta, float* running_mean, float* running_var,
+                          float drop_p, uint64_t seed, float* mean, float* invstd, float* y, int64_t ld_y,
+                          double* scratch, int phase, int64_t B_total, void* stream);
+int b200rec_bn_backward_dp(const float* dy, int64_t ld_dy, const float* z, int64_t ld_z, int64_t B, int64_t H, int act,
+                           const float* mean, const float* invstd, const float* gamma, float drop_p, uint64_t seed,
+                           float* dz, int64_t ld_dz, float* dgamma, float* dbeta, float* dbias, double* scratch,
+                           int phase, int64_t B_total, void* stream);
 /* y = dropout(act(z)) without BatchNorm (ItemTower.content_projection, two_tower.py:184-191) and its backward. */
 int b200rec_act_dropout(const float* z, int64_t B, int64_t H, int64_t ld, int act, float drop_p, uint64_t seed,
                         float* y, int64_t ld_y, void* stream);

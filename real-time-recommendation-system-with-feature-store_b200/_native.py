@@ -43,6 +43,10 @@ SIGNATURES = {
                                 _P]),
     "b200rec_bn_backward": (_I, [_P, _I64, _P, _I64, _I64, _I64, _I, _I, _P, _P, _P, _F, _U64, _P, _I64, _P, _P, _P,
                                  _P, _P]),
+    "b200rec_bn_forward_dp": (_I, [_P, _I64, _I64, _I64, _I, _F, _F, _P, _P, _P, _P, _F, _U64, _P, _P, _P, _I64, _P, _I,
+                                   _I64, _P]),
+    "b200rec_bn_backward_dp": (_I, [_P, _I64, _P, _I64, _I64, _I64, _I, _P, _P, _P, _F, _U64, _P, _I64, _P, _P, _P, _P,
+                                    _I, _I64, _P]),
     "b200rec_act_dropout": (_I, [_P, _I64, _I64, _I64, _I, _F, _U64, _P, _I64, _P]),
     "b200rec_act_dropout_bwd": (_I, [_P, _I64, _P, _I64, _I64, _I64, _I, _F, _U64, _P, _I64, _P]),
     "b200rec_colsum": (_I, [_P, _I64, _I64, _I64, _P, _I, _P, _P]),

@@ -154,9 +154,9 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ dy, int64_t ld_dy, const float* __restrict__ z, int64_t ld_z, int64_t B,
                     int64_t H, int act, const float* __restrict__ mean, const float* __restrict__ invstd,
                     const float* __restrict__ gamma, const double* __restrict__ sums, int training, float drop_p,
-                    uint64_t seed, float* __restrict__ dz, int64_t ld_dz) {
+                    uint64_t seed, float* __restrict__ dz, int64_t ld_dz, int64_t B_stat) {
   const int64_t total = B * H;
-  const double inv_n = 1.0 / (double)B;
+  const double inv_n = 1.0 / (double)B_stat;  // rows the statistics were taken over (all replicas under data parallel)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = i / H, h = i - b * H;
     const float zz = __ldg(z + b * ld_z + h);
@@ -280,7 +280,7 @@ extern "C" int b200rec_bn_backward(const float* dy, int64_t ld_dy, const float* 
   bn_bwd_stats_kernel<<<col_grid(B, H, 128), 128, 0, st>>>(dy, ld_dy, z, ld_z, B, H, act, mean, invstd, p, seed, scratch);
   B200_LAUNCH_OK("bn_bwd_stats_kernel");
   bn_bwd_apply_kernel<<<flat_grid(B * H), 256, 0, st>>>(dy, ld_dy, z, ld_z, B, H, act, mean, invstd, gamma, scratch,
-                                                        training, p, seed, dz, ld_dz);
+                                                        training, p, seed, dz, ld_dz, B);
   B200_LAUNCH_OK("bn_bwd_apply_kernel");
   const unsigned hb = (unsigned)((H + 127) / 128);
   sums_to_float_kernel<<<hb, 128, 0, st>>>(scratch, H, dbeta, 1);
@@ -288,6 +288,70 @@ extern "C" int b200rec_bn_backward(const float* dy, int64_t ld_dy, const float* 
   sums_to_float_kernel<<<hb, 128, 0, st>>>(scratch + H, H, dgamma, 1);
   B200_LAUNCH_OK("sums_to_float_kernel");
   if (dbias) {
+    colsum_kernel<<<col_grid(B, H, 128), 128, 0, st>>>(dz, B, H, ld_dz, scratch + 2 * H);
+    B200_LAUNCH_OK("colsum_kernel");
+    sums_to_float_kernel<<<hb, 128, 0, st>>>(scratch + 2 * H, H, dbias, 1);
+    B200_LAUNCH_OK("sums_to_float_kernel");
+  }
+  return 0;
+}
+
+// Data-parallel BatchNorm (batch statistics over ALL replicas, as a single process on the global batch computes
+// them): the caller all-reduces (sum) the fp64 partial sums in `scratch[0, 2H)` between phase 0 and phase 1.
+//   forward  phase 0: scratch = [sum act(z), sum act(z)^2] of the local rows
+//            phase 1: mean / invstd / running stats from the reduced sums over B_total rows, then y for the local rows
+//   backward phase 0: scratch = [sum dy', sum dy' xhat] of the local rows; dbeta / dgamma accumulate the LOCAL sums (the
+//                     flat gradient all-reduce adds the replicas up once)
+//            phase 1: dz for the local rows from the reduced sums over B_total rows (+ dbias = local colsum(dz))
+extern "C" int b200rec_bn_forward_dp(const float* z, int64_t B, int64_t H, int64_t ld, int act, float eps, float momentum,
+                                     const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                     float drop_p, uint64_t seed, float* mean, float* invstd, float* y, int64_t ld_y,
+                                     double* scratch, int phase, int64_t B_total, void* stream) {
+  if (!z || !scratch) return fail("bn_forward_dp: null pointer");
+  if (B <= 0 || H <= 0) return fail("bn_forward_dp: empty input");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (phase == 0) {
+    B200_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * H, st));
+    bn_stats_kernel<<<col_grid(B, H, 128), 128, 0, st>>>(z, B, H, ld, act, scratch);
+    B200_LAUNCH_OK("bn_stats_kernel");
+    return 0;
+  }
+  if (!gamma || !beta || !mean || !invstd || !y) return fail("bn_forward_dp: null pointer");
+  if (B_total < 2 || B_total < B) return fail("bn_forward_dp: B_total must be >= max(2, B)");
+  const unsigned hb = (unsigned)((H + 127) / 128);
+  bn_finalize_kernel<<<hb, 128, 0, st>>>(scratch, B_total, H, eps, momentum, mean, invstd, running_mean, running_var);
+  B200_LAUNCH_OK("bn_finalize_kernel");
+  bn_apply_kernel<<<flat_grid(B * H), 256, 0, st>>>(z, B, H, ld, act, mean, invstd, gamma, beta, drop_p, seed, y, ld_y);
+  B200_LAUNCH_OK("bn_apply_kernel");
+  return 0;
+}
+
+extern "C" int b200rec_bn_backward_dp(const float* dy, int64_t ld_dy, const float* z, int64_t ld_z, int64_t B, int64_t H,
+                                      int act, const float* mean, const float* invstd, const float* gamma, float drop_p,
+                                      uint64_t seed, float* dz, int64_t ld_dz, float* dgamma, float* dbeta, float* dbias,
+                                      double* scratch, int phase, int64_t B_total, void* stream) {
+  if (!dy || !z || !mean || !invstd || !gamma || !scratch) return fail("bn_backward_dp: null pointer");
+  if (B <= 0 || H <= 0) return fail("bn_backward_dp: empty input");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned hb = (unsigned)((H + 127) / 128);
+  if (phase == 0) {
+    if (!dgamma || !dbeta) return fail("bn_backward_dp: null pointer");
+    B200_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(double) * 3 * H, st));
+    bn_bwd_stats_kernel<<<col_grid(B, H, 128), 128, 0, st>>>(dy, ld_dy, z, ld_z, B, H, act, mean, invstd, drop_p, seed, scratch);
+    B200_LAUNCH_OK("bn_bwd_stats_kernel");
+    sums_to_float_kernel<<<hb, 128, 0, st>>>(scratch, H, dbeta, 1);
+    B200_LAUNCH_OK("sums_to_float_kernel");
+    sums_to_float_kernel<<<hb, 128, 0, st>>>(scratch + H, H, dgamma, 1);
+    B200_LAUNCH_OK("sums_to_float_kernel");
+    return 0;
+  }
+  if (!dz) return fail("bn_backward_dp: null pointer");
+  if (B_total < B) return fail("bn_backward_dp: B_total must be >= B");
+  bn_bwd_apply_kernel<<<flat_grid(B * H), 256, 0, st>>>(dy, ld_dy, z, ld_z, B, H, act, mean, invstd, gamma, scratch, 1,
+                                                        drop_p, seed, dz, ld_dz, B_total);
+  B200_LAUNCH_OK("bn_bwd_apply_kernel");
+  if (dbias) {
+    B200_CUDA_OK(cudaMemsetAsync(scratch + 2 * H, 0, sizeof(double) * H, st));
     colsum_kernel<<<col_grid(B, H, 128), 128, 0, st>>>(dz, B, H, ld_dz, scratch + 2 * H);
     B200_LAUNCH_OK("colsum_kernel");
     sums_to_float_kernel<<<hb, 128, 0, st>>>(scratch + 2 * H, H, dbias, 1);

@@ -199,6 +199,66 @@ class ShardedFlatIndex:
         return self.merge(gs.view(world, q, -1), gi.view(world, q, -1), k)
 
 
+class _AllGatherRows(torch.autograd.Function):
+    """x [B,E] on every replica -> [world*B, E] (rank-major); backward = reduce-scatter (sum) of the gathered gradient."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        x = x.contiguous()
+        out = torch.empty((dist.get_world_size(group) * x.shape[0], x.shape[1]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x, group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        world = dist.get_world_size(ctx.group)
+        gx = torch.empty((g.shape[0] // world, g.shape[1]), dtype=g.dtype, device=g.device)
+        dist.reduce_scatter_tensor(gx, g.contiguous(), op=dist.ReduceOp.SUM, group=ctx.group)
+        return gx, None
+
+
+class DataParallel:
+    """Exact data-parallel training of the two-tower model (one process per GPU, equal local batches): the result is
+    what ONE process computes on the concatenated global batch (reference trainers/two_tower.py:98-151):
+      * BatchNorm batch statistics over all replicas (fp64 partial sums all-reduced inside b200rec_bn_*_dp);
+      * in-batch negatives = the all-gathered item embeddings of the global batch, gradients reduce-scattered back;
+      * losses normalised by the GLOBAL batch, so gradients are SUMMED: one all-reduce of the flat dense gradient buffer
+        and an all-gather + re-coalesce of the touched rows of row-sparse embedding tables."""
+
+    def __init__(self, model, group=None):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("DataParallel needs an initialised torch.distributed process group")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        model.dp = self
+        model.user_tower.dp = self
+        model.item_tower.dp = self
+
+    def reduce_sums(self, t: torch.Tensor) -> None:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def all_gather_rows(self, x: torch.Tensor) -> torch.Tensor:
+        return _AllGatherRows.apply(x, self.group)
+
+    def reduce_dense_grad_(self, flat: torch.Tensor) -> None:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+
+    def gather_sparse(self, rows: torch.Tensor, vals: torch.Tensor):
+        """(rows [n], vals [n,e]) of this replica -> concatenation over replicas (padding rows stay 0)."""
+        ar = torch.empty((self.world * rows.shape[0],), dtype=rows.dtype, device=rows.device)
+        av = torch.empty((self.world * vals.shape[0], vals.shape[1]), dtype=vals.dtype, device=vals.device)
+        dist.all_gather_into_tensor(ar, rows.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(av, vals.contiguous(), group=self.group)
+        return ar, av
+
+    def global_loss(self, local_share: torch.Tensor) -> torch.Tensor:
+        out = local_share.detach().clone()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+        return out
+
+
 def allreduce_mean_(flat: torch.Tensor, group=None) -> None:
     """Data-parallel gradient exchange: one all-reduce over the flat fp32 gradient buffer, then divide by the world."""
     world, _ = _world()

@@ -233,6 +233,37 @@ def bn_backward(dy, z, act: int, training: bool, mean, invstd, gamma, drop_p: fl
     return dz, dgamma, dbeta
 
 
+def bn_forward_dp(z, act: int, eps: float, momentum: float, gamma, beta, running_mean, running_var, drop_p: float,
+                  seed: int, reduce_sums, b_total: int):
+    """Training-mode BatchNorm with statistics over all data-parallel replicas.  `reduce_sums(t)` all-reduces (sum) the
+    fp64 tensor t in place (torch.distributed.all_reduce on the NCCL group)."""
+    B, H = z.shape
+    y = torch.empty_like(z)
+    mean = torch.empty((H,), dtype=torch.float32, device=z.device)
+    invstd = torch.empty((H,), dtype=torch.float32, device=z.device)
+    scratch = _scratch(3 * H, z.device)
+    args = (N.ptr(z), B, H, z.stride(0), act, eps, momentum, N.ptr(gamma), N.ptr(beta), N.ptr(running_mean),
+            N.ptr(running_var), drop_p, seed, N.ptr(mean), N.ptr(invstd), N.ptr(y), y.stride(0), N.ptr(scratch))
+    N.check(N.lib().b200rec_bn_forward_dp(*args, 0, b_total, N.stream()), "bn_forward_dp")
+    reduce_sums(scratch[: 2 * H])
+    N.check(N.lib().b200rec_bn_forward_dp(*args, 1, b_total, N.stream()), "bn_forward_dp")
+    return y, mean, invstd
+
+
+def bn_backward_dp(dy, z, act: int, mean, invstd, gamma, drop_p: float, seed: int, reduce_sums, b_total: int):
+    B, H = z.shape
+    dz = torch.empty_like(z)
+    dgamma = torch.zeros((H,), dtype=torch.float32, device=z.device)
+    dbeta = torch.zeros((H,), dtype=torch.float32, device=z.device)
+    scratch = _scratch(3 * H, z.device)
+    args = (N.ptr(dy), dy.stride(0), N.ptr(z), z.stride(0), B, H, act, N.ptr(mean), N.ptr(invstd), N.ptr(gamma), drop_p,
+            seed, N.ptr(dz), dz.stride(0), N.ptr(dgamma), N.ptr(dbeta), None, N.ptr(scratch))
+    N.check(N.lib().b200rec_bn_backward_dp(*args, 0, b_total, N.stream()), "bn_backward_dp")
+    reduce_sums(scratch[: 2 * H])
+    N.check(N.lib().b200rec_bn_backward_dp(*args, 1, b_total, N.stream()), "bn_backward_dp")
+    return dz, dgamma, dbeta
+
+
 def act_dropout(z, act: int, drop_p: float, seed: int):
     B, H = z.shape
     y = torch.empty_like(z)

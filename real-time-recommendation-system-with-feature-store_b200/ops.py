@@ -34,6 +34,9 @@ class LinearFn(Function):
     def forward(ctx, x, w, b, terms: int):
         require_cuda(x, w)
         x, w = _c32(x), _c32(w)
+        if x.dim() != 2 or x.shape[1] != w.shape[1]:   # nn.Linear's own error for a wrong feature width
+            raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({x.shape[0]}x{x.shape[-1]} and "
+                               f"{w.shape[1]}x{w.shape[0]})")
         xo = K.split_bf16(x, terms, 0)
         wo = K.split_bf16(w, terms, 1)
         z = K.gemm_tn(xo, wo, x.shape[0], w.shape[0], xo.shape[1], None if b is None else _c32(b))
@@ -65,24 +68,34 @@ class LinearFn(Function):
 
 
 class ActBNDropFn(Function):
-    """y = Dropout(BatchNorm1d(act(z)))  — the hidden block after each Linear (two_tower.py:60-66)."""
+    """y = Dropout(BatchNorm1d(act(z)))  — the hidden block after each Linear (two_tower.py:60-66).
+    `dp` (a dist.DataParallel context, training only): batch statistics over the rows of all replicas."""
 
     @staticmethod
     def forward(ctx, z, gamma, beta, running_mean, running_var, act: int, training: bool, eps: float, momentum: float,
-                drop_p: float, seed: int):
+                drop_p: float, seed: int, dp=None):
         z = _c32(z)
-        y, mean, invstd = K.bn_forward(z, act, training, eps, momentum, gamma, beta, running_mean, running_var,
-                                       drop_p, seed)
+        if dp is not None and training:
+            y, mean, invstd = K.bn_forward_dp(z, act, eps, momentum, gamma, beta, running_mean, running_var, drop_p,
+                                              seed, dp.reduce_sums, z.shape[0] * dp.world)
+        else:
+            dp = None
+            y, mean, invstd = K.bn_forward(z, act, training, eps, momentum, gamma, beta, running_mean, running_var,
+                                           drop_p, seed)
         ctx.save_for_backward(z, mean, invstd, gamma)
-        ctx.cfg = (act, training, drop_p, seed)
+        ctx.cfg = (act, training, drop_p, seed, dp)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         z, mean, invstd, gamma = ctx.saved_tensors
-        act, training, drop_p, seed = ctx.cfg
-        dz, dgamma, dbeta = K.bn_backward(_c32(dy), z, act, training, mean, invstd, gamma, drop_p, seed)
-        return dz, dgamma, dbeta, None, None, None, None, None, None, None, None
+        act, training, drop_p, seed, dp = ctx.cfg
+        if dp is not None:
+            dz, dgamma, dbeta = K.bn_backward_dp(_c32(dy), z, act, mean, invstd, gamma, drop_p, seed, dp.reduce_sums,
+                                                 z.shape[0] * dp.world)
+        else:
+            dz, dgamma, dbeta = K.bn_backward(_c32(dy), z, act, training, mean, invstd, gamma, drop_p, seed)
+        return dz, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 
 class ActDropFn(Function):

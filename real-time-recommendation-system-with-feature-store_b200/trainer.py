@@ -58,6 +58,13 @@ class FlatAdam:
 
     def _sparse_lists(self, p):
         lists = getattr(p, "_b200_sparse_grad", None) or []
+        dp = getattr(self, "dp", None)
+        if dp is not None and lists:
+            # data parallel: every replica applies the touched rows of ALL replicas (tables are replicated)
+            rows = torch.cat([r for r, _, _ in lists]) if len(lists) > 1 else lists[0][0]
+            vals = torch.cat([v for _, v, _ in lists]) if len(lists) > 1 else lists[0][1]
+            rows, vals = dp.gather_sparse(rows, vals)
+            return [K.embedding_sparse_grad(rows, vals, vals.shape[1], p.shape[0], 0)]
         if len(lists) <= 1:
             return lists
         # several gathers hit the table this step: concatenate and coalesce again (invalid tail rows are 0 = padding)
@@ -69,6 +76,9 @@ class FlatAdam:
         self.step_count += 1
         lr = self.param_groups[0]["lr"]
         clip = None
+        dp = getattr(self, "dp", None)
+        if dp is not None:
+            dp.reduce_dense_grad_(self.grad)   # losses are normalised by the global batch: gradients add up
         sparse = [(p, self._sparse_lists(p)) for p in self.sparse]
         if self.max_grad_norm is not None:
             self._acc.zero_()
@@ -121,6 +131,8 @@ class TwoTowerTrainer:
                    user_categorical: Optional[Dict[str, torch.Tensor]] = None,
                    item_categorical: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
         model = self.model
+        dp = getattr(model, "dp", None)
+        self.optimizer.dp = dp
         self.optimizer.zero_grad()
         u = model.get_user_embeddings({"numerical": user_features, "categorical": user_categorical or {}})
         p = model.get_item_embeddings({"numerical": pos_item_features, "categorical": item_categorical or {}})
@@ -128,13 +140,15 @@ class TwoTowerTrainer:
             batch_size, num_neg, feat_dim = neg_item_features.shape
             n = model.get_item_embeddings({"numerical": neg_item_features.view(-1, feat_dim), "categorical": {}})
             explicit_loss = model.contrastive_loss(u, p, n)
+            if dp is not None:
+                explicit_loss = explicit_loss / dp.world   # this replica's share of the global-batch mean
             in_batch_loss = model.in_batch_negative_loss(u, p)
             loss = 0.7 * explicit_loss + 0.3 * in_batch_loss
         else:
             loss = model.in_batch_negative_loss(u, p)
         loss.backward()
         self.optimizer.step()
-        return loss.detach()
+        return dp.global_loss(loss) if dp is not None else loss.detach()
 
     def train_epoch(self, epoch: int) -> float:
         self.model.train()

@@ -90,7 +90,9 @@ class _TowerBase(nn.Module):
     def _next_seed(self) -> int:
         self._seed_counter += 1
         base = int(torch.initial_seed())
-        return (base * 0x9E3779B97F4A7C15 + self._seed_counter * 0xD1B54A32D192ED03 + (id(self) >> 4)) & 0xFFFFFFFFFFFFFFFF
+        dp = getattr(self, "dp", None)  # data parallel: every replica draws its own dropout masks
+        rank_mix = (dp.rank + 1) * 0xA24BAED4963EE407 if dp is not None else 0
+        return (base * 0x9E3779B97F4A7C15 + self._seed_counter * 0xD1B54A32D192ED03 + (id(self) >> 4) + rank_mix) & 0xFFFFFFFFFFFFFFFF
 
     def _concat_inputs(self, numerical: torch.Tensor, categorical: Optional[Dict[str, torch.Tensor]],
                        extra: Optional[torch.Tensor]) -> torch.Tensor:
@@ -119,7 +121,7 @@ class _TowerBase(nn.Module):
             p = self.dropout_rate if self.training else 0.0
             x = ops.ActBNDropFn.apply(z, bn.weight, bn.bias, bn.running_mean, bn.running_var, act, self.training,
                                       bn.eps, bn.momentum if bn.momentum is not None else 0.1, p,
-                                      self._next_seed() if p > 0 else 0)
+                                      self._next_seed() if p > 0 else 0, getattr(self, "dp", None))
             if self.training:
                 bn.num_batches_tracked += 1
         last = self.mlp[4 * self._num_hidden]
@@ -244,6 +246,14 @@ class TwoTowerModel(nn.Module):
 
     def in_batch_negative_loss(self, user_embedding: torch.Tensor, item_embedding: torch.Tensor) -> torch.Tensor:
         terms = _TERMS[self.precision]
+        dp = getattr(self, "dp", None)
+        if dp is not None:
+            # data parallel: the negatives are the WHOLE global batch, as in a single process (two_tower.py:453-479).
+            # Returns this replica's share sum_local(...) / B_global; the replicas' shares add up to the loss.
+            b = user_embedding.shape[0]
+            items_all = dp.all_gather_rows(item_embedding)
+            return ops.InBatchCEFn.apply(user_embedding, items_all, 1.0 / self.temperature, terms, dp.rank * b,
+                                         dp.world * b)
         return ops.InBatchCEFn.apply(user_embedding, item_embedding, 1.0 / self.temperature, terms, 0,
                                      user_embedding.shape[0])
 

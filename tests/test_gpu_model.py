@@ -229,3 +229,27 @@ def test_dropout_mask_rate_and_scaling():
     assert abs(kept - 0.8) < 0.01
     assert torch.allclose(y[y > 0], torch.full_like(y[y > 0], 1.25))
     assert torch.equal(y, K.act_dropout(z, K.ACT_IDS["identity"], 0.2, 1234))  # same seed, same mask
+
+
+def test_linear_rejects_wrong_feature_width():
+    """nn.Linear's error for an input whose width does not match the weight (reference towers raise the same)."""
+    from b200rec import ops
+    x = torch.randn(8, 16, device="cuda")
+    w = torch.randn(32, 80, device="cuda")
+    with pytest.raises(RuntimeError, match="mat1 and mat2 shapes cannot be multiplied"):
+        ops.LinearFn.apply(x, w, None, 6)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_data_parallel_training_equals_single_process():
+    """Two replicas (NCCL): synced BatchNorm statistics + all-gathered in-batch negatives + summed gradients reproduce the
+    single-process step on the concatenated batch (tools/check_dp_training.py exits non-zero otherwise)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BLOCAL="512")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "check_dp_training.py")],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
