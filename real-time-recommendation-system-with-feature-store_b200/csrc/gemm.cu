@@ -69,37 +69,44 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (nkb > 0) {
+    // Producer and MMA issuer run warp-uniform loops and let one ELECTED lane issue (elect.sync): under a `lane == 0`
+    // branch ptxas wraps every TMA / tcgen05 instruction in an ELECT + R2UR waterfall loop (~19 SASS instructions per
+    // MMA), which for the 32-64 cycle MMAs of these tiles made the issuing thread the bottleneck (ncu: tensor pipe
+    // 22 % active on the in-batch backward GEMMs).
     if (warp == 0) {
-      if (lane == 0) {
-        for (int i = 0; i < nkb; ++i) {
-          const int s = i % Cfg::STAGES;
-          const uint32_t ph = (i / Cfg::STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % Cfg::STAGES;
+        const uint32_t ph = (i / Cfg::STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (elect_one()) {
           uint8_t* a_dst = smem + s * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           tma_load_2d(a_dst, &tmap_a, &full_bar[s], (kb_begin + i) * GEMM_BK, m0);
           tma_load_2d(b_dst, &tmap_b, &full_bar[s], (kb_begin + i) * GEMM_BK, n0);
         }
+        __syncwarp();
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        const uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
-        for (int i = 0; i < nkb; ++i) {
-          const int s = i % Cfg::STAGES;
-          const uint32_t ph = (i / Cfg::STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+      const uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+      const uint64_t desc_base = umma_desc_k_sw128(0);
+      const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % Cfg::STAGES;
+        const uint32_t ph = (i / Cfg::STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t a_desc = desc_base + (smem_lo + ((s * Cfg::STAGE_BYTES) >> 4));
+          const uint64_t b_desc = a_desc + (Cfg::A_BYTES >> 4);
+          const uint32_t d_addr = tmem_base + (i % Cfg::NACC) * BN;
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            umma_bf16(tmem_base + (i % Cfg::NACC) * BN, umma_desc_k_sw128(a_addr + k * 32),
-                      umma_desc_k_sw128(b_addr + k * 32), idesc, (i >= Cfg::NACC) || (k != 0));
-          }
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            umma_bf16(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc, (i >= Cfg::NACC) || (k != 0));
           umma_commit(&empty_bar[s]);
+          if (i == nkb - 1) umma_commit(acc_bar);
         }
-        umma_commit(acc_bar);
+        __syncwarp();
       }
     } else if (warp >= 4) {
       const int quarter = warp & 3;

@@ -41,6 +41,10 @@ __device__ __forceinline__ void store_terms(__nv_bfloat16* drow, int64_t c, int6
     if (t < terms) drow[t * kpad + c] = p[part_of(terms, side, t)];
 }
 
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
@@ -54,6 +58,8 @@ prep_rows_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int6
                  __nv_bfloat16* __restrict__ dst_bf16, int64_t kpad, int terms, int side) {
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const bool vec_ok = ((ld_src & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(dst_bf16) & 15) == 0) && ((kpad & 7) == 0);
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps_total) {
     const float* srow = src + r * ld_src;
     float scale = 1.0f, denom = 1.0f;
@@ -77,6 +83,38 @@ prep_rows_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int6
       }
     }
     __nv_bfloat16* drow = dst_bf16 ? dst_bf16 + r * terms * kpad : nullptr;
+    if (drow && vec_ok) {
+      // 8 columns per lane: two 128-bit loads, one 128-bit store per term block (2-byte stores ran at 1 TB/s)
+      for (int64_t c = (int64_t)lane * 8; c < kpad; c += 256) {
+        float x[8];
+        if (c + 8 <= cols) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(srow + c));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(srow + c + 4));
+          x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w, x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = (c + j < cols) ? __ldg(srow + c + j) : 0.f;
+        }
+        __nv_bfloat16 p[3][8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (normalize) x[j] = faiss_zero_rule ? x[j] * scale : x[j] / denom;
+          if (dst_f32 && c + j < cols) dst_f32[r * ld_dst + c + j] = x[j];
+          split3(x[j], p[0][j], p[1][j], p[2][j]);
+        }
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+          if (t < terms) {
+            const int part = part_of(terms, side, t);
+            uint4 o;
+            const __nv_bfloat16* q = part == 0 ? p[0] : (part == 1 ? p[1] : p[2]);
+            o.x = pack2(q[0], q[1]), o.y = pack2(q[2], q[3]), o.z = pack2(q[4], q[5]), o.w = pack2(q[6], q[7]);
+            *reinterpret_cast<uint4*>(drow + t * kpad + c) = o;
+          }
+        }
+      }
+      continue;
+    }
     const int64_t cmax = dst_bf16 ? kpad : cols;
     for (int64_t c = lane; c < cmax; c += 32) {
       float x = 0.f;
@@ -90,24 +128,37 @@ prep_rows_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int6
   }
 }
 
-// dst[r, c] = src[c, r]   (src has `cols` rows of `rows` floats); 32x32 tiles through padded smem
+// dst[r, c] = src[c, r]   (src has `cols` rows of `rows` floats); 64 (dst columns) x 32 (dst rows) tiles through padded
+// shared memory, 4-byte (bf16x2) stores: 128 B per warp and term instead of 64 B
 __global__ void __launch_bounds__(256)
 prep_transpose_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int64_t ld_src,
                       __nv_bfloat16* __restrict__ dst, int64_t kpad, int terms, int side) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[64][33];
   const int64_t r0 = (int64_t)blockIdx.y * 32;  // dst rows   = src columns
-  const int64_t c0 = (int64_t)blockIdx.x * 32;  // dst cols   = src rows
+  const int64_t c0 = (int64_t)blockIdx.x * 64;  // dst cols   = src rows
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
 #pragma unroll
-  for (int i = ty; i < 32; i += 8) {
+  for (int i = ty; i < 64; i += 8) {
     const int64_t sr = c0 + i, sc = r0 + tx;
     tile[i][tx] = (sr < cols && sc < rows) ? __ldg(src + sr * ld_src + sc) : 0.f;
   }
   __syncthreads();
 #pragma unroll
   for (int i = ty; i < 32; i += 8) {
-    const int64_t r = r0 + i, c = c0 + tx;
-    if (r < rows && c < kpad) store_terms(dst + r * terms * kpad, c, kpad, terms, side, tile[tx][i]);
+    const int64_t r = r0 + i, c = c0 + 2 * tx;
+    if (r < rows && c < kpad) {   // kpad is a multiple of 8, c is even: c + 1 < kpad
+      __nv_bfloat16 pa[3], pb[3];
+      split3(tile[2 * tx][i], pa[0], pa[1], pa[2]);
+      split3(tile[2 * tx + 1][i], pb[0], pb[1], pb[2]);
+      __nv_bfloat16* drow = dst + r * terms * kpad;
+#pragma unroll
+      for (int t = 0; t < 6; ++t) {
+        if (t < terms) {
+          const int part = part_of(terms, side, t);
+          *reinterpret_cast<uint32_t*>(drow + t * kpad + c) = pack2(pa[part], pb[part]);
+        }
+      }
+    }
   }
 }
 
@@ -134,7 +185,7 @@ extern "C" int b200rec_split_bf16(const float* src, int64_t rows, int64_t cols, 
                                            reinterpret_cast<__nv_bfloat16*>(dst), kpad, terms, side);
     B200_LAUNCH_OK("prep_rows_kernel");
   } else {
-    dim3 grid((unsigned)((kpad + 31) / 32), (unsigned)((rows + 31) / 32));
+    dim3 grid((unsigned)((kpad + 63) / 64), (unsigned)((rows + 31) / 32));
     if (grid.y > 65535) return fail("split_bf16(transpose): too many rows (%lld)", (long long)rows);
     prep_transpose_kernel<<<grid, 256, 0, st>>>(src, rows, cols, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), kpad,
                                                 terms, side);
