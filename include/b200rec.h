@@ -193,6 +193,21 @@ int b200rec_sparse_adam(float* table, float* exp_avg, float* exp_avg_sq, int64_t
                         float beta2, float eps, float bias_c1, float bias_c2_sqrt, const float* clip_coef_dev,
                         void* stream);
 
+/* ---- device-side batch feed (replaces MovieLensDataset.__getitem__ + collate_fn, reference
+ * src/training/datasets/movielens.py:86-162, and sample_negative_items, src/data/movielens.py:487-512) ----
+ * out[b, :] = table[idx[b], :] (fp32 rows of `width` floats).  An index outside [0, n_rows) sets *err_flag = 1 (numpy's
+ * fancy indexing raises IndexError there) and yields a zero row. */
+int b200rec_gather_rows(const float* table, int64_t n_rows, int width, int64_t ld, const int64_t* idx, int64_t B,
+                        float* out, int64_t ld_out, int* err_flag, void* stream);
+/* out_items [B, num_negatives]: for every row, `num_negatives` DISTINCT items drawn uniformly from the items its user
+ * has not interacted with (np.random.choice(list(all_items - positives), n, replace=False)).  Positives come as a CSR
+ * over users (pos_indptr int64 [n_users + 1], pos_items int32 sorted ascending per user).  Deterministic in
+ * (seed, row_base + row).  *err_flag = 2 when a user's pool is smaller than num_negatives (the reference then returns
+ * a short list and collate_fn fails). */
+int b200rec_sample_negatives(const int64_t* user_of_row, int64_t B, const int64_t* pos_indptr, const int32_t* pos_items,
+                             int64_t n_users, int64_t num_items, int num_negatives, uint64_t seed, uint64_t row_base,
+                             int64_t* out_items, int* err_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,8 @@ SIGNATURES = {
     "b200rec_topk_sample_fanout": (_I, [_P, _I64, _I64, _P, _I64, _I, _I, _I, _I, _P, _P, _SZ, _P]),
     "b200rec_topk_merge": (_I, [_P, _P, _I, _I64, _I, _I, _I64, _I64, _P, _P, _P]),
     "b200rec_gather_concat": (_I, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P, _I, _I64, _P, _I64, _P, _P]),
+    "b200rec_gather_rows": (_I, [_P, _I64, _I, _I64, _P, _I64, _P, _I64, _P, _P]),
+    "b200rec_sample_negatives": (_I, [_P, _I64, _P, _P, _I64, _I64, _I, _U64, _U64, _P, _P, _P]),
     "b200rec_sparse_grad_workspace_bytes": (_SZ, [_I64]),
     "b200rec_embedding_sparse_grad": (_I, [_P, _I64, _P, _I64, _I, _I64, _I64, _P, _P, _P, _P, _SZ, _P]),
     "b200rec_scatter_rows": (_I, [_P, _P, _P, _I64, _I, _P, _I64, _I, _P]),

@@ -381,3 +381,27 @@ def sparse_adam_(table, m, v, rows, grads, n, lr, beta1, beta2, eps, step: int, 
     N.check(N.lib().b200rec_sparse_adam(N.ptr(table), N.ptr(m), N.ptr(v), table.stride(0), grads.shape[1], N.ptr(rows),
                                         N.ptr(grads), N.ptr(n), rows.shape[0], lr, beta1, beta2, eps, bc1, bc2s,
                                         N.ptr(clip), N.stream()), "sparse_adam")
+
+
+# ------------------------------------------------------------------------------------------------ device-side batch feed
+def gather_rows(table: torch.Tensor, idx: torch.Tensor, err: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b, :] = table[idx[b], :] (fp32 feature rows); an out-of-range index raises err (int32[1]) to 1."""
+    assert table.dtype == torch.float32 and table.dim() == 2 and table.stride(1) == 1 and idx.dtype == torch.int64
+    B, width = idx.numel(), table.shape[1]
+    if out is None:
+        out = torch.empty((B, width), dtype=torch.float32, device=table.device)
+    N.check(N.lib().b200rec_gather_rows(N.ptr(table), table.shape[0], width, table.stride(0), N.ptr(idx), B, N.ptr(out),
+                                        out.stride(0), N.ptr(err), N.stream()), "gather_rows")
+    return out
+
+
+def sample_negatives(user_of_row: torch.Tensor, pos_indptr: torch.Tensor, pos_items: torch.Tensor, num_items: int,
+                     num_negatives: int, seed: int, row_base: int, err: torch.Tensor) -> torch.Tensor:
+    """[B, num_negatives] int64: distinct items, uniform over the items each row's user has not interacted with."""
+    B = user_of_row.numel()
+    out = torch.empty((B, num_negatives), dtype=torch.int64, device=user_of_row.device)
+    N.check(N.lib().b200rec_sample_negatives(N.ptr(user_of_row), B, N.ptr(pos_indptr), N.ptr(pos_items),
+                                             pos_indptr.numel() - 1, num_items, num_negatives,
+                                             seed & 0xFFFFFFFFFFFFFFFF, row_base, N.ptr(out), N.ptr(err), N.stream()),
+            "sample_negatives")
+    return out

@@ -177,3 +177,24 @@ def test_bf16_round():
     x = np.random.default_rng(3).standard_normal(4096).astype(np.float32)
     ref = torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
     assert np.array_equal(flat_ip.bf16_round(x), ref)
+
+
+def test_feed_oracle_matches_reference_batches():
+    """oracle/feed.py (sample_negative_items + __getitem__ + collate_fn restated) reproduces, bit for bit and from the
+    same numpy seed, the batch the imported reference built (tests/golden/make_golden_feed.py)."""
+    import os
+    from oracle.feed import make_batch
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "feed_small.npz"))
+    pos = {}
+    for u, i in zip(g["in_user_idx"].tolist(), g["in_item_idx"].tolist()):
+        pos.setdefault(u, []).append(i)
+    np.random.seed(int(g["seed"]))
+    b = make_batch(g["rows"].tolist(), g["in_user_idx"], g["in_item_idx"], g["in_label"], g["in_uf"], g["in_mf"], pos,
+                   int(g["n_items"]), int(g["R"]), True)
+    for k, v in b.items():
+        ref = g["out_" + k]
+        assert v.shape == ref.shape, k
+        assert np.array_equal(v, ref), k
+    # the sampler's contract, used as the property oracle for the device sampler
+    for u, neg in zip(b["user_idx"].tolist(), b["neg_item_indices"].tolist()):
+        assert len(set(neg)) == len(neg) and not (set(neg) & set(pos[u])) and all(0 <= x < int(g["n_items"]) for x in neg)
