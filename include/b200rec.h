@@ -193,6 +193,20 @@ int b200rec_sparse_adam(float* table, float* exp_avg, float* exp_avg_sq, int64_t
                         float beta2, float eps, float bias_c1, float bias_c2_sqrt, const float* clip_coef_dev,
                         void* stream);
 
+/* ---- CUDA-graph training: per-step state in device memory ----
+ * A captured step replays with the kernel arguments of the capture, so the step counter, Adam's bias corrections, the
+ * learning rate and the dropout streams live on the device.  b200rec_train_step_begin (first node of the graph):
+ * step = ++*step_dev; hyper_dev[0..2] = {*lr_dev, 1 - beta1^step, sqrt(1 - beta2^step)}; every dropout seed of the step
+ * is XOR-ed with a hash of (salt_key, step) (salt_key 0 = no salt).  b200rec_adam_dense_dev / _sparse_adam_dev are
+ * b200rec_adam_dense / _sparse_adam reading hyper_dev instead of host scalars.  One training stream per process. */
+int b200rec_train_step_begin(int64_t* step_dev, const float* lr_dev, float beta1, float beta2, float* hyper_dev,
+                             uint64_t salt_key, void* stream);
+int b200rec_adam_dense_dev(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
+                           float weight_decay, const float* hyper_dev, const float* clip_coef_dev, void* stream);
+int b200rec_sparse_adam_dev(float* table, float* exp_avg, float* exp_avg_sq, int64_t ld, int width, const int64_t* rows,
+                            const float* grad_rows, const int32_t* n_rows, int64_t max_rows, float beta1, float beta2,
+                            float eps, const float* hyper_dev, const float* clip_coef_dev, void* stream);
+
 /* ---- device-side batch feed (replaces MovieLensDataset.__getitem__ + collate_fn, reference
  * src/training/datasets/movielens.py:86-162, and sample_negative_items, src/data/movielens.py:487-512) ----
  * out[b, :] = table[idx[b], :] (fp32 rows of `width` floats).  An index outside [0, n_rows) sets *err_flag = 1 (numpy's

@@ -46,8 +46,13 @@ __global__ void clip_coef_kernel(const double* __restrict__ sumsq, float max_nor
 __global__ void __launch_bounds__(256)
 adam_dense_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                   int64_t n, float lr, float beta1, float beta2, float eps, float wd, float bias_c1, float bias_c2_sqrt,
-                  const float* __restrict__ clip_coef) {
+                  const float* __restrict__ clip_coef, const float* __restrict__ hyper_dev) {
   const float cc = clip_coef ? __ldg(clip_coef) : 1.f;
+  if (hyper_dev) {  // CUDA-graph training: {lr, 1 - beta1^t, sqrt(1 - beta2^t)} written by b200rec_train_step_begin
+    lr = __ldg(hyper_dev);
+    bias_c1 = __ldg(hyper_dev + 1);
+    bias_c2_sqrt = __ldg(hyper_dev + 2);
+  }
   const float step_size = lr / bias_c1;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float pi = p[i];
@@ -67,10 +72,15 @@ __global__ void __launch_bounds__(256)
 sparse_adam_kernel(float* __restrict__ table, float* __restrict__ m, float* __restrict__ v, int64_t ld, int width,
                    const int64_t* __restrict__ rows, const float* __restrict__ grad_rows,
                    const int32_t* __restrict__ n_rows, float lr, float beta1, float beta2, float eps, float bias_c1,
-                   float bias_c2_sqrt, const float* __restrict__ clip_coef) {
+                   float bias_c2_sqrt, const float* __restrict__ clip_coef, const float* __restrict__ hyper_dev) {
   const int lane = threadIdx.x & 31;
   const int n = __ldg(n_rows);
   const float cc = clip_coef ? __ldg(clip_coef) : 1.f;
+  if (hyper_dev) {
+    lr = __ldg(hyper_dev);
+    bias_c1 = __ldg(hyper_dev + 1);
+    bias_c2_sqrt = __ldg(hyper_dev + 2);
+  }
   const float step_size = lr / bias_c1;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < n; u += warps) {
@@ -118,7 +128,20 @@ extern "C" int b200rec_adam_dense(float* p, const float* g, float* m, float* v, 
   if (!p || !g || !m || !v) return fail("adam_dense: null pointer");
   if (n <= 0) return fail("adam_dense: empty input");
   adam_dense_kernel<<<flat_grid(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2_sqrt, clip_coef_dev);
+      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2_sqrt, clip_coef_dev, nullptr);
+  B200_LAUNCH_OK("adam_dense_kernel");
+  return 0;
+}
+
+// the same update with {lr, 1 - beta1^t, sqrt(1 - beta2^t)} read from device memory (hyper_dev, see
+// b200rec_train_step_begin): the form a CUDA-graph-captured training step uses
+extern "C" int b200rec_adam_dense_dev(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2,
+                                      float eps, float weight_decay, const float* hyper_dev, const float* clip_coef_dev,
+                                      void* stream) {
+  if (!p || !g || !m || !v || !hyper_dev) return fail("adam_dense_dev: null pointer");
+  if (n <= 0) return fail("adam_dense_dev: empty input");
+  adam_dense_kernel<<<flat_grid(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, n, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f, clip_coef_dev, hyper_dev);
   B200_LAUNCH_OK("adam_dense_kernel");
   return 0;
 }
@@ -133,7 +156,23 @@ extern "C" int b200rec_sparse_adam(float* table, float* exp_avg, float* exp_avg_
   const int grid = (int)(blocks < (int64_t)num_sms() * 16 ? blocks : (int64_t)num_sms() * 16);
   sparse_adam_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       table, exp_avg, exp_avg_sq, ld, width, rows, grad_rows, n_rows, lr, beta1, beta2, eps, bias_c1, bias_c2_sqrt,
-      clip_coef_dev);
+      clip_coef_dev, nullptr);
+  B200_LAUNCH_OK("sparse_adam_kernel");
+  return 0;
+}
+
+extern "C" int b200rec_sparse_adam_dev(float* table, float* exp_avg, float* exp_avg_sq, int64_t ld, int width,
+                                       const int64_t* rows, const float* grad_rows, const int32_t* n_rows,
+                                       int64_t max_rows, float beta1, float beta2, float eps, const float* hyper_dev,
+                                       const float* clip_coef_dev, void* stream) {
+  if (!table || !exp_avg || !exp_avg_sq || !rows || !grad_rows || !n_rows || !hyper_dev)
+    return fail("sparse_adam_dev: null pointer");
+  if (max_rows <= 0 || width <= 0) return fail("sparse_adam_dev: empty input");
+  const int64_t blocks = (max_rows + 7) / 8;
+  const int grid = (int)(blocks < (int64_t)num_sms() * 16 ? blocks : (int64_t)num_sms() * 16);
+  sparse_adam_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      table, exp_avg, exp_avg_sq, ld, width, rows, grad_rows, n_rows, 0.f, beta1, beta2, eps, 1.f, 1.f, clip_coef_dev,
+      hyper_dev);
   B200_LAUNCH_OK("sparse_adam_kernel");
   return 0;
 }

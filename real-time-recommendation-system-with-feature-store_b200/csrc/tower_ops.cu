@@ -57,9 +57,15 @@ __device__ __forceinline__ uint4 philox4(uint64_t seed, uint64_t ctr) {
   }
   return make_uint4(c0, c1, c2, c3);
 }
+// Per-step salt of every dropout seed, set on the device by b200rec_train_step_begin.  A training step captured in a
+// CUDA graph replays with the kernel arguments of the capture, so what must change from step to step (the dropout
+// streams here, Adam's bias corrections in optim.cu) lives in device memory.  0 (never set) in eager training.
+__device__ unsigned long long g_seed_salt = 0ull;
+
 // keep-scale of element (row, col): 0 when dropped, 1/(1-p) when kept; p == 0 -> 1
 __device__ __forceinline__ float drop_scale(float p, uint64_t seed, int64_t row, int64_t col, int64_t H) {
   if (p <= 0.f) return 1.f;
+  seed ^= g_seed_salt;
   const uint64_t idx = (uint64_t)row * (uint64_t)H + (uint64_t)col;
   const uint4 r = philox4(seed, idx >> 2);
   const uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
@@ -357,6 +363,30 @@ extern "C" int b200rec_bn_backward_dp(const float* dy, int64_t ld_dy, const floa
     sums_to_float_kernel<<<hb, 128, 0, st>>>(scratch + 2 * H, H, dbias, 1);
     B200_LAUNCH_OK("sums_to_float_kernel");
   }
+  return 0;
+}
+
+// step = ++*step_dev; hyper_dev = {lr, 1 - beta1^step, sqrt(1 - beta2^step)} for b200rec_adam_*_dev; the dropout seeds
+// of this step are salted with a hash of (salt_key, step).  One thread.
+__global__ void train_step_begin_kernel(long long* step_dev, const float* lr_dev, float beta1, float beta2,
+                                        float* hyper_dev, unsigned long long salt_key) {
+  const long long step = *step_dev + 1;
+  *step_dev = step;
+  hyper_dev[0] = *lr_dev;
+  hyper_dev[1] = (float)(1.0 - pow((double)beta1, (double)step));
+  hyper_dev[2] = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  unsigned long long x = salt_key + 0x9E3779B97F4A7C15ull * (unsigned long long)step;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  g_seed_salt = salt_key ? (x ^ (x >> 31)) : 0ull;
+}
+
+extern "C" int b200rec_train_step_begin(int64_t* step_dev, const float* lr_dev, float beta1, float beta2, float* hyper_dev,
+                                        uint64_t salt_key, void* stream) {
+  if (!step_dev || !lr_dev || !hyper_dev) return fail("train_step_begin: null pointer");
+  train_step_begin_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<long long*>(step_dev), lr_dev, beta1, beta2, hyper_dev, (unsigned long long)salt_key);
+  B200_LAUNCH_OK("train_step_begin_kernel");
   return 0;
 }
 

@@ -383,6 +383,22 @@ def sparse_adam_(table, m, v, rows, grads, n, lr, beta1, beta2, eps, step: int, 
                                         N.ptr(clip), N.stream()), "sparse_adam")
 
 
+def train_step_begin(step_dev, lr_dev, beta1: float, beta2: float, hyper_dev, salt_key: int) -> None:
+    N.check(N.lib().b200rec_train_step_begin(N.ptr(step_dev), N.ptr(lr_dev), beta1, beta2, N.ptr(hyper_dev),
+                                             salt_key & 0xFFFFFFFFFFFFFFFF, N.stream()), "train_step_begin")
+
+
+def adam_dense_dev_(p, g, m, v, beta1, beta2, eps, wd, hyper_dev, clip=None) -> None:
+    N.check(N.lib().b200rec_adam_dense_dev(N.ptr(p), N.ptr(g), N.ptr(m), N.ptr(v), p.numel(), beta1, beta2, eps, wd,
+                                           N.ptr(hyper_dev), N.ptr(clip), N.stream()), "adam_dense_dev")
+
+
+def sparse_adam_dev_(table, m, v, rows, grads, n, beta1, beta2, eps, hyper_dev, clip=None) -> None:
+    N.check(N.lib().b200rec_sparse_adam_dev(N.ptr(table), N.ptr(m), N.ptr(v), table.stride(0), grads.shape[1],
+                                            N.ptr(rows), N.ptr(grads), N.ptr(n), rows.shape[0], beta1, beta2, eps,
+                                            N.ptr(hyper_dev), N.ptr(clip), N.stream()), "sparse_adam_dev")
+
+
 # ------------------------------------------------------------------------------------------------ device-side batch feed
 def gather_rows(table: torch.Tensor, idx: torch.Tensor, err: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[b, :] = table[idx[b], :] (fp32 feature rows); an out-of-range index raises err (int32[1]) to 1."""

@@ -50,6 +50,8 @@ class FlatAdam:
         self._coef = torch.ones((1,), dtype=torch.float32, device=dev)
         self.grad_norm = torch.zeros((1,), dtype=torch.float32, device=dev)
         self.param_groups = [{"lr": lr}]
+        # CUDA-graph training (TwoTowerTrainer.enable_cuda_graph): step counter, lr and Adam's bias corrections on the device
+        self.dev_state = None
 
     def zero_grad(self, set_to_none: bool = False) -> None:
         self.grad.zero_()
@@ -72,6 +74,24 @@ class FlatAdam:
         vals = torch.cat([v for _, v, _ in lists])
         return [K.embedding_sparse_grad(rows, vals, vals.shape[1], p.shape[0], 0)]
 
+    def enable_device_state(self) -> None:
+        if self.dev_state is None:
+            dev = self.flat.device
+            self.dev_state = {"step": torch.full((1,), self.step_count, dtype=torch.int64, device=dev),
+                              "lr": torch.full((1,), float(self.param_groups[0]["lr"]), dtype=torch.float32, device=dev),
+                              "hyper": torch.zeros((3,), dtype=torch.float32, device=dev), "lr_host": None}
+
+    def sync_device_state(self) -> None:
+        """Before a graph replay: the scheduler may have changed the learning rate and eager steps (ragged batches) may
+        have advanced the step counter (tiny fills, outside the graph, only when something changed)."""
+        lr = float(self.param_groups[0]["lr"])
+        if self.dev_state["lr_host"] != lr:
+            self.dev_state["lr"].fill_(lr)
+            self.dev_state["lr_host"] = lr
+        if self.dev_state.get("step_host") != self.step_count:
+            self.dev_state["step"].fill_(self.step_count)
+            self.dev_state["step_host"] = self.step_count
+
     def step(self) -> None:
         self.step_count += 1
         lr = self.param_groups[0]["lr"]
@@ -88,6 +108,15 @@ class FlatAdam:
                     K.sumsq_(vals.reshape(-1), self._acc)   # rows beyond n are zero-filled by the coalescing kernel
             K.clip_coef(self._acc, float(self.max_grad_norm), self._coef, self.grad_norm)
             clip = self._coef
+        if self.dev_state is not None and getattr(self, "use_device_state", False):
+            hyper = self.dev_state["hyper"]   # written by K.train_step_begin at the start of this step
+            K.adam_dense_dev_(self.flat, self.grad, self.m, self.v, self.betas[0], self.betas[1], self.eps, self.wd, hyper,
+                              clip)
+            for p, lists in sparse:
+                m, v = self.sparse_state[id(p)]
+                for rows, vals, n in lists:
+                    K.sparse_adam_dev_(p.data, m, v, rows, vals, n, self.betas[0], self.betas[1], self.eps, hyper, clip)
+            return
         K.adam_dense_(self.flat, self.grad, self.m, self.v, lr, self.betas[0], self.betas[1], self.eps, self.wd,
                       self.step_count, clip)
         for p, lists in sparse:
@@ -125,11 +154,75 @@ class TwoTowerTrainer:
         self.train_losses: List[float] = []
         self.val_losses: List[float] = []
 
+    # ------------------------------------------------------------------ CUDA-graph replay of the hot step
+    def enable_cuda_graph(self, warm_steps: int = 2) -> None:
+        """Replay the training step as ONE CUDA graph per input shape (the eager step is ~210 kernel launches and
+        host-launch-bound at ~18 us each).  The first `warm_steps` calls of a shape run eagerly, the next one is
+        captured; shapes that differ (the ragged last batch) keep running eagerly.  What changes from step to step lives
+        on the device: step counter / lr / Adam bias corrections (b200rec_train_step_begin, *_adam_*_dev) and a
+        per-step salt of every dropout seed.  Not used under data parallel (collectives stay eager)."""
+        self._graph_warm = int(warm_steps)
+        self._graphs: Dict[Any, Any] = {}
+        self._graph_seen: Dict[Any, int] = {}
+        self.optimizer.enable_device_state()
+
+    def _graph_key(self, uf, pf, nf, uc, ic):
+        cat = lambda d: tuple((k, tuple(v.shape), v.dtype) for k, v in (d or {}).items())
+        return (tuple(uf.shape), tuple(pf.shape), None if nf is None else tuple(nf.shape), cat(uc), cat(ic),
+                self.model.training)
+
+    def _graphed_step(self, key, uf, pf, nf, uc, ic):
+        entry = self._graphs.get(key)
+        if entry is None:
+            static = {"uf": uf.clone(), "pf": pf.clone(), "nf": None if nf is None else nf.clone(),
+                      "uc": {k: v.clone() for k, v in (uc or {}).items()},
+                      "ic": {k: v.clone() for k, v in (ic or {}).items()}}
+            opt = self.optimizer
+            opt.sync_device_state()
+            salt = (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + 0x51ED27) & 0xFFFFFFFFFFFFFFFF
+            graph = torch.cuda.CUDAGraph()
+            opt.use_device_state = True
+            try:
+                with torch.cuda.graph(graph):
+                    K.train_step_begin(opt.dev_state["step"], opt.dev_state["lr"], opt.betas[0], opt.betas[1],
+                                       opt.dev_state["hyper"], salt or 1)
+                    loss = self._step_body(static["uf"], static["pf"], static["nf"], static["uc"] or None,
+                                           static["ic"] or None)
+            finally:
+                opt.use_device_state = False
+            opt.step_count -= 1          # the capture ran the Python of one step without executing it
+            entry = self._graphs[key] = (graph, static, loss)
+        graph, static, loss = entry
+        static["uf"].copy_(uf)
+        static["pf"].copy_(pf)
+        if nf is not None:
+            static["nf"].copy_(nf)
+        for k, v in (uc or {}).items():
+            static["uc"][k].copy_(v)
+        for k, v in (ic or {}).items():
+            static["ic"][k].copy_(v)
+        self.optimizer.sync_device_state()
+        graph.replay()
+        self.optimizer.step_count += 1
+        self.optimizer.dev_state["step_host"] = self.optimizer.step_count   # the graph's first node incremented it
+        return loss                      # static tensor: overwritten by the next replay of this shape
+
     # ------------------------------------------------------------------ the hot step (trainers/two_tower.py:98-146)
     def train_step(self, user_features: torch.Tensor, pos_item_features: torch.Tensor,
                    neg_item_features: Optional[torch.Tensor] = None,
                    user_categorical: Optional[Dict[str, torch.Tensor]] = None,
                    item_categorical: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+        if getattr(self, "_graphs", None) is not None and getattr(self.model, "dp", None) is None:
+            key = self._graph_key(user_features, pos_item_features, neg_item_features, user_categorical, item_categorical)
+            seen = self._graph_seen.get(key, 0)
+            self._graph_seen[key] = seen + 1
+            if seen >= self._graph_warm:
+                return self._graphed_step(key, user_features, pos_item_features, neg_item_features, user_categorical,
+                                          item_categorical)
+        return self._step_body(user_features, pos_item_features, neg_item_features, user_categorical, item_categorical)
+
+    def _step_body(self, user_features, pos_item_features, neg_item_features=None, user_categorical=None,
+                   item_categorical=None) -> torch.Tensor:
         model = self.model
         dp = getattr(model, "dp", None)
         self.optimizer.dp = dp

@@ -253,3 +253,51 @@ def test_data_parallel_training_equals_single_process():
                         "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "check_dp_training.py")],
                        cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_cuda_graph_training_step_matches_eager():
+    """TwoTowerTrainer.enable_cuda_graph: the captured step (device-resident step counter / Adam bias corrections) gives
+    the eager losses and parameters; ragged batches fall back to eager without desynchronising the step counter."""
+    from b200rec.trainer import TwoTowerTrainer
+    from b200rec.training_utils import create_two_tower_model_for_training
+    cfg = {"embedding_dim": 32, "hidden_layers": [64, 32], "dropout_rate": 0.0, "temperature": 0.05,
+           "user_categorical_features": {"user_id": 500}, "item_categorical_features": {"item_id": 300},
+           "embedding_dims": {"user_id": 16, "item_id": 16}}
+    g = torch.Generator(device="cuda").manual_seed(3)
+    batches = []
+    for step in range(9):
+        B = 256 if step != 6 else 100      # one ragged batch in the middle
+        batches.append((torch.randn(B, 3, device="cuda", generator=g), torch.randn(B, 20, device="cuda", generator=g),
+                        torch.randint(1, 501, (B,), device="cuda", generator=g),
+                        torch.randint(1, 301, (B,), device="cuda", generator=g)))
+    runs = []
+    for graphed in (False, True):
+        torch.manual_seed(0)
+        model = create_two_tower_model_for_training(3, 20, cfg)
+        tr = TwoTowerTrainer(model, [], [], {"checkpoint_dir": "/tmp/b200rec_graph_test"}, device="cuda")
+        model.train()
+        if graphed:
+            tr.enable_cuda_graph(warm_steps=2)
+        losses = [float(tr.train_step(uf, pf, None, {"user_id": u}, {"item_id": i}).item()) for uf, pf, u, i in batches]
+        runs.append((losses, [p.detach().clone() for p in model.parameters()], tr.optimizer.step_count,
+                     [b.detach().clone() for b in model.buffers()]))
+    (le, pe, se, be), (lg, pg, sg, bg) = runs
+    assert se == sg == len(batches)
+    assert np.allclose(le, lg, rtol=2e-6, atol=0), (le, lg)
+    assert max((a - b).abs().max().item() for a, b in zip(pe, pg)) <= 2e-5
+    assert all(torch.allclose(a.float(), b.float(), atol=1e-6) for a, b in zip(be, bg))
+
+
+def test_cuda_graph_training_with_dropout_varies_masks():
+    from b200rec.trainer import TwoTowerTrainer
+    from b200rec.training_utils import create_two_tower_model_for_training
+    torch.manual_seed(0)
+    model = create_two_tower_model_for_training(3, 20, {"embedding_dim": 32, "hidden_layers": [64, 32], "dropout_rate": 0.5})
+    tr = TwoTowerTrainer(model, [], [], {"checkpoint_dir": "/tmp/b200rec_graph_test", "learning_rate": 0.0,
+                                         "weight_decay": 0.0}, device="cuda")
+    model.train()
+    tr.enable_cuda_graph(warm_steps=1)
+    uf, pf = torch.randn(128, 3, device="cuda"), torch.randn(128, 20, device="cuda")
+    # lr = 0: the parameters never move, so the loss changes from step to step only through the dropout masks
+    losses = [float(tr.train_step(uf, pf).item()) for _ in range(6)]
+    assert np.isfinite(losses).all() and len(set(round(x, 6) for x in losses[1:])) >= 4, losses
