@@ -1059,9 +1059,12 @@ static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k, int s
   const bool want_v2 = v2e ? atoi(v2e) != 0 : true;
   const int v2shape = v2e ? atoi(v2e) : (q128 >= 3 ? 2 : 1);
   if (want_v2 && q128 >= 2 && (sms % 2) == 0) {
-    if (v2shape == 2 && stream_geom2<2>(p.g, N, (int)Q, KB, sms, TopkEpi::SCRATCH_BYTES) && p.g.max_parts + 1 <= FIN_MAX_SRC) {
+    // (the final kernel tabulates every unit's last supertile in FIN_MAX_SRC shared-memory slots)
+    if (v2shape == 2 && stream_geom2<2>(p.g, N, (int)Q, KB, sms, TopkEpi::SCRATCH_BYTES) && p.g.max_parts + 1 <= FIN_MAX_SRC &&
+        p.g.grid / 2 <= FIN_MAX_SRC) {
       p.v2 = 2, p.nq = 2, p.bn = 128, ok = true;  // nq/bn describe one CTA's share: 256 slots, 128 columns per thread
-    } else if (stream_geom2<1>(p.g, N, (int)Q, KB, sms, TopkEpi::SCRATCH_BYTES) && 2 * p.g.max_parts + 1 <= FIN_MAX_SRC) {
+    } else if (stream_geom2<1>(p.g, N, (int)Q, KB, sms, TopkEpi::SCRATCH_BYTES) && 2 * p.g.max_parts + 1 <= FIN_MAX_SRC &&
+               p.g.grid / 2 <= FIN_MAX_SRC) {
       p.v2 = 1, p.nq = 2, p.bn = 128, ok = true;
     }
   }
