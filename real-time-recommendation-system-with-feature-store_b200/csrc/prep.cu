@@ -128,34 +128,42 @@ prep_rows_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int6
   }
 }
 
-// dst[r, c] = src[c, r]   (src has `cols` rows of `rows` floats); 64 (dst columns) x 32 (dst rows) tiles through padded
-// shared memory, 4-byte (bf16x2) stores: 128 B per warp and term instead of 64 B
+// dst[r, c] = src[c, r]   (src has `cols` rows of `rows` floats).  One block = 32 dst rows x 128 dst columns: the source
+// tile is transposed on its way into shared memory (row stride 132 floats keeps the rows 16-byte aligned), every lane
+// then reads four consecutive columns with one 128-bit shared load and stores them as one 8-byte bf16x4 per term block:
+// 256 B per warp and store instead of 64-128 B.
 __global__ void __launch_bounds__(256)
 prep_transpose_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int64_t ld_src,
                       __nv_bfloat16* __restrict__ dst, int64_t kpad, int terms, int side) {
-  __shared__ float tile[64][33];
-  const int64_t r0 = (int64_t)blockIdx.y * 32;  // dst rows   = src columns
-  const int64_t c0 = (int64_t)blockIdx.x * 64;  // dst cols   = src rows
+  __shared__ __align__(16) float tile[32][132];
+  const int64_t r0 = (int64_t)blockIdx.y * 32;   // dst rows   = src columns
+  const int64_t c0 = (int64_t)blockIdx.x * 128;  // dst cols   = src rows
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-#pragma unroll
-  for (int i = ty; i < 64; i += 8) {
+#pragma unroll 4
+  for (int i = ty; i < 128; i += 8) {
     const int64_t sr = c0 + i, sc = r0 + tx;
-    tile[i][tx] = (sr < cols && sc < rows) ? __ldg(src + sr * ld_src + sc) : 0.f;
+    tile[tx][i] = (sr < cols && sc < rows) ? __ldg(src + sr * ld_src + sc) : 0.f;
   }
   __syncthreads();
 #pragma unroll
   for (int i = ty; i < 32; i += 8) {
-    const int64_t r = r0 + i, c = c0 + 2 * tx;
-    if (r < rows && c < kpad) {   // kpad is a multiple of 8, c is even: c + 1 < kpad
-      __nv_bfloat16 pa[3], pb[3];
-      split3(tile[2 * tx][i], pa[0], pa[1], pa[2]);
-      split3(tile[2 * tx + 1][i], pb[0], pb[1], pb[2]);
+    const int64_t r = r0 + i, c = c0 + 4 * tx;
+    if (r < rows && c < kpad) {   // kpad is a multiple of 8 and c of 4: c + 3 < kpad
+      const float4 x = *reinterpret_cast<const float4*>(&tile[i][4 * tx]);
+      __nv_bfloat16 p0[3], p1[3], p2[3], p3[3];
+      split3(x.x, p0[0], p0[1], p0[2]);
+      split3(x.y, p1[0], p1[1], p1[2]);
+      split3(x.z, p2[0], p2[1], p2[2]);
+      split3(x.w, p3[0], p3[1], p3[2]);
       __nv_bfloat16* drow = dst + r * terms * kpad;
 #pragma unroll
       for (int t = 0; t < 6; ++t) {
         if (t < terms) {
           const int part = part_of(terms, side, t);
-          *reinterpret_cast<uint32_t*>(drow + t * kpad + c) = pack2(pa[part], pb[part]);
+          uint2 o;
+          o.x = pack2(p0[part], p1[part]);
+          o.y = pack2(p2[part], p3[part]);
+          *reinterpret_cast<uint2*>(drow + t * kpad + c) = o;
         }
       }
     }
@@ -185,7 +193,7 @@ extern "C" int b200rec_split_bf16(const float* src, int64_t rows, int64_t cols, 
                                            reinterpret_cast<__nv_bfloat16*>(dst), kpad, terms, side);
     B200_LAUNCH_OK("prep_rows_kernel");
   } else {
-    dim3 grid((unsigned)((kpad + 63) / 64), (unsigned)((rows + 31) / 32));
+    dim3 grid((unsigned)((kpad + 127) / 128), (unsigned)((rows + 31) / 32));
     if (grid.y > 65535) return fail("split_bf16(transpose): too many rows (%lld)", (long long)rows);
     prep_transpose_kernel<<<grid, 256, 0, st>>>(src, rows, cols, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), kpad,
                                                 terms, side);

@@ -291,7 +291,11 @@ class InBatchCEFn(Function):
             S = K.gemm_tn(uo[r0:r1], io, rows, NI, uo.shape[1])
             K.softmax_grad_(S, inv_t, lse[r0:r1], diag_offset + r0, inv_t / total_rows, gdev)
             go = K.split_bf16(S, terms, 0)                            # [rows, terms*kpad(NI)]
-            K.gemm_tn(go, it, rows, E, go.shape[1], out=du[r0:r1])
+            # [rows x E] output with K = terms * NI: a handful of tiles and a very long reduction -> split K over the SMs
+            # (16 CTAs on 148 SMs ran this GEMM at 115-200 us per chunk)
+            tiles = math.ceil(rows / 128) * math.ceil(E / (64 if E <= 64 else 128))
+            ks = max(1, min(16, NUM_SMS // tiles, go.shape[1] // 512))
+            K.gemm_tn(go, it, rows, E, go.shape[1], k_splits=ks, out=du[r0:r1])
             gt = K.split_bf16(S, terms, 0, transpose=True)            # [NI, terms*kpad(rows)]
             ut = K.split_bf16(u[r0:r1], terms, 1, transpose=True)     # [E,  terms*kpad(rows)]
             K.gemm_tn(gt, ut, NI, E, gt.shape[1], k_splits=2, out=di, accumulate=True)
