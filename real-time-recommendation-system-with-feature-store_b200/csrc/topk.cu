@@ -1268,9 +1268,13 @@ extern "C" int b200rec_debug_topk_kernel_timing(int enable, float* last_ms_host)
 }
 
 extern "C" size_t b200rec_topk_workspace_bytes(int64_t N, int64_t ld, int64_t Q, int k) {
-  b200::TopkPlan p;
+  // one workspace serves the search and the pooled sampling pass of row shards, whose densest sample (two shards) is
+  // twice as dense as the local one
+  b200::TopkPlan p, p2;
   if (b200::plan_topk(p, N, ld, Q, k)) return 0;
-  return p.total();
+  size_t need = p.total();
+  if (b200::plan_topk(p2, N, ld, Q, k, 2) == 0 && p2.total() > need) need = p2.total();
+  return need;
 }
 
 static int topk_dispatch(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k,
