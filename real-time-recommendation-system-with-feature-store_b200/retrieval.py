@@ -212,6 +212,7 @@ class B200FlatIndex(IndexBase):
         self.index.add(np.asarray(embeddings, dtype=np.float32), normalize=(self.metric == "cosine"))
         self.id_map = {}
         self.reverse_id_map = {}
+        self._id_array = None
         for i, item_id in enumerate(ids):
             self.id_map[i] = item_id
             self.reverse_id_map[item_id] = i
@@ -222,11 +223,23 @@ class B200FlatIndex(IndexBase):
                filter_ids: Optional[List[str]] = None) -> Tuple[List[List[str]], List[List[float]]]:
         if self.index is None:
             raise ValueError("Index not built yet")
-        query_embeddings = np.asarray(query_embeddings).astype(np.float32)
+        if not (torch.is_tensor(query_embeddings) and query_embeddings.is_cuda):   # device tensors skip the host round trip
+            query_embeddings = np.asarray(query_embeddings).astype(np.float32)
         if len(query_embeddings.shape) == 1:
             query_embeddings = query_embeddings.reshape(1, -1)
         k_search = min(k * 2, self.current_size) if filter_ids else k
         distances, indices = self.index.search(query_embeddings, k_search, normalize=(self.metric == "cosine"))
+        if filter_ids is None and len(self.id_map) == self.current_size:
+            # vectorised idx -> id map (the reference walks nq x k entries in Python, retrieval.py:177-195)
+            if getattr(self, "_id_array", None) is None or len(self._id_array) != self.current_size:
+                self._id_array = np.empty(self.current_size, dtype=object)
+                self._id_array[:] = [self.id_map[i] for i in range(self.current_size)]
+            valid = (indices >= 0) & (indices < self.current_size)
+            names = self._id_array[np.where(valid, indices, 0)]
+            if valid.all():
+                return names[:, :k].tolist(), distances[:, :k].astype(float).tolist()
+            return ([names[i][valid[i]][:k].tolist() for i in range(len(indices))],
+                    [distances[i][valid[i]][:k].astype(float).tolist() for i in range(len(indices))])
         allowed = set(filter_ids) if filter_ids is not None else None
         batch_ids, batch_distances = [], []
         for i in range(len(query_embeddings)):
@@ -292,6 +305,7 @@ class B200FlatIndex(IndexBase):
             data = pickle.load(f)
         self.id_map = data["id_map"]
         self.reverse_id_map = data["reverse_id_map"]
+        self._id_array = None
         self.current_size = data["current_size"]
         self.config = data["config"]
         self.dimension = d

@@ -165,3 +165,55 @@ def test_sharded_retrieval_world_size_2_gloo(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert [open(tmp_path / f"ok{r}").read() for r in range(2)] == ["1", "1"]
+
+
+def test_retrieval_batcher_groups_concurrent_requests():
+    """Host logic of the serving micro-batcher (no GPU: a stand-in model and index): concurrent requests share one tower
+    forward and one search, every caller gets its own rows cut to its own k, failures reach every waiting caller."""
+    import asyncio
+    import torch
+    from b200rec.serving import RetrievalBatcher
+
+    class Model:
+        def __init__(self):
+            self.w = torch.nn.Parameter(torch.eye(4))
+            self.calls = []
+
+        def parameters(self):
+            return iter([self.w])
+
+        def get_user_embeddings(self, feats):
+            self.calls.append(tuple(feats["numerical"].shape))
+            return feats["numerical"] @ self.w
+
+    class Index:
+        def __init__(self):
+            self.calls = []
+            self.fail = False
+
+        def search(self, emb, k):
+            if self.fail:
+                raise ValueError("Index not built yet")
+            self.calls.append((emb.shape[0], k))
+            return ([[f"item_{int(e[0])}_{j}" for j in range(k)] for e in emb],
+                    [[float(e[0]) - j for j in range(k)] for e in emb])
+
+    class Engine:
+        def __init__(self):
+            self.index, self.total_queries, self.total_latency = Index(), 0, 0.0
+
+    async def run():
+        model, engine = Model(), Engine()
+        b = RetrievalBatcher(model, engine, max_batch=4, max_wait_ms=5.0)
+        reqs = [({"numerical": torch.tensor([[float(i), 0., 0., 0.]]), "categorical": {}}, 2 + i % 3) for i in range(10)]
+        out = await asyncio.gather(*[b.recommend(f, k) for f, k in reqs])
+        assert [c[0] for c in model.calls] == [4, 4, 2] and [c[0] for c in engine.index.calls] == [4, 4, 2]
+        assert engine.index.calls[0][1] == 4                      # searched with the largest k of the batch
+        for i, ((ids, scores, m), (_, k)) in enumerate(zip(out, reqs)):
+            assert ids == [[f"item_{i}_{j}" for j in range(k)]] and len(scores[0]) == k and m["num_results"] == k
+        assert engine.total_queries == 10 and b.batches == 3
+        engine.index.fail = True
+        res = await asyncio.gather(*[b.recommend(f, k) for f, k in reqs[:3]], return_exceptions=True)
+        assert all(isinstance(r, ValueError) for r in res)
+
+    asyncio.run(run())

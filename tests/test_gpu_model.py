@@ -301,3 +301,36 @@ def test_cuda_graph_training_with_dropout_varies_masks():
     # lr = 0: the parameters never move, so the loss changes from step to step only through the dropout masks
     losses = [float(tr.train_step(uf, pf).item()) for _ in range(6)]
     assert np.isfinite(losses).all() and len(set(round(x, 6) for x in losses[1:])) >= 4, losses
+
+
+def test_serving_batcher_equals_unbatched_requests():
+    """Concurrent requests through RetrievalBatcher (one tower forward + one exact search per batch) return what the
+    per-request path of the reference service returns (user-tower forward on [1,F], engine.retrieve(embedding, k))."""
+    import asyncio
+    from b200rec.retrieval import RetrievalEngine
+    from b200rec.serving import RetrievalBatcher
+    from b200rec.training_utils import create_two_tower_model_for_training
+    torch.manual_seed(5)
+    model = create_two_tower_model_for_training(10, 10, {"embedding_dim": 64, "hidden_layers": [128, 64]}).cuda().eval()
+    rng = np.random.default_rng(5)
+    items = rng.standard_normal((5000, 10)).astype(np.float32)
+    with torch.no_grad():
+        emb = model.get_item_embeddings({"numerical": torch.from_numpy(items).cuda(), "categorical": {}}).cpu().numpy()
+    engine = RetrievalEngine({"index_type": "b200", "embedding_dim": 64})
+    engine.build_index(emb, [f"item_{i}" for i in range(len(emb))])
+    users = [torch.from_numpy(rng.standard_normal((1, 10)).astype(np.float32)) for _ in range(37)]
+    ks = [5 + (i % 4) * 5 for i in range(37)]
+
+    async def run():
+        b = RetrievalBatcher(model, engine, max_batch=16, max_wait_ms=1.0)
+        out = await asyncio.gather(*[b.recommend({"numerical": u, "categorical": {}}, k) for u, k in zip(users, ks)])
+        return out, b.batches
+
+    got, batches = asyncio.run(run())
+    assert batches == 3
+    for u, k, (ids, scores, _) in zip(users, ks, got):
+        with torch.no_grad():
+            e = model.get_user_embeddings({"numerical": u.cuda(), "categorical": {}}).cpu().numpy()
+        rids, rscores, _ = engine.retrieve(e, k=k)
+        assert ids[0] == rids[0]
+        assert np.allclose(scores[0], rscores[0], atol=1e-5)
