@@ -73,6 +73,9 @@ int b200rec_flat_ip_topk(const void* catalogue, int64_t N, int64_t ld, const voi
 int b200rec_topk_sample(const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q, int k, int k_out,
                         int shards, float* out_vals, void* workspace, size_t workspace_bytes, void* stream);
 int b200rec_topk_has_sample(int64_t N, int64_t ld, int64_t Q, int k);
+/* out_kth[q] = k-th largest of the parts x k_in pooled sample maxima vals[parts][Q][k_in] of query q: the shared
+ * starting threshold of row-sharded search (a lower bound of the global k-th score), in one launch. */
+int b200rec_topk_pooled_kth(const float* vals, int parts, int64_t Q, int k_in, int k, float* out_kth, void* stream);
 /* Fan-out variants for row-sharded search over NVLink peer memory: the select kernels store every result row to n_dst
  * (<= 16) destinations — dst_*[d] are device pointers to [Q,k] (resp. [Q,k_out]) arrays, typically this shard's slot in
  * each GPU's gather buffer (peer-mapped symmetric memory) — so the kernel that produces the local top-k is also the

@@ -905,6 +905,32 @@ sample_topk_kernel(const float* __restrict__ S, int m, int k, int P, int stage_c
   }
 }
 
+// k-th largest of the `parts` x k_in pooled sample maxima of every query (parts-major layout [parts][Q][k_in], as the
+// shards' fan-out stores leave it): the shared threshold of row-sharded search in one launch (no ids, no sort output)
+struct PooledLoader {
+  const float* vals;
+  size_t part_stride;
+  int k_in;
+  __device__ __forceinline__ uint64_t operator()(int i) const {
+    const int p = i / k_in, j = i - p * k_in;
+    return (static_cast<uint64_t>(f32_ord(__ldcg(vals + (size_t)p * part_stride + j))) << 32) | static_cast<uint64_t>(~(uint32_t)i);
+  }
+};
+__global__ void __launch_bounds__(FIN_THREADS)
+pooled_kth_kernel(const float* __restrict__ vals, int parts, long long Q, int k_in, int k, int P, int stage_cap,
+                  float* __restrict__ out_kth) {
+  extern __shared__ uint64_t fin_smem[];
+  __shared__ uint32_t hist[256];
+  __shared__ int s_misc[8];
+  const long long q = blockIdx.x;
+  PooledLoader ld{vals + (size_t)q * k_in, (size_t)Q * k_in, k_in};
+  block_select_sort(ld, parts * k_in, k, fin_smem, P, hist, s_misc, fin_smem + P, stage_cap);
+  if (threadIdx.x == 0) {
+    const uint64_t key = fin_smem[k - 1];
+    out_kth[q] = key == 0ull ? -FLT_MAX : ord_f32((uint32_t)(key >> 32));
+  }
+}
+
 // thresholds supplied by the caller (a valid lower bound of each query's final k-th score), with the same 64-ulp slack
 __global__ void topk_init_from_kernel(QMeta* meta, int Q, const float* __restrict__ tau_init) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1356,6 +1382,21 @@ extern "C" int b200rec_topk_has_sample(int64_t N, int64_t ld, int64_t Q, int k) 
   b200::TopkPlan p;
   if (b200::plan_topk(p, N, ld, Q, k)) return 0;
   return p.sample_m > 0 ? 1 : 0;
+}
+
+extern "C" int b200rec_topk_pooled_kth(const float* vals, int parts, int64_t Q, int k_in, int k, float* out_kth,
+                                       void* stream) {
+  using namespace b200;
+  if (!vals || !out_kth) return fail("topk_pooled_kth: null pointer");
+  if (parts < 1 || Q < 1 || k_in < 1 || k < 1 || k > 2048) return fail("topk_pooled_kth: bad sizes");
+  if ((int64_t)parts * k_in < k) return fail("topk_pooled_kth: the pool holds fewer than k values");
+  const int P = next_pow2(k);
+  const int64_t n_in = (int64_t)parts * k_in;
+  const int sc = (n_in + P) * 8 <= 40960 ? (int)n_in : 0;
+  pooled_kth_kernel<<<(unsigned)Q, FIN_THREADS, (P + sc) * sizeof(uint64_t), reinterpret_cast<cudaStream_t>(stream)>>>(
+      vals, parts, (long long)Q, k_in, k, P, sc, out_kth);
+  B200_LAUNCH_OK("pooled_kth_kernel");
+  return 0;
 }
 
 extern "C" int b200rec_topk_merge(const float* scores, const int64_t* ids, int parts, int64_t Q, int k_in, int k_out,

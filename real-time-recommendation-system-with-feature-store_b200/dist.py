@@ -50,7 +50,6 @@ class _PeerExchange:
         self.tau_all = self.buf[off[0]: off[0] + world * q * kx * 4].view(torch.float32).view(world, q, kx)
         self.s_all = self.buf[off[1]: off[1] + world * q * k * 4].view(torch.float32).view(world, q, k)
         self.i_all = self.buf[off[2]: off[2] + world * q * k * 8].view(torch.int64).view(world, q, k)
-        self.tau_ids = torch.arange(world * q * kx, dtype=torch.int64, device=device).view(world, q, kx)
 
     def barrier(self, channel: int) -> None:
         self.hdl.barrier(channel=channel)
@@ -124,8 +123,8 @@ class ShardedFlatIndex:
         ix = self.peer_index
         ix.sample_fanout(queries, k, px.tau_all.shape[2], world, px.tau_dst)     # (1) sample -> every gather buffer
         px.barrier(0)
-        top, _ = self.merge(px.tau_all, px.tau_ids, k)                           # (2) k-th best of the pooled sample
-        tau = top[:, k - 1].contiguous()
+        from . import kernels as K
+        tau = K.topk_pooled_kth(px.tau_all, k)                                   # (2) k-th best of the pooled sample
         ix.search_fanout(queries, k, tau, px.s_dst, px.i_dst)                    # (3) local top-k -> every gather buffer
         px.barrier(1)
         return self.merge(px.s_all, px.i_all, k)                                 # (4) k-way select

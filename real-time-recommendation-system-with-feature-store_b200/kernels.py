@@ -104,6 +104,15 @@ def flat_ip_topk(catalogue: torch.Tensor, queries: torch.Tensor, k: int, row_off
     return scores, ids
 
 
+def topk_pooled_kth(vals: torch.Tensor, k: int) -> torch.Tensor:
+    """vals [parts, Q, k_in] fp32 (contiguous) -> [Q]: k-th largest of each query's parts*k_in pooled sample maxima."""
+    assert vals.dim() == 3 and vals.is_contiguous() and vals.dtype == torch.float32
+    parts, q, k_in = vals.shape
+    out = torch.empty((q,), dtype=torch.float32, device=vals.device)
+    N.check(N.lib().b200rec_topk_pooled_kth(N.ptr(vals), parts, q, k_in, k, N.ptr(out), N.stream()), "topk_pooled_kth")
+    return out
+
+
 def _ptr_table(ptrs):
     import ctypes
     return (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])

@@ -212,6 +212,7 @@ def test_sharded_search_with_shared_thresholds_single_gpu():
     vals = torch.stack([ix.sample_device(q_op, k, kx, 2) for ix in shards])     # [2, Q, kx]: thinned sample, kx maxima each
     ids = torch.arange(vals.numel(), device="cuda").view_as(vals)
     tau = KR.topk_merge(vals.contiguous(), ids.contiguous(), k)[0][:, k - 1].contiguous()
+    assert torch.equal(tau, KR.topk_pooled_kth(vals.contiguous(), k))            # the one-launch form the shards use
     assert (tau.cpu().numpy() <= rD[:, k - 1] + 1e-6).all(), "shared threshold must be a lower bound of the k-th score"
     parts = [ix.search_device(q_op, k, tau_init=tau) for ix in shards]
     s = torch.stack([p[0] for p in parts]).contiguous()
