@@ -217,3 +217,48 @@ def test_retrieval_batcher_groups_concurrent_requests():
         assert all(isinstance(r, ValueError) for r in res)
 
     asyncio.run(run())
+
+
+def _gloo_dp_worker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    from b200rec.dist import DataParallel, ShardedFlatIndex, _AllGatherRows
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(3)
+    B, E = 5, 4
+    xs = [torch.randn(B, E, generator=g) for _ in range(world)]          # every rank's local rows (same on all ranks)
+    ws = [torch.randn(world * B, E, generator=g) for _ in range(world)]  # every rank's weights on the gathered rows
+    x = xs[rank].clone().requires_grad_(True)
+    y = _AllGatherRows.apply(x, None)
+    ok = torch.equal(y.detach(), torch.cat(xs))                          # forward: rank-major concatenation
+    (y * ws[rank]).sum().backward()
+    want = sum(w[rank * B:(rank + 1) * B] for w in ws)                   # backward: every rank's gradient of MY rows, summed
+    ok = ok and torch.allclose(x.grad, want, atol=1e-6)
+
+    class M:  # DataParallel only attaches itself to the model and its towers
+        pass
+    m = M(); m.user_tower = M(); m.item_tower = M()
+    dp = DataParallel(m)
+    ok = ok and m.dp is dp and m.user_tower.dp is dp and dp.world == world and dp.rank == rank
+    t = torch.full((3,), float(rank + 1), dtype=torch.float64)
+    dp.reduce_sums(t)
+    ok = ok and torch.equal(t, torch.full((3,), float(sum(range(1, world + 1))), dtype=torch.float64))
+    rows, vals = dp.gather_sparse(torch.tensor([rank + 1, 0]), torch.full((2, 3), float(rank)))
+    ok = ok and rows.tolist() == [1, 0, 2, 0] and vals[2].tolist() == [1.0, 1.0, 1.0]
+    ok = ok and float(dp.global_loss(torch.tensor(0.5 * (rank + 1)))) == 1.5
+    ok = ok and ShardedFlatIndex.exchange_width(100, 8) == 33 and ShardedFlatIndex.exchange_width(100, 1) == 100
+    with open(os.path.join(tmp, f"dp{rank}"), "w") as fh:
+        fh.write("1" if ok else "0")
+    dist.destroy_process_group()
+
+
+def test_data_parallel_plumbing_world_size_2_gloo(tmp_path):
+    """The collectives of exact data-parallel training on CPU tensors (gloo): all-gathered rows with reduce-scattered
+    gradients, summed statistics, gathered sparse rows, the global loss, the threshold-exchange width."""
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert [open(tmp_path / f"dp{r}").read() for r in range(2)] == ["1", "1"]
