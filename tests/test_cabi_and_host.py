@@ -262,3 +262,23 @@ def test_data_parallel_plumbing_world_size_2_gloo(tmp_path):
     port = 31500 + (os.getpid() % 2000)
     mp.spawn(_gloo_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert [open(tmp_path / f"dp{r}").read() for r in range(2)] == ["1", "1"]
+
+
+def test_feed_positives_csr_host_logic():
+    """dict user -> positives (reference get_user_positive_items) -> CSR over users: duplicates collapse like the
+    reference's set(), users without interactions get empty rows, out-of-range users are ignored."""
+    import numpy as np
+    from b200rec.feed import positives_csr
+    indptr, items = positives_csr({0: [5, 3, 5, 1], 2: [7], 9: [1]}, n_users=4)
+    assert indptr.tolist() == [0, 3, 3, 4, 4] and items.tolist() == [1, 3, 5, 7] and items.dtype == np.int32
+    indptr, items = positives_csr({}, n_users=3)
+    assert indptr.tolist() == [0, 0, 0, 0] and items.size >= 1      # never an empty device buffer
+
+
+def test_feed_requires_cuda_and_big_enough_pools():
+    import numpy as np
+    import pytest
+    from b200rec.feed import DeviceInteractionFeed
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        DeviceInteractionFeed(np.zeros(4, np.int64), np.zeros(4, np.int64), np.ones(4), np.zeros((2, 3), np.float32),
+                              np.zeros((5, 2), np.float32), {}, device="cpu")
