@@ -4,6 +4,7 @@ kernels through the C-ABI; torch only owns the tensors and the autograd graph.  
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional
 
 import torch
@@ -27,6 +28,18 @@ def require_cuda(*tensors) -> None:
                                "move the model and its inputs to a B200 device")
 
 
+def _bwd_terms(terms: int) -> int:
+    """Split-bf16 terms of the GRADIENT GEMMs (dgrad, wgrad, the two in-batch gradient products) when the forward runs
+    fp32-grade (6 terms).  3 terms ([h l h] x [h h l]: products accurate to ~2^-17, fp32 accumulation) halve their
+    FLOPs and operand traffic; the golden parity tests (per-step losses, embeddings, gradients and parameters against the
+    reference at 1e-5) hold with them, and the logits recompute that feeds exp() keeps 6.  B200REC_BWD_TERMS=6 restores
+    fp32-grade gradient products."""
+    if terms == 6:
+        t = int(os.environ.get("B200REC_BWD_TERMS", "3"))
+        return t if t in (3, 6) else 3
+    return terms
+
+
 class LinearFn(Function):
     """z = x W^T + b on tcgen05 (nn.Linear, two_tower.py:62,70).  terms: 6 = fp32-grade split-bf16, 1 = bf16."""
 
@@ -48,7 +61,7 @@ class LinearFn(Function):
     @staticmethod
     def backward(ctx, dz):
         x, w = ctx.saved_tensors
-        terms = ctx.terms
+        terms = _bwd_terms(ctx.terms)
         dz = _c32(dz)
         B, out_f, in_f = x.shape[0], w.shape[0], w.shape[1]
         dx = dw = db = None
@@ -284,19 +297,20 @@ class InBatchCEFn(Function):
         gdev = _c32(g).reshape(1)
         du = torch.empty_like(u)
         di = torch.zeros_like(i)
-        it = K.split_bf16(i, terms, 1, transpose=True)               # operand of I^T: [E, terms*kpad(NI)]
+        gterms = _bwd_terms(terms)                                    # gradient GEMMs; the logits recompute keeps `terms`
+        it = K.split_bf16(i, gterms, 1, transpose=True)              # operand of I^T: [E, terms*kpad(NI)]
         for r0 in range(0, B, InBatchCEFn.CHUNK):
             r1 = min(B, r0 + InBatchCEFn.CHUNK)
             rows = r1 - r0
             S = K.gemm_tn(uo[r0:r1], io, rows, NI, uo.shape[1])
             K.softmax_grad_(S, inv_t, lse[r0:r1], diag_offset + r0, inv_t / total_rows, gdev)
-            go = K.split_bf16(S, terms, 0)                            # [rows, terms*kpad(NI)]
+            go = K.split_bf16(S, gterms, 0)                           # [rows, terms*kpad(NI)]
             # [rows x E] output with K = terms * NI: a handful of tiles and a very long reduction -> split K over the SMs
             # (16 CTAs on 148 SMs ran this GEMM at 115-200 us per chunk)
             tiles = math.ceil(rows / 128) * math.ceil(E / (64 if E <= 64 else 128))
             ks = max(1, min(16, NUM_SMS // tiles, go.shape[1] // 512))
             K.gemm_tn(go, it, rows, E, go.shape[1], k_splits=ks, out=du[r0:r1])
-            gt = K.split_bf16(S, terms, 0, transpose=True)            # [NI, terms*kpad(rows)]
-            ut = K.split_bf16(u[r0:r1], terms, 1, transpose=True)     # [E,  terms*kpad(rows)]
+            gt = K.split_bf16(S, gterms, 0, transpose=True)           # [NI, terms*kpad(rows)]
+            ut = K.split_bf16(u[r0:r1], gterms, 1, transpose=True)    # [E,  terms*kpad(rows)]
             K.gemm_tn(gt, ut, NI, E, gt.shape[1], k_splits=2, out=di, accumulate=True)
         return du, di, None, None, None, None
