@@ -31,6 +31,7 @@ for sparse, mixed in ((False, False), (True, False), (False, True)):
         ref_model = make(); ref_trainer = TwoTowerTrainer(ref_model, [], [], tcfg, device=str(dev)); ref_model.train()
         g = torch.Generator(device=dev).manual_seed(99)
         losses, ref_losses = [], []
+        grad_rel = 0.0
         for step in range(4):
             uf = torch.randn(world * B, FD, device=dev, generator=g); pf = torch.randn(world * B, FD, device=dev, generator=g)
             nf = torch.randn(world * B, R, FD, device=dev, generator=g) if mixed else None
@@ -40,17 +41,22 @@ for sparse, mixed in ((False, False), (True, False), (False, True)):
             losses.append(trainer.train_step(uf[sl], pf[sl], nf[sl] if mixed else None, cu, ci))
             cu, ci = (None, None) if mixed else ({"user_id": uid}, {"item_id": iid})
             ref_losses.append(ref_trainer.train_step(uf, pf, nf, cu, ci))
+            if step == 0:   # the summed DP gradient vs the single-process gradient, before Adam turns noise into steps
+                gd, gr = trainer.optimizer.grad, ref_trainer.optimizer.grad
+                grad_rel = ((gd - gr).norm() / gr.norm()).item()
         l = torch.stack([x.reshape(()) for x in losses]).cpu(); r = torch.stack([x.reshape(()) for x in ref_losses]).cpu()
         rel = ((l - r).abs() / r.abs()).max().item()
         pmax = 0.0
         for (n1, p1), (_, p2) in zip(dp_model.named_parameters(), ref_model.named_parameters()):
             pmax = max(pmax, (p1.detach() - p2.detach()).abs().max().item())
         bn = max((b1 - b2).abs().max().item() for (k1, b1), (_, b2) in zip(dp_model.named_buffers(), ref_model.named_buffers()) if b1.dtype.is_floating_point)
-        good = rel <= 1e-5 and pmax <= 1e-4 and bn <= 1e-5   # Adam turns 1e-9 gradient noise on near-zero gradients into 1e-5 steps
+        # losses and first-step gradients agree to rounding (the two runs sum in different orders: chunking, split-K);
+        # parameters are only bounded loosely: Adam turns 1e-9 gradient noise on near-zero gradients into lr-sized steps
+        good = rel <= 1e-6 and grad_rel <= 1e-5 and pmax <= 1e-3 and bn <= 1e-5
         ok = ok and good
         if rank == 0:
             print(f"sparse_tables={sparse} mixed_loss={mixed}: losses DP {l.tolist()} vs single {r.tolist()} max rel diff {rel:.2e}; "
-                  f"max |param diff| {pmax:.2e}; max |BN running-stat diff| {bn:.2e} -> {'OK' if good else 'MISMATCH'}", flush=True)
+                  f"first-step gradient rel diff {grad_rel:.2e}; max |param diff| {pmax:.2e}; max |BN running-stat diff| {bn:.2e} -> {'OK' if good else 'MISMATCH'}", flush=True)
 flag = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 # throughput of the DP step at the config-2 shape (per-GPU batch 8192)
 B2, NU2, NI2 = 8192, 1_000_000, 100_000
