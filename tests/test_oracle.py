@@ -198,3 +198,38 @@ def test_feed_oracle_matches_reference_batches():
     # the sampler's contract, used as the property oracle for the device sampler
     for u, neg in zip(b["user_idx"].tolist(), b["neg_item_indices"].tolist()):
         assert len(set(neg)) == len(neg) and not (set(neg) & set(pos[u])) and all(0 <= x < int(g["n_items"]) for x in neg)
+
+
+def test_wrapper_oracle_matches_the_reference_wrapper():
+    """oracle.flat_ip.FaissIndexOracle (FaissIndex wrapper restated) against the REFERENCE's own FaissIndex /
+    RetrievalEngine code run with a numpy stand-in for faiss (tests/golden/make_golden_wrapper.py): casts, 1-D promotion,
+    cosine normalisation, id maps, the filter_ids post-pass with k_search = min(2k, N), incremental add."""
+    import json
+    import os
+    from oracle.flat_ip import FaissIndexOracle
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wrapper_small.npz"))
+    cases = json.loads(str(g["cases_json"]))
+    allowed = json.loads(str(g["allowed_json"]))
+    emb, extra, qry, N, D = g["emb"], g["extra"], g["qry"], int(g["N"]), int(g["D"])
+    ids = [f"item_{i}" for i in range(N)]
+    extra_ids = [f"new_{i}" for i in range(len(extra))]
+
+    def same(got, want):
+        assert got[0] == want[0]                                   # item ids, list of lists
+        assert len(got[1]) == len(want[1])
+        for a, b in zip(got[1], want[1]):
+            assert np.allclose(a, b, rtol=0, atol=1e-6)
+
+    for metric in ("cosine", "ip"):
+        ix = FaissIndexOracle({"dimension": D, "metric": metric})
+        ix.build(emb.copy(), ids)
+        same(ix.search(qry.copy(), k=10), cases[f"{metric}_k10"])
+        same(ix.search(qry[0].copy(), k=5), cases[f"{metric}_1d_k5"])
+        same(ix.search(qry.copy(), k=7, filter_ids=allowed), cases[f"{metric}_filter_k7"])
+        ix.add(extra.copy(), extra_ids)
+        same(ix.search(qry.copy(), k=10), cases[f"{metric}_after_add_k10"])
+        assert ix.current_size == cases[f"{metric}_size"]
+    ix = FaissIndexOracle({"dimension": D, "metric": "cosine"})
+    ix.build(emb.copy(), ids)
+    same(ix.search(qry[:2].copy(), k=6), cases["engine_retrieve_k6"])
+    assert cases["engine_metrics_keys"] == ["avg_score", "cache_hit", "latency_ms", "num_results"]  # mirrored by b200rec.retrieval
