@@ -233,3 +233,23 @@ def test_wrapper_oracle_matches_the_reference_wrapper():
     ix.build(emb.copy(), ids)
     same(ix.search(qry[:2].copy(), k=6), cases["engine_retrieve_k6"])
     assert cases["engine_metrics_keys"] == ["avg_score", "cache_hit", "latency_ms", "num_results"]  # mirrored by b200rec.retrieval
+
+
+def test_flat_ip_oracle_matches_the_reference_recommendation_twin():
+    """IndexFlatIP restated (with the exclusion lists of the eval path) against the REFERENCE's generate_recommendations
+    (scripts/evaluate_model.py:160-234: np.dot, -inf mask of the train items, argsort[::-1][:k]) on tie-free synthetic
+    embeddings — the in-repo exact twin of the search the serving path delegates to faiss."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "evaltwin_small.npz"))
+    items, users, test_users, k = g["items"], g["users"], g["test_users"], int(g["k"])
+    train = {int(u): g["train_items"][g["train_indptr"][j]:g["train_indptr"][j + 1]]
+             for j, u in enumerate(g["train_users"].tolist())}
+    n_items = items.shape[0]
+    excl = [np.unique(train[int(u)][train[int(u)] < n_items]).astype(np.int64) if int(u) in train
+            else np.empty(0, np.int64) for u in test_users.tolist()]
+    idx = flat_ip.IndexFlatIP(items.shape[1], db_block=500)
+    idx.add(items)
+    D, I = idx.search(users[test_users], k, exclude=excl)
+    assert np.array_equal(I, g["recs"])
+    twin = flat_ip.eval_twin_topk(users[test_users], items, {u: v.tolist() for u, v in train.items()}, test_users.tolist(), k)
+    assert [twin[int(u)] for u in test_users.tolist()] == g["recs"].tolist()
