@@ -225,6 +225,23 @@ int b200rec_sample_negatives(const int64_t* user_of_row, int64_t B, const int64_
                              int64_t n_users, int64_t num_items, int num_negatives, uint64_t seed, uint64_t row_base,
                              int64_t* out_items, int* err_flag, void* stream);
 
+/* ---- on-device ranking metrics (csrc/eval_metrics.cu; replaces the per-user Python of Evaluator.evaluate,
+ * reference src/evaluation/metrics.py:240-319 with helpers :74-231) ----
+ * pred int64 [Q, K] (ld_pred): ranked item ROWS per user as the top-K kernel emits them (-1 = empty slot);
+ * repeat uint8 [Q, K] (nullable): 1 where a position repeats an id seen earlier in its row (set semantics of
+ * recall / precision / hit rate; the fused top-K never repeats); ground truth as a CSR over the Q users (gt_rows
+ * ascending per user) with gt_count (nullable) = |ground truth| when it also holds items outside the catalogue.
+ * inv_log2[i] = 1/log2(i+2) for i < K and idcg[n] = sum_{i<n} inv_log2[i] (n <= max k) come from the host so that the
+ * fp64 results equal the reference's expressions bit for bit.  per_user fp64 [Q, 4*n_k + 2]: for each k
+ * (recall, precision, ndcg, hit), then reciprocal rank and average precision; sums (nullable) fp64 [4*n_k + 2] =
+ * column sums; coverage_bits (nullable, uint32 [ceil(n_items/32)]) / coverage_count: distinct rows recommended in the
+ * first coverage_k positions (metrics.py:279,312-314). */
+int b200rec_eval_metrics(const int64_t* pred, int64_t Q, int K, int64_t ld_pred, const uint8_t* repeat,
+                         int64_t ld_repeat, const int64_t* gt_indptr, const int64_t* gt_rows, const int64_t* gt_count,
+                         const int32_t* k_values_host, int n_k, const double* inv_log2, const double* idcg,
+                         double* per_user, double* sums, uint32_t* coverage_bits, int64_t n_items, int coverage_k,
+                         unsigned long long* coverage_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,9 +51,17 @@ gather_concat_kernel(const float* __restrict__ numerical, int num_cols, int64_t 
   }
 }
 
-__global__ void iota_kernel(int32_t* __restrict__ pos, int64_t n) {
+// pos[i] = i and key[i] = idx[i], with every id outside [0, table_rows) replaced by the padding row: such a sample
+// contributes no gradient (nn.Embedding raises IndexError in the forward — gather_concat_kernel flags it — so the
+// backward must never hand an unchecked row to scatter_rows / sparse_adam, which write table[row]).
+__global__ void keys_iota_kernel(const int64_t* __restrict__ idx, int64_t n, int64_t table_rows, int64_t padding_idx,
+                                 int64_t* __restrict__ key, int32_t* __restrict__ pos) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) pos[i] = (int32_t)i;
+  if (i < n) {
+    const int64_t r = idx[i];
+    key[i] = (r < 0 || (table_rows > 0 && r >= table_rows)) ? padding_idx : r;
+    pos[i] = (int32_t)i;
+  }
 }
 
 // head[i] = 1 when sorted position i starts a new row that is not the padding row
@@ -132,6 +140,7 @@ scatter_rows_kernel(const int64_t* __restrict__ rows, const float* __restrict__ 
 }
 
 struct SparseGradWs {
+  int64_t* key;
   int64_t* sidx;
   int32_t* pos;
   int32_t* spos;
@@ -152,6 +161,7 @@ static void plan_sparse_ws(SparseGradWs& w, int64_t B, void* base) {
   w.cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   size_t off = 0;
+  w.key = reinterpret_cast<int64_t*>(p + off); off += align256(sizeof(int64_t) * B);
   w.sidx = reinterpret_cast<int64_t*>(p + off); off += align256(sizeof(int64_t) * B);
   w.pos = reinterpret_cast<int32_t*>(p + off); off += align256(sizeof(int32_t) * B);
   w.spos = reinterpret_cast<int32_t*>(p + off); off += align256(sizeof(int32_t) * B);
@@ -214,15 +224,17 @@ extern "C" int b200rec_embedding_sparse_grad(const int64_t* idx, int64_t B, cons
   // entries beyond *n_unique_out read as (row 0 = padding, zero gradient): lists can be concatenated and re-coalesced
   B200_CUDA_OK(cudaMemsetAsync(unique_rows, 0, sizeof(int64_t) * B, st));
   B200_CUDA_OK(cudaMemsetAsync(grad_rows, 0, sizeof(float) * B * width, st));
-  iota_kernel<<<nb, 256, 0, st>>>(w.pos, B);
-  B200_LAUNCH_OK("iota_kernel");
+  if (padding_idx < 0 || (table_rows > 0 && padding_idx >= table_rows))
+    return fail("sparse_grad: padding_idx %lld outside the table", (long long)padding_idx);
+  keys_iota_kernel<<<nb, 256, 0, st>>>(idx, B, table_rows, padding_idx, w.key, w.pos);
+  B200_LAUNCH_OK("keys_iota_kernel");
   int end_bit = 64;
   if (table_rows > 0) {
     end_bit = 1;
     while (end_bit < 63 && (1ll << end_bit) < table_rows) ++end_bit;
   }
   size_t tmp = w.cub_bytes;
-  B200_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, idx, w.sidx, w.pos, w.spos, (int)B, 0, end_bit, st));
+  B200_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.key, w.sidx, w.pos, w.spos, (int)B, 0, end_bit, st));
   b200::g_launches.fetch_add(1);
   mark_heads_kernel<<<nb, 256, 0, st>>>(w.sidx, B, padding_idx, w.head);
   B200_LAUNCH_OK("mark_heads_kernel");

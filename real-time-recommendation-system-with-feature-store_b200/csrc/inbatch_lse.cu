@@ -11,6 +11,7 @@
 namespace b200 {
 
 struct LseEpi {
+  static constexpr bool kDbg = false;
   static constexpr int SCRATCH_BYTES = 64;
   struct Args {
     float* part_m;  // [S][max_parts][128*NQ]  running max (log2 domain)

@@ -45,6 +45,22 @@ struct StreamGeom {
   long long Tmain, Tt, We;
 };
 
+// development knobs of the geometry (read from the environment once; b200rec_debug_reload_env re-reads them)
+struct StreamKnobs {
+  int mma_order = 0, sched = -1, ks = 0;
+};
+inline StreamKnobs read_stream_knobs() {
+  StreamKnobs k;
+  if (const char* e = getenv("B200REC_MMA_ORDER")) k.mma_order = atoi(e);
+  if (const char* e = getenv("B200REC_SCHED")) k.sched = atoi(e);
+  if (const char* e = getenv("B200REC_KS")) k.ks = atoi(e);
+  return k;
+}
+inline StreamKnobs& stream_knobs() {
+  static StreamKnobs k = read_stream_knobs();
+  return k;
+}
+
 // development counters of the 2-CTA kernel (one copy per translation unit): [0] MMA warp cycles waiting for a free
 // accumulator, [1] waiting for operands, [2] epilogue-warp cycles waiting for an accumulator, [3] consuming it, [4] tiles
 static __device__ unsigned long long g_stream_stats[8];

@@ -87,7 +87,8 @@ inline bool stream_geom2(StreamGeom& g, long long N, int Q, int KB, int sms, int
   g.KB = KB;
   g.dbg_nofeed = 0;
   g.dbg_stats = 0;
-  g.mma_order = getenv("B200REC_MMA_ORDER") ? atoi(getenv("B200REC_MMA_ORDER")) : 0;
+  const StreamKnobs& skn = stream_knobs();
+  g.mma_order = skn.mma_order;
   g.S = (Q + S2_QUERIES - 1) / S2_QUERIES;
   g.T = (N + S2_ROWS - 1) / S2_ROWS;
   g.total = g.S * g.T;
@@ -99,8 +100,8 @@ inline bool stream_geom2(StreamGeom& g, long long N, int Q, int KB, int sms, int
   // comes from HBM once instead of once per supertile (ncu: 11.3 GB of DRAM reads per launch for a 2.56 GB catalogue
   // with the contiguous split).  The U - R*S leftover units share the last Tt tiles of every supertile so that all
   // units still do W tiles.  Falls back to the contiguous split when there are more supertiles than units.
-  const char* sch = getenv("B200REC_SCHED");
-  const bool aligned = !(sch && atoi(sch) == 0) && g.S <= units && g.T >= 4 * (units / g.S);
+  const int sch = skn.sched;
+  const bool aligned = sch != 0 && g.S <= units && g.T >= 4 * (units / g.S);
   long long used;
   if (aligned) {
     g.R = (int)(units / g.S);
@@ -109,8 +110,8 @@ inline bool stream_geom2(StreamGeom& g, long long N, int Q, int KB, int sms, int
     // merge backlog), so when only a few units are left over they stay idle rather than become stragglers.
     // (~600 us per unit, measured); on long scans the extra 2.7 % of capacity is worth more than that tail (10 M rows:
     // 9.93 ms with the leftover units working vs 10.05 ms idle; 1.25 M rows: 2.49 vs 1.93 ms).
-    const bool long_scan = g.W >= 6000 && !(sch && atoi(sch) == 4);
-    if (extra * 16 <= units && !long_scan && !(sch && atoi(sch) == 3)) extra = 0;
+    const bool long_scan = g.W >= 6000 && sch != 4;
+    if (extra * 16 <= units && !long_scan && sch != 3) extra = 0;
     g.n_main = g.R * g.S;
     g.Tmain = extra == 0 ? g.T : (g.R * g.W < g.T ? g.R * g.W : g.T);
     g.Tt = g.T - g.Tmain;
@@ -131,9 +132,8 @@ inline bool stream_geom2(StreamGeom& g, long long N, int Q, int KB, int sms, int
   }
   const int q_bytes = NQ2 * KB * ST_QTILE_BYTES;
   const int avail = ST_SMEM_LIMIT - 1024 - ST_BAR_BYTES - scratch_bytes - q_bytes;
-  const char* kse = getenv("B200REC_KS");
   g.ks = (KB % 2 == 0) ? 2 : 1;
-  if (kse && atoi(kse) == 1) g.ks = 1;
+  if (skn.ks == 1) g.ks = 1;
   int stages = avail / (S2_STAGE_BYTES * g.ks);
   if (stages > ST_MAX_STAGES) stages = ST_MAX_STAGES;
   g.stages = stages;
@@ -239,7 +239,12 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const bool dbg_st = g.dbg_stats == 1 || g.dbg_stats == 2 + (int)unit;  // development counters: all units or one
+  // development paths (pipeline counters, operand-less MMA issue, alternative MMA orders) exist only in the
+  // instantiations of policies with kDbg = true; release kernels fold all of this to constants
+  constexpr bool kDbg = Epi::kDbg;
+  const bool dbg_st = kDbg && (g.dbg_stats == 1 || g.dbg_stats == 2 + (int)unit);
+  const bool nofeed = kDbg && g.dbg_nofeed != 0;
+  const int mma_order = kDbg ? g.mma_order : 0;
   int s;                       // segment: supertile, first tile, tile count, tile stride, last segment of the unit
   long long t0, ntile, tstep;
   bool last_seg;
@@ -260,7 +265,7 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                               s * S2_QUERIES + qt * 256 + (int)rank * 128);
         }
         __syncwarp();
-        if (!g.dbg_nofeed) {  // development knob off: MMA issue rate without any operand traffic
+        if (!nofeed) {  // development knob off: MMA issue rate without any operand traffic
           for (long long ti = 0, t = t0; ti < ntile; ++ti, t += tstep) {
             for (int step = 0; step < nsteps; ++step, ++it) {
               const int st = it % g.stages;
@@ -298,12 +303,12 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         for (long long ti = 0; ti < ntile; ++ti, ++tc) {
           const uint32_t buf = tc & 1;
           const uint32_t acc_ph = ((tc >> 1) & 1) ^ 1;
-          if (NSUB == 2 && nsteps == 1 && g.mma_order != 1 && g.mma_order != 3) {
+          if (NSUB == 2 && nsteps == 1 && mma_order != 1 && mma_order != 3) {
             // query-tile-major: [wait operands] { wait acc(sub) ; 4*ks MMAs ; commit acc_full(sub) } x 2 ; release stage
             const int st = it % g.stages;
             const uint32_t ph = (it / g.stages) & 1;
             ++it;
-            if (!g.dbg_nofeed) {
+            if (!nofeed) {
               const long long c2 = dbg_st ? clock64() : 0;
               mbar_wait(&full_bar[st], ph);
               if (dbg_st) c_full += clock64() - c2;
@@ -311,7 +316,7 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
             for (int qt = 0; qt < NSUB; ++qt) {
               const long long c0 = dbg_st ? clock64() : 0;
-              if (g.mma_order == 2) {
+              if (mma_order == 2) {
                 if (qt == 0) {
                   mbar_wait(&acc_empty[buf * 2 + 0], acc_ph);
                   mbar_wait(&acc_empty[buf * 2 + 1], acc_ph);
@@ -331,7 +336,7 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     umma_bf16_2sm(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc, (a | k) != 0);
                 }
                 umma_commit_2sm(&acc_full[buf * 2 + qt]);
-                if (qt == NSUB - 1 && !g.dbg_nofeed) umma_commit_2sm(&empty_bar[st]);
+                if (qt == NSUB - 1 && !nofeed) umma_commit_2sm(&empty_bar[st]);
               }
               __syncwarp();
             }
@@ -345,7 +350,7 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
           for (int step = 0; step < nsteps; ++step, ++it) {
             const int st = it % g.stages;
             const uint32_t ph = (it / g.stages) & 1;
-            if (!g.dbg_nofeed) {
+            if (!nofeed) {
               const long long c2 = dbg_st ? clock64() : 0;
               mbar_wait(&full_bar[st], ph);
               tc_fence_after();
@@ -355,7 +360,7 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
               for (int a = 0; a < ks; ++a) {
                 const int kb = step * ks + a;
                 const uint64_t b_desc = desc_base + (ring_lo + ((st * stage_bytes + a * S2_STAGE_BYTES) >> 4));
-                if (g.mma_order == 3) {  // development variant: alternate the query tiles every MMA
+                if (mma_order == 3) {  // development variant: alternate the query tiles every MMA
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
 #pragma unroll
@@ -375,7 +380,7 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     umma_bf16_2sm(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
                 }
               }
-              if (!g.dbg_nofeed) umma_commit_2sm(&empty_bar[st]);
+              if (!nofeed) umma_commit_2sm(&empty_bar[st]);
               if (step == nsteps - 1) {
                 for (int sub = 0; sub < NSUB; ++sub) umma_commit_2sm(&acc_full[buf * 2 + sub]);
               }

@@ -14,6 +14,7 @@
 // later-merged feeder holds a lower row id at the threshold score.  Scores are never written to HBM.
 #include <cfloat>
 #include <cstdlib>
+#include <mutex>
 #include "stream_scores.cuh"
 #include "stream_scores2.cuh"
 #include "../../include/b200rec.h"
@@ -132,21 +133,28 @@ constexpr uint32_t REQ_VALID = 1u << 31, REQ_FINAL = 1u << 30, REQ_BUF = 1u << 2
 constexpr int TOPK_STG = 704;  // keys a helper warp can stage in shared memory (5.5 KB)
 constexpr uint32_t NO_QUERY = 0xFFFFFFFFu;
 
-struct TopkEpi {
+struct TopkArgs {
+  uint64_t* lists;                // [grid][128*NQ][2*cap]   private candidate lists A/B
+  uint64_t* tlists;               // [Q][2*k]                shared running top-k lists T0/T1
+  QMeta* meta;                    // [Q]
+  uint32_t* left;                 // [grid][128*NQ]  leftover (list id << 31 | count) of each CTA's last segment
+  const int64_t* excl_indptr;     // [Q+1] or null
+  const int32_t* excl_rows;       // sorted per query
+  int k;
+  int cap;
+  int flush;  // hand a list to the helper warps once it holds this many candidates (keeps tau fresh)
+  int debug;  // development knob (DBG instantiation only): 1 = reject everything, 2 = count events, 3/5/6/8 = partial pipelines
+  int hsleep; // nanoseconds an idle helper warp sleeps between mailbox polls
+};
+
+// DBG = false is the release instantiation: every development knob, counter and clock stamp below is compiled out
+// (dbgv() folds to 0).  DBG = true is launched only when B200REC_TOPK_DEBUG / B200REC_STREAM_STATS is set (tools/).
+template <bool DBG>
+struct TopkEpiT {
+  static constexpr bool kDbg = DBG;
   static constexpr int SCRATCH_BYTES = 2368 * 4 + 4 * TOPK_STG * 8;
-  struct Args {
-    uint64_t* lists;                // [grid][128*NQ][2*cap]   private candidate lists A/B
-    uint64_t* tlists;               // [Q][2*k]                shared running top-k lists T0/T1
-    QMeta* meta;                    // [Q]
-    uint32_t* left;                 // [grid][128*NQ]  leftover (list id << 31 | count) of each CTA's last segment
-    const int64_t* excl_indptr;     // [Q+1] or null
-    const int32_t* excl_rows;       // sorted per query
-    int k;
-    int cap;
-    int flush;  // hand a list to the helper warps once it holds this many candidates (keeps tau fresh)
-    int debug;  // development knob: 1 = reject everything (MMA + fast-path ceiling), 2 = count events
-    int hsleep; // nanoseconds an idle helper warp sleeps between mailbox polls
-  };
+  using Args = TopkArgs;
+  static __device__ __forceinline__ int dbgv(const Args& ea) { return DBG ? dbgv(ea) : 0; }
   float tau[2];
   int cnt[2];
   uint32_t active[2] = {0u, 0u};  // which of the slot's two lists is being filled (kept across segments)
@@ -178,7 +186,7 @@ struct TopkEpi {
   __device__ __forceinline__ void begin_segment(const Args& ea, const StreamGeom& g, int s, int part,
                                                 const long long (&qrow)[QPT], const int (&qslot)[QPT], int lane,
                                                 uint32_t* scratch) {
-    if (ea.debug == 2 && blockIdx.x == 144 && threadIdx.x == 128 && dbg_seg < 60) {
+    if (dbgv(ea) == 2 && blockIdx.x == 144 && threadIdx.x == 128 && dbg_seg < 60) {
       unsigned long long ns;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
       g_cta_end[256 + 2 * dbg_seg] = ns;
@@ -186,7 +194,7 @@ struct TopkEpi {
 #pragma unroll
     for (int a = 0; a < QPT; ++a) {
       const long long q = qrow[a];
-      const bool valid = (q >= 0) && ea.debug != 1 && ea.debug != 3 && ea.debug != 5;
+      const bool valid = (q >= 0) && dbgv(ea) != 1 && dbgv(ea) != 3 && dbgv(ea) != 5;
       qid[a] = valid ? (uint32_t)q : NO_QUERY;
       tau[a] = valid ? __ldcg(&ea.meta[q].tau) : INFINITY;
       cnt[a] = 0;
@@ -214,11 +222,11 @@ struct TopkEpi {
       if ((uint32_t)(pub >> 32) == qid[a] && qid[a] != NO_QUERY) tau[a] = fmaxf(tau[a], __uint_as_float((uint32_t)pub));
       const bool must = cnt[a] + BN > ea.cap;   // the list could overflow during the next tile
       volatile uint32_t* reqp = scratch + 1536 + qslot[a];
-      if (ea.debug == 6) {  // development knob: candidates are found and appended but never merged
+      if (dbgv(ea) == 6) {  // development knob: candidates are found and appended but never merged
         if (must || cnt[a] >= ea.flush) cnt[a] = 0;
       } else if (must || (cnt[a] >= ea.flush && *reqp == 0u)) {
         volatile uint32_t* req = reqp;
-        if (ea.debug == 2) {
+        if (dbgv(ea) == 2) {
           const long long t0 = clock64();
           wait_idle(req);
           atomicAdd(&g_topk_stats[2], (unsigned long long)(clock64() - t0));
@@ -242,7 +250,7 @@ struct TopkEpi {
     if (ex_n[a] == 0 || !row_excluded(ex_lo[a], ex_n[a], row)) {
       __stcg(buf[a] + (active[a] ? ea.cap : 0) + cnt[a], make_key(x, row));
       ++cnt[a];
-      if (ea.debug == 2) ++n_app;
+      if (dbgv(ea) == 2) ++n_app;
     }
   }
 
@@ -256,14 +264,14 @@ struct TopkEpi {
   __device__ __forceinline__ void tile(const Args& ea, const StreamGeom& g, int a, uint32_t taddr,
                                        unsigned long long row0_ll) {
     const uint32_t row0 = (uint32_t)row0_ll;
-    if (ea.debug == 3) return;  // development knob: MMA + TMA pipeline only (TMEM never read)
+    if (dbgv(ea) == 3) return;  // development knob: MMA + TMA pipeline only (TMEM never read)
 #pragma unroll 1
     for (int c = 0; c < BN; c += 64) {
       uint32_t v0[32], v1[32];
       tmem_ld_32x32(taddr + c, v0);
       tmem_ld_32x32(taddr + c + 32, v1);
       tmem_ld_wait();
-      if (ea.debug == 5) {  // development knob: TMEM read cost only
+      if (dbgv(ea) == 5) {  // development knob: TMEM read cost only
         asm volatile("" ::"r"(v0[0]), "r"(v1[31]));
         continue;
       }
@@ -274,12 +282,12 @@ struct TopkEpi {
       const float m64 = fmax3(fmax3(gm[0], gm[1], gm[2]), fmax3(gm[3], gm[4], gm[5]), fmaxf(gm[6], gm[7]));
       if (!__any_sync(FULL_MASK, m64 >= tau[a])) continue;
       long long sp0 = 0;
-      if (ea.debug == 2) sp0 = clock64();
+      if (dbgv(ea) == 2) sp0 = clock64();
       uint32_t gbits = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) gbits |= (gm[j] >= tau[a]) ? (1u << j) : 0u;
       uint32_t pending = __reduce_or_sync(FULL_MASK, gbits);
-      if (ea.debug == 2) {
+      if (dbgv(ea) == 2) {
         const long long t1 = clock64();
         sp_a += t1 - sp0;
       }
@@ -291,10 +299,10 @@ struct TopkEpi {
         pending &= pending - 1;
         uint32_t w[8];
         long long t2 = 0;
-        if (ea.debug == 2) t2 = clock64();
+        if (dbgv(ea) == 2) t2 = clock64();
         tmem_ld_32x8(taddr + c + 8 * j, w);
         tmem_ld_wait();
-        if (ea.debug == 2) {
+        if (dbgv(ea) == 2) {
           asm volatile("" ::"r"(w[0]), "r"(w[7]) : "memory");
           const long long t3 = clock64();
           sp_b += t3 - t2;
@@ -302,12 +310,12 @@ struct TopkEpi {
         }
         const uint32_t rb = base + 8u * (uint32_t)j;
         test_group(ea, g, a, w, rb, edge);
-        if (ea.debug == 2) {
+        if (dbgv(ea) == 2) {
           ++sp_grp;
           sp_c += clock64() - t2;
         }
       }
-      if (ea.debug == 2) {
+      if (dbgv(ea) == 2) {
         sp_cyc += clock64() - sp0;
         ++sp_ent;
       }
@@ -362,7 +370,7 @@ struct TopkEpi {
   template <int SLOTS, int QPT>
   __device__ __forceinline__ void end_segment(const Args& ea, const StreamGeom& g, int s, int part,
                                               const int (&qslot)[QPT], int lane, uint32_t* scratch, bool last) {
-    if (ea.debug == 2 && blockIdx.x == 144 && threadIdx.x == 128 && dbg_seg < 60) {
+    if (dbgv(ea) == 2 && blockIdx.x == 144 && threadIdx.x == 128 && dbg_seg < 60) {
       unsigned long long ns;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
       g_cta_end[256 + 2 * dbg_seg + 1] = ns;
@@ -373,7 +381,7 @@ struct TopkEpi {
       ++dbg_seg;
     }
     if (last) {
-      if (ea.debug == 2) {
+      if (dbgv(ea) == 2) {
         const int apps = __reduce_add_sync(FULL_MASK, n_app);
         if (lane == 0 && (blockIdx.x == 144 || blockIdx.x == 145 || blockIdx.x == 0)) {
           const int w = (blockIdx.x == 0 ? 16 : (blockIdx.x - 144) * 8) + (threadIdx.x >> 5) - 4;
@@ -523,7 +531,7 @@ struct TopkEpi {
     uint64_t* stage = reinterpret_cast<uint64_t*>(scratch + 2368) + hw * TOPK_STG;
     const int k = ea.k;
     // SM cycles and wall nanoseconds of this launch as seen by CTA 0 (=> the SM clock the kernel really ran at)
-    const bool stamp = hw == 0 && lane == 0;
+    const bool stamp = DBG && hw == 0 && lane == 0;
     long long c_begin = 0;
     unsigned long long ns_begin = 0;
     if (stamp) {
@@ -548,7 +556,7 @@ struct TopkEpi {
         uint32_t todo = __ballot_sync(FULL_MASK, (r & REQ_VALID) != 0u);
         while (todo) {
           any = true;
-          const long long hb0 = clock64();
+          const long long hb0 = DBG ? clock64() : 0;
           const int owner = __ffs(todo) - 1;
           todo &= todo - 1;
           const uint32_t ro = __shfl_sync(FULL_MASK, r, owner);
@@ -565,7 +573,7 @@ struct TopkEpi {
           if (lane == 0) got = (atomicCAS(&m->lock, 0u, 1u) == 0u) ? 1u : 0u;
           got = __shfl_sync(FULL_MASK, got, 0);
           if (!got) {  // another CTA is merging into this query's T: retry on the next poll
-            if (ea.debug == 2 && lane == 0) atomicAdd(&g_topk_stats[4], 1ull);
+            if (dbgv(ea) == 2 && lane == 0) atomicAdd(&g_topk_stats[4], 1ull);
             continue;
           }
           __threadfence();
@@ -582,7 +590,7 @@ struct TopkEpi {
           } else {
             const int total = tc + n;
             float newtau;
-            if (total <= 256 && ea.debug != 8) {
+            if (total <= 256 && dbgv(ea) != 8) {
               newtau = merge_select_regs(tcur, tc, src, n, k, tnext, lane);
             } else if (total <= TOPK_STG) {
               for (int i = lane; i < total; i += 32) stage[i] = (i < tc) ? __ldcg(tcur + i) : __ldcg(src + (i - tc));
@@ -605,7 +613,7 @@ struct TopkEpi {
             reqs[slot] = 0u;
           }
           __syncwarp();
-          if (ea.debug == 2 && lane == 0) atomicAdd(&g_topk_stats[3], (unsigned long long)(clock64() - hb0));
+          if (dbgv(ea) == 2 && lane == 0) atomicAdd(&g_topk_stats[3], (unsigned long long)(clock64() - hb0));
         }
       }
       if (!any) {
@@ -624,6 +632,9 @@ struct TopkEpi {
   }
 };
 
+using TopkEpi = TopkEpiT<false>;
+using TopkEpiDbg = TopkEpiT<true>;
+
 // ---------------------------------------------------------------------------------------------------------------
 // Sampling pass policy: the same streaming kernel over a strided sample of the catalogue (m = N/32 rows), fast path
 // only — each epilogue thread writes the MAXIMUM score of every group of `gw` sampled rows for its query.  Group
@@ -632,6 +643,7 @@ struct TopkEpi {
 // selection at all.  It removes the cold-start phase in which almost every score is a candidate.
 // ---------------------------------------------------------------------------------------------------------------
 struct SampleMaxEpi {
+  static constexpr bool kDbg = false;
   static constexpr int SCRATCH_BYTES = 64;
   struct Args {
     float* out;     // [Q][ngroups]
@@ -1064,13 +1076,67 @@ struct TopkPlan {
   size_t total() const { return lists_bytes + tlists_bytes + meta_bytes + left_bytes + sample_bytes; }
 };
 
-static int cap_for(int k, int bn) {
-  const char* e = getenv("B200REC_TOPK_CAPMULT");
-  const int mult = e ? atoi(e) : 2;
-  return ((mult * k + bn + 31) / 32) * 32;
+// Development knobs come from the environment ONCE (first call) — not ~10 getenv() per search; tools that change them
+// inside one process call b200rec_debug_reload_env().
+struct TopkKnobs {
+  int capmult = 2, v2 = -1, force_nq = 0, nosample = 0, sample_frac = 0, flush = -1, debug = 0, hsleep = 400,
+      stream_stats = 0, stats_unit = -1;
+};
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+static TopkKnobs read_knobs() {
+  TopkKnobs k;
+  k.capmult = env_int("B200REC_TOPK_CAPMULT", 2);
+  k.v2 = env_int("B200REC_TOPK_V2", -1);
+  k.force_nq = env_int("B200REC_TOPK_NQ", 0);
+  k.nosample = env_int("B200REC_TOPK_NOSAMPLE", 0);
+  k.sample_frac = env_int("B200REC_TOPK_SAMPLE_FRAC", 0);
+  k.flush = env_int("B200REC_TOPK_FLUSH", -1);
+  k.debug = env_int("B200REC_TOPK_DEBUG", 0);
+  k.hsleep = env_int("B200REC_TOPK_HSLEEP", 400);
+  k.stream_stats = getenv("B200REC_STREAM_STATS") != nullptr ? 1 : 0;
+  k.stats_unit = env_int("B200REC_STATS_UNIT", -1);
+  return k;
+}
+static TopkKnobs& knobs() {
+  static TopkKnobs k = read_knobs();
+  return k;
 }
 
-static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k, int shards = 1) {
+static int cap_for(int k, int bn) { return ((knobs().capmult * k + bn + 31) / 32) * 32; }
+
+// Encoded tensor maps are pure functions of (base, rows, ld, pitch, box): the catalogue's and — with a caching
+// allocator behind the caller — the query operand's recur call after call, so a search re-encodes nothing.
+struct TmapKey {
+  const void* base;
+  uint64_t rows, cols, ld;
+  uint32_t box;
+  bool operator==(const TmapKey& o) const { return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box == o.box; }
+};
+static std::mutex g_cache_mu;
+static int cached_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box) {
+  constexpr int SLOTS = 32;
+  static TmapKey keys[SLOTS];
+  static CUtensorMap maps[SLOTS];
+  static int used = 0, next = 0;
+  const TmapKey key{base, rows, cols, ld, box};
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  for (int i = 0; i < used; ++i)
+    if (keys[i] == key) {
+      *out = maps[i];
+      return 0;
+    }
+  if (make_tmap_bf16_2d(out, base, rows, cols, ld, box)) return 1;
+  const int slot = used < SLOTS ? used++ : (next = (next + 1) % SLOTS);
+  keys[slot] = key;
+  maps[slot] = *out;
+  return 0;
+}
+
+static int plan_topk_uncached(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k, int shards) {
+  const TopkKnobs& kn = knobs();
   if (N <= 0 || Q <= 0) return fail("topk: empty catalogue or query set");
   if (N >= (1ll << 32) - 1) return fail("topk: a shard holds at most 2^32-2 rows");
   if (Q > INT32_MAX / 2) return fail("topk: too many queries");
@@ -1081,9 +1147,8 @@ static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k, int s
   const int q128 = (int)((Q + 127) / 128);
   bool ok = false;
   p.v2 = 0;
-  const char* v2e = getenv("B200REC_TOPK_V2");
-  const bool want_v2 = v2e ? atoi(v2e) != 0 : true;
-  const int v2shape = v2e ? atoi(v2e) : (q128 >= 3 ? 2 : 1);
+  const bool want_v2 = kn.v2 != 0;
+  const int v2shape = kn.v2 >= 0 ? kn.v2 : (q128 >= 3 ? 2 : 1);
   if (want_v2 && q128 >= 2 && (sms % 2) == 0) {
     // (the final kernel tabulates every unit's last supertile in FIN_MAX_SRC shared-memory slots)
     if (v2shape == 2 && stream_geom2<2>(p.g, N, (int)Q, KB, sms, TopkEpi::SCRATCH_BYTES) && p.g.max_parts + 1 <= FIN_MAX_SRC &&
@@ -1094,8 +1159,7 @@ static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k, int s
       p.v2 = 1, p.nq = 2, p.bn = 128, ok = true;
     }
   }
-  const char* force = getenv("B200REC_TOPK_NQ");
-  const int fnq = force ? atoi(force) : 0;
+  const int fnq = kn.force_nq;
   if (ok) {
   } else if (fnq == 2 && stream_geom<2, 128>(p.g, N, (int)Q, KB, sms, TopkEpi::SCRATCH_BYTES)) {
     p.nq = 2, p.bn = 128, ok = true;
@@ -1119,17 +1183,15 @@ static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k, int s
   p.sample_m = p.sample_stride = 0;
   p.sample_bytes = 0;
   p.sample_gw = 32;
-  const char* ns = getenv("B200REC_TOPK_NOSAMPLE");
-  const char* sf = getenv("B200REC_TOPK_SAMPLE_FRAC");
   // `shards` row shards pool their samples (b200rec_topk_sample): the density is chosen for the pooled catalogue
   const int64_t n_pool = N * (shards > 1 ? shards : 1);
   int64_t frac = n_pool >= (4ll << 20) ? 32 : (n_pool >= (256ll << 10) ? 16 : 8);
   // A shard cannot see the other shards' running thresholds, so its own threshold only climbs to the LOCAL k-th score:
   // a tighter pooled start pays for a denser sample (8 x 1.25 M rows: 1/16 -> 1.58 ms per batch, 1/32 -> 1.69, 1/8 -> 1.64)
   if (shards > 1 && frac > 8) frac /= 2;
-  if (sf && atoi(sf) > 0) frac = atoi(sf);
+  if (kn.sample_frac > 0) frac = kn.sample_frac;
   int64_t m = (N / frac) / 256 * 256;
-  if (!(ns && atoi(ns)) && m >= 2048) {
+  if (!kn.nosample && m >= 2048) {
     int gw = 32;
     while (gw < 128 && gw < p.bn && m / gw > 8192) gw *= 2;
     if (m / gw >= 2 * (int64_t)k) {
@@ -1149,7 +1211,35 @@ static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k, int s
   return 0;
 }
 
-template <int NQ, int BN, int V2>
+// plans are pure functions of (N, ld, Q, k, shards) and the knobs: computed once per shape
+struct PlanKey {
+  int64_t N, ld, Q;
+  int k, shards;
+  bool operator==(const PlanKey& o) const { return N == o.N && ld == o.ld && Q == o.Q && k == o.k && shards == o.shards; }
+};
+static PlanKey g_plan_keys[64];
+static TopkPlan g_plans[64];
+static int g_plan_used = 0, g_plan_next = 0;
+
+static int plan_topk(TopkPlan& p, int64_t N, int64_t ld, int64_t Q, int k, int shards = 1) {
+  const PlanKey key{N, ld, Q, k, shards};
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    for (int i = 0; i < g_plan_used; ++i)
+      if (g_plan_keys[i] == key) {
+        p = g_plans[i];
+        return 0;
+      }
+  }
+  if (plan_topk_uncached(p, N, ld, Q, k, shards)) return 1;   // argument errors are not cached
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  const int slot = g_plan_used < 64 ? g_plan_used++ : (g_plan_next = (g_plan_next + 1) % 64);
+  g_plan_keys[slot] = key;
+  g_plans[slot] = p;
+  return 0;
+}
+
+template <int NQ, int BN, int V2, bool DBG>
 static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int64_t ld, const void* queries, int64_t Q,
                        int k, int64_t row_offset, const int64_t* excl_indptr, const int32_t* excl_rows,
                        float* out_scores, int64_t* out_ids, void* workspace, cudaStream_t st,
@@ -1162,11 +1252,13 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
     fan.s[0] = sample_vals_out != nullptr ? sample_vals_out : out_scores;
     fan.i[0] = out_ids;
   }
+  using Epi = TopkEpiT<DBG>;
+  const TopkKnobs& kn = knobs();
   CUtensorMap tq, tx;
-  if (make_tmap_bf16_2d(&tq, queries, (uint64_t)Q, (uint64_t)ld, (uint64_t)ld, 128)) return 1;
+  if (cached_tmap(&tq, queries, (uint64_t)Q, (uint64_t)ld, (uint64_t)ld, 128)) return 1;
   constexpr int XBOX = V2 == 1 ? 128 : (V2 == 2 ? 64 : BN);  // rows per TMA box (a CTA of a pair loads its half)
-  if (make_tmap_bf16_2d(&tx, catalogue, (uint64_t)N, (uint64_t)ld, (uint64_t)ld, XBOX)) return 1;
-  TopkEpi::Args ea;
+  if (cached_tmap(&tx, catalogue, (uint64_t)N, (uint64_t)ld, (uint64_t)ld, XBOX)) return 1;
+  TopkArgs ea;
   ea.lists = reinterpret_cast<uint64_t*>(workspace);
   ea.tlists = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(workspace) + p.lists_bytes);
   ea.meta = reinterpret_cast<QMeta*>(reinterpret_cast<uint8_t*>(workspace) + p.lists_bytes + p.tlists_bytes);
@@ -1178,12 +1270,12 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
   ea.cap = p.cap;
   // hand a list over every ~k/4 candidates: each merge selects over k + list keys, so the threshold scales with k
   // (k = 1000: 7.6 ms per 1024-query batch at 32, 5.3 ms at 256)
-  ea.flush = getenv("B200REC_TOPK_FLUSH") ? atoi(getenv("B200REC_TOPK_FLUSH")) : (k / 4 > 32 ? (k / 4) / 32 * 32 : 32);
-  ea.debug = getenv("B200REC_TOPK_DEBUG") ? atoi(getenv("B200REC_TOPK_DEBUG")) : 0;
-  ea.hsleep = getenv("B200REC_TOPK_HSLEEP") ? atoi(getenv("B200REC_TOPK_HSLEEP")) : 400;
-  void (*kern)(const CUtensorMap, const CUtensorMap, const StreamGeom, const TopkEpi::Args);
-  if constexpr (V2 != 0) kern = stream_scores2_kernel<(V2 == 2 ? 2 : 1), TopkEpi>;
-  else kern = stream_scores_kernel<NQ, BN, TopkEpi>;
+  ea.flush = kn.flush >= 0 ? kn.flush : (k / 4 > 32 ? (k / 4) / 32 * 32 : 32);
+  ea.debug = kn.debug;
+  ea.hsleep = kn.hsleep;
+  void (*kern)(const CUtensorMap, const CUtensorMap, const StreamGeom, const TopkArgs);
+  if constexpr (V2 != 0) kern = stream_scores2_kernel<(V2 == 2 ? 2 : 1), Epi>;
+  else kern = stream_scores_kernel<NQ, BN, Epi>;
   static int smem_set = 0;
   if (smem_set < p.g.smem_bytes) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_LIMIT));
@@ -1195,7 +1287,7 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
   } else if (p.sample_m > 0 && excl_indptr == nullptr) {
     float* S = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + p.lists_bytes + p.tlists_bytes + p.meta_bytes + p.left_bytes);
     CUtensorMap ts;  // row i of this map is catalogue row i * stride
-    if (make_tmap_bf16_2d(&ts, catalogue, (uint64_t)p.sample_m, (uint64_t)ld, (uint64_t)(ld * p.sample_stride), XBOX)) return 1;
+    if (cached_tmap(&ts, catalogue, (uint64_t)p.sample_m, (uint64_t)ld, (uint64_t)(ld * p.sample_stride), XBOX)) return 1;
     SampleMaxEpi::Args sa;
     sa.out = S;
     sa.ngroups = (int)(p.sample_m / p.sample_gw);
@@ -1235,8 +1327,8 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
   }
   StreamGeom gl = p.g;
   gl.dbg_nofeed = (ea.debug == 4) ? 1 : 0;
-  gl.dbg_stats = (ea.debug == 2 || getenv("B200REC_STREAM_STATS") != nullptr) ? 1 : 0;
-  if (getenv("B200REC_STATS_UNIT")) gl.dbg_stats = 2 + atoi(getenv("B200REC_STATS_UNIT"));
+  gl.dbg_stats = (ea.debug == 2 || kn.stream_stats) ? 1 : 0;
+  if (kn.stats_unit >= 0) gl.dbg_stats = 2 + kn.stats_unit;
   if (ea.debug == 4) ea.debug = 3;
   kern<<<gl.grid, ST_THREADS, gl.smem_bytes, st>>>(tq, tx, gl, ea);
   B200_LAUNCH_OK("stream_scores_kernel<topk>");
@@ -1251,6 +1343,15 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
 }
 
 }  // namespace b200
+
+extern "C" int b200rec_debug_reload_env(void) {
+  using namespace b200;
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  knobs() = read_knobs();
+  stream_knobs() = read_stream_knobs();
+  g_plan_used = g_plan_next = 0;
+  return 0;
+}
 
 extern "C" int b200rec_debug_topk_stats(unsigned long long* out8_host, int reset) {
   using namespace b200;
@@ -1318,11 +1419,18 @@ static int topk_dispatch(const void* catalogue, int64_t N, int64_t ld, const voi
   if (sample_vals_out != nullptr && p.sample_m == 0) return fail("topk_sample: catalogue too small for a sampling pass");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define B200_TOPK_ARGS p, catalogue, N, ld, queries, Q, k, row_offset, exclude_indptr, exclude_rows, out_scores, out_ids, workspace, st, tau_init, sample_vals_out, fan
-  if (p.v2 == 2) return launch_topk<2, 128, 2>(B200_TOPK_ARGS);
-  if (p.v2 == 1) return launch_topk<2, 128, 1>(B200_TOPK_ARGS);
-  if (p.nq == 2) return launch_topk<2, 128, 0>(B200_TOPK_ARGS);
-  if (p.bn == 256) return launch_topk<1, 256, 0>(B200_TOPK_ARGS);
-  return launch_topk<1, 64, 0>(B200_TOPK_ARGS);
+  if (knobs().debug != 0 || knobs().stream_stats || knobs().stats_unit >= 0) {  // development instantiation
+    if (p.v2 == 2) return launch_topk<2, 128, 2, true>(B200_TOPK_ARGS);
+    if (p.v2 == 1) return launch_topk<2, 128, 1, true>(B200_TOPK_ARGS);
+    if (p.nq == 2) return launch_topk<2, 128, 0, true>(B200_TOPK_ARGS);
+    if (p.bn == 256) return launch_topk<1, 256, 0, true>(B200_TOPK_ARGS);
+    return launch_topk<1, 64, 0, true>(B200_TOPK_ARGS);
+  }
+  if (p.v2 == 2) return launch_topk<2, 128, 2, false>(B200_TOPK_ARGS);
+  if (p.v2 == 1) return launch_topk<2, 128, 1, false>(B200_TOPK_ARGS);
+  if (p.nq == 2) return launch_topk<2, 128, 0, false>(B200_TOPK_ARGS);
+  if (p.bn == 256) return launch_topk<1, 256, 0, false>(B200_TOPK_ARGS);
+  return launch_topk<1, 64, 0, false>(B200_TOPK_ARGS);
 #undef B200_TOPK_ARGS
 }
 

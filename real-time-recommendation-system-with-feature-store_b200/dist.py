@@ -75,7 +75,8 @@ class ShardedFlatIndex:
         self._sample_takes_width = (local_sample is not None
                                     and len(inspect.signature(local_sample).parameters) >= 4)
         self.packed_exchange = False   # set by from_device_index: needs a local_search that writes into `out`
-        self.peer_index = None         # set by from_device_index(peer_exchange=True): fan-out stores over NVLink
+        self.peer_index = None         # set by from_device_index: the local FlatIPDeviceIndex
+        self.use_peer_exchange = False # from_device_index(peer_exchange=True): fan-out stores over NVLink
         self._ids_cache = {}
 
     @classmethod
@@ -95,7 +96,8 @@ class ShardedFlatIndex:
 
         obj = cls(local, merge, group, sample)
         obj.packed_exchange = True
-        obj.peer_index = index if peer_exchange else None
+        obj.peer_index = index
+        obj.use_peer_exchange = bool(peer_exchange)
         return obj
 
     def _peer(self, q: int, k: int, world: int, device):
@@ -168,7 +170,7 @@ class ShardedFlatIndex:
         world, _ = _world()
         if world == 1:
             return self.local_search(queries, k)
-        if self.peer_index is not None:
+        if self.peer_index is not None and self.use_peer_exchange:
             px = self._peer(int(queries.shape[0]), k, world, queries.device)
             if px is not None:
                 return self._search_peer(px, queries, k, world)
@@ -196,6 +198,45 @@ class ShardedFlatIndex:
         dist.all_gather_into_tensor(gs, s.contiguous(), group=self.group)
         dist.all_gather_into_tensor(gi, i.contiguous(), group=self.group)
         return self.merge(gs.view(world, q, -1), gi.view(world, q, -1), k)
+
+
+    # ------------------------------------------------------------------ host-facing calls (faiss array contract)
+    def _host_pipe(self, k: int, normalize: bool, share: bool):
+        from .retrieval import HostPipeline
+        world, rank = _world()
+        key = ("pipe", k, normalize, share)
+        if key not in self._ids_cache:
+            rows = None
+            if share and world > 1:     # every replica returns the answers of ITS contiguous share of the query batch
+                rows = _ShareSlice(world, rank)
+            self._ids_cache[key] = HostPipeline(self.peer_index, k, normalize, lambda q_op, kk: self.search(q_op, kk), rows)
+        return self._ids_cache[key]
+
+    def search_stream(self, batches, k: int, normalize: bool = False, share_results: bool = False):
+        """`FlatIPDeviceIndex.search_stream` over the row-sharded catalogue: every replica passes the same HOST query
+        batches (numpy) and gets faiss-shaped (D, I) numpy pairs with GLOBAL row ids.  share_results=True copies back
+        only this replica's contiguous share of the queries (rows shard_bounds(nq, world, rank)), which is what a
+        replicated serving tier needs; False returns the full result on every replica."""
+        if self.peer_index is None:
+            raise RuntimeError("search_stream needs a ShardedFlatIndex built by from_device_index")
+        pipe = self._host_pipe(k, normalize, share_results)
+        return self.peer_index.search_stream(batches, k, normalize, device_search=pipe)
+
+    def search_numpy(self, q, k: int, normalize: bool = False, share_results: bool = False):
+        """One blocking faiss-shaped call: numpy queries in, (D, I) numpy out."""
+        for out in self.search_stream([q], k, normalize, share_results):
+            return out
+
+
+class _ShareSlice:
+    """slice-like: rows [lo, hi) of an nq-row batch owned by `rank` (HostPipeline calls .indices(nq))."""
+
+    def __init__(self, world: int, rank: int):
+        self.world, self.rank = world, rank
+
+    def indices(self, nq: int):
+        lo, hi = shard_bounds(nq, self.world, self.rank)
+        return lo, hi, 1
 
 
 class _AllGatherRows(torch.autograd.Function):
@@ -258,16 +299,15 @@ class DataParallel:
         dist.all_gather_into_tensor(av, vals.contiguous(), group=self.group)
         return ar, av
 
+    def gather_counts(self, n: int):
+        """[n of every replica] (host ints; one small collective, used outside the hot step)."""
+        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+        t = torch.zeros((self.world,), dtype=torch.int64, device=dev)
+        t[self.rank] = int(n)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return [int(x) for x in t.tolist()]
+
     def global_loss(self, local_share: torch.Tensor) -> torch.Tensor:
         out = local_share.detach().clone()
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
         return out
-
-
-def allreduce_mean_(flat: torch.Tensor, group=None) -> None:
-    """Data-parallel gradient exchange: one all-reduce over the flat fp32 gradient buffer, then divide by the world."""
-    world, _ = _world()
-    if world == 1:
-        return
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    flat.div_(world)

@@ -171,8 +171,9 @@ import ctypes as _C  # noqa: E402
 
 
 def gather_concat(numerical: Optional[torch.Tensor], tables, indices, widths, col_offsets, out_cols: int,
-                  batch: int, device) -> torch.Tensor:
-    """Fused multi-field gather writing the MLP input [B, out_cols] (numerical block first)."""
+                  batch: int, device, err: torch.Tensor) -> torch.Tensor:
+    """Fused multi-field gather writing the MLP input [B, out_cols] (numerical block first).  `err` (int32[1]) is set to
+    field + 1 when an id lies outside its table (ops.check_index_errors raises IndexError from it)."""
     F = len(tables)
     out = torch.empty((batch, out_cols), dtype=torch.float32, device=device)
     num_cols = 0 if numerical is None else numerical.shape[1]
@@ -182,11 +183,10 @@ def gather_concat(numerical: Optional[torch.Tensor], tables, indices, widths, co
     wd = (_C.c_int32 * max(F, 1))(*widths)
     tld = (_C.c_int32 * max(F, 1))(*[t.stride(0) for t in tables])
     co = (_C.c_int32 * max(F, 1))(*col_offsets)
-    err = torch.zeros((1,), dtype=torch.int32, device=device)
     N.check(N.lib().b200rec_gather_concat(N.ptr(numerical), num_cols, numerical.stride(0) if numerical is not None else 0,
                                           tp, ip, rows, wd, tld, co, F, batch, N.ptr(out), out.stride(0), N.ptr(err),
                                           N.stream()), "gather_concat")
-    return out, err
+    return out
 
 
 def embedding_sparse_grad(idx: torch.Tensor, dY: torch.Tensor, width: int, table_rows: int, padding_idx: int = 0):

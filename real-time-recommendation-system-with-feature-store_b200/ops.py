@@ -28,6 +28,34 @@ def require_cuda(*tensors) -> None:
                                "move the model and its inputs to a B200 device")
 
 
+# ---------------------------------------------------------------------------------------------- index-range errors
+# nn.Embedding raises IndexError for an id outside [0, cardinality]; a kernel cannot raise, so every gather ORs into one
+# device flag per GPU (field number + 1 of the offending table) and the host reads it at a point where it synchronises
+# anyway: TwoTowerTrainer checks it once per epoch, `check_index_errors()` on demand, B200REC_SYNC_CHECKS=1 after every
+# gather (debugging).  Offending samples read row 0 in the forward and contribute NO gradient (csrc/embedding.cu).
+_ERR_FLAGS = {}
+
+
+def _err_flag(device: torch.device) -> torch.Tensor:
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    t = _ERR_FLAGS.get(key)
+    if t is None:
+        t = _ERR_FLAGS[key] = torch.zeros((1,), dtype=torch.int32, device=device)
+    return t
+
+
+def check_index_errors(device=None) -> None:
+    """Raise IndexError (as nn.Embedding does) if any embedding gather since the last check saw an out-of-range id."""
+    for key, t in list(_ERR_FLAGS.items()):
+        if device is not None and torch.device(device).index not in (None, key[1]):
+            continue
+        v = int(t.item())
+        if v:
+            t.zero_()
+            raise IndexError(f"index out of range in self (embedding field #{v - 1} of a b200rec gather received an id "
+                             "outside [0, num_embeddings))")
+
+
 def _bwd_terms(terms: int) -> int:
     """Split-bf16 terms of the GRADIENT GEMMs (dgrad, wgrad, the two in-batch gradient products) when the forward runs
     fp32-grade (6 terms).  3 terms ([h l h] x [h h l]: products accurate to ~2^-17, fp32 accumulation) halve their
@@ -162,12 +190,19 @@ class GatherConcatFn(Function):
             offs.append(c)
             c += w
         idx64 = [i.to(torch.int64).contiguous() for i in indices]
-        out, err = K.gather_concat(numerical if numerical.shape[1] > 0 else None, tables, idx64, widths, offs, c, B,
-                                   numerical.device)
+        for f, i in enumerate(idx64):
+            require_cuda(i)
+            if i.numel() != B:
+                raise RuntimeError(f"categorical field #{f}: expected {B} ids (one per row of the numerical block), "
+                                   f"got {i.numel()}")
+        err = _err_flag(numerical.device)
+        out = K.gather_concat(numerical if numerical.shape[1] > 0 else None, tables, idx64, widths, offs, c, B,
+                              numerical.device, err)
+        if os.environ.get("B200REC_SYNC_CHECKS") == "1":
+            check_index_errors(numerical.device)
         ctx.save_for_backward(*idx64)
         ctx.tables = tables
         ctx.meta = (numerical.shape[1], widths, offs)
-        ctx.err = err
         return out
 
     @staticmethod
@@ -192,6 +227,9 @@ class GatherConcatFn(Function):
                 # rows in place instead of materialising a dense [rows, e] tensor for autograd to add (for the 1 M-row
                 # table of config 2 that was a 256 MB fill + a 770 MB read-modify-write per step)
                 K.scatter_rows(rows, vals, n, table.grad, accumulate=True)
+                touch = getattr(table, "_b200_touch", None)   # FlatAdam: this table received a gradient this step
+                if touch is not None:
+                    touch[0]._mark(touch[1])
                 grads.append(None)
             else:
                 dense = torch.zeros_like(table)
@@ -233,6 +271,8 @@ class ExplicitCEFn(Function):
         require_cuda(u, p, n)
         u, p, n = _c32(u), _c32(p), _c32(n)
         B = u.shape[0]
+        if n.shape[0] % B != 0:   # the reference's neg.view(B, R, -1) raises for this shape (two_tower.py:428)
+            raise RuntimeError(f"shape '[{B}, -1, {n.shape[1]}]' is invalid for input of size {n.numel()}")
         R = n.shape[0] // B
         row_loss, *_ = K.explicit_ce(u, p, n, R, inv_t, user_bias, item_bias)
         acc = torch.zeros((1,), dtype=torch.float32, device=u.device)

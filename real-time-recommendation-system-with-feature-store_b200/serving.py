@@ -62,7 +62,7 @@ class RetrievalBatcher:
             return
         if self._pending:  # more than one batch was waiting: keep draining
             self._timer = asyncio.get_running_loop().call_soon(self._flush)
-        t0 = time.time()
+        t0 = time.perf_counter()
         try:
             feats = self._stack([b[0] for b in batch])
             dev = next(self.model.parameters()).device
@@ -72,9 +72,11 @@ class RetrievalBatcher:
                 emb = self.model.get_user_embeddings(feats)                 # ONE tower forward for the whole batch
             k_max = max(b[1] for b in batch)
             ids, scores = self.engine.index.search(emb, k=k_max)           # ONE exact top-k search for the whole batch
-            latency_ms = (time.time() - t0) * 1e3
-            self.engine.total_queries += len(batch)
-            self.engine.total_latency += latency_ms
+            seconds = time.perf_counter() - t0
+            latency_ms = seconds * 1e3
+            # every request of the batch waited for the one shared search: charge `seconds` to each of them, so the
+            # engine's avg_latency_ms stays the per-request latency (RetrievalEngine accounts in seconds)
+            self.engine.account(seconds * len(batch), calls=len(batch))
             self.batches += 1
             self.requests += len(batch)
             for row, (_, k, fut) in enumerate(batch):

@@ -24,6 +24,7 @@ class FlatAdam:
     def __init__(self, params, lr: float = 1e-3, weight_decay: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8,
                  max_grad_norm: Optional[float] = 1.0):
         params = [p for p in params if p.requires_grad]
+        self.params = params                      # torch.optim order (state_dict indices)
         self.dense = [p for p in params if not getattr(p, "_b200_sparse", False)]
         self.sparse = [p for p in params if getattr(p, "_b200_sparse", False)]
         if not self.dense:
@@ -37,12 +38,22 @@ class FlatAdam:
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
         off = 0
+        self._seg = []                            # (offset, numel) of every dense parameter inside the flat buffers
         for p in self.dense:
             k = p.numel()
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view(p.shape)
             p.grad = self.grad[off:off + k].view(p.shape)
+            self._seg.append((off, k))
             off += k
+        # torch.optim.Adam skips a parameter whose .grad is None (never reached by backward): no update, no weight decay,
+        # no moment decay.  Gradients here are views of one buffer, so "reached by backward" is tracked per segment: an
+        # autograd hook marks dense parameters, GatherConcatFn marks tables it scatters into in place.
+        self._touched = [False] * len(self.dense)
+        self._touch_sticky = False
+        for i, p in enumerate(self.dense):
+            p._b200_touch = (self, i)
+            p.register_post_accumulate_grad_hook(lambda t, _i=i: self._mark(_i))
         self.sparse_state = {id(p): (torch.zeros_like(p.data), torch.zeros_like(p.data)) for p in self.sparse}
         self.lr, self.wd, self.betas, self.eps, self.max_grad_norm = lr, weight_decay, betas, eps, max_grad_norm
         self.step_count = 0
@@ -53,8 +64,30 @@ class FlatAdam:
         # CUDA-graph training (TwoTowerTrainer.enable_cuda_graph): step counter, lr and Adam's bias corrections on the device
         self.dev_state = None
 
+    def _mark(self, i: int) -> None:
+        self._touched[i] = True
+
+    def touch_all(self) -> None:
+        """Gradients are written straight into .grad by the caller (no autograd): update every parameter."""
+        self._touch_sticky = True
+
+    def _runs(self):
+        """Contiguous [lo, hi) element ranges of the flat buffer whose parameters received a gradient this step."""
+        if self._touch_sticky or all(self._touched):
+            return [(0, self.flat.numel())]
+        runs = []
+        for (off, k), t in zip(self._seg, self._touched):
+            if not t:
+                continue
+            if runs and runs[-1][1] == off:
+                runs[-1] = (runs[-1][0], off + k)
+            else:
+                runs.append((off, off + k))
+        return runs
+
     def zero_grad(self, set_to_none: bool = False) -> None:
         self.grad.zero_()
+        self._touched = [False] * len(self.dense)
         for p in self.sparse:
             p._b200_sparse_grad = None
 
@@ -108,25 +141,67 @@ class FlatAdam:
                     K.sumsq_(vals.reshape(-1), self._acc)   # rows beyond n are zero-filled by the coalescing kernel
             K.clip_coef(self._acc, float(self.max_grad_norm), self._coef, self.grad_norm)
             clip = self._coef
+        runs = self._runs()
         if self.dev_state is not None and getattr(self, "use_device_state", False):
             hyper = self.dev_state["hyper"]   # written by K.train_step_begin at the start of this step
-            K.adam_dense_dev_(self.flat, self.grad, self.m, self.v, self.betas[0], self.betas[1], self.eps, self.wd, hyper,
-                              clip)
+            for lo, hi in runs:
+                K.adam_dense_dev_(self.flat[lo:hi], self.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], self.betas[0],
+                                  self.betas[1], self.eps, self.wd, hyper, clip)
             for p, lists in sparse:
                 m, v = self.sparse_state[id(p)]
                 for rows, vals, n in lists:
                     K.sparse_adam_dev_(p.data, m, v, rows, vals, n, self.betas[0], self.betas[1], self.eps, hyper, clip)
             return
-        K.adam_dense_(self.flat, self.grad, self.m, self.v, lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                      self.step_count, clip)
+        for lo, hi in runs:
+            K.adam_dense_(self.flat[lo:hi], self.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], lr, self.betas[0],
+                          self.betas[1], self.eps, self.wd, self.step_count, clip)
         for p, lists in sparse:
             m, v = self.sparse_state[id(p)]
             for rows, vals, n in lists:
                 K.sparse_adam_(p.data, m, v, rows, vals, n, lr, self.betas[0], self.betas[1], self.eps,
                                self.step_count, clip)
 
+    def _moments(self, p):
+        if getattr(p, "_b200_sparse", False):
+            return self.sparse_state[id(p)]
+        off, k = self._seg[p._b200_touch[1]]
+        return self.m[off:off + k].view(p.shape), self.v[off:off + k].view(p.shape)
+
     def state_dict(self) -> Dict[str, Any]:
-        return {"step": self.step_count, "exp_avg": self.m, "exp_avg_sq": self.v, "lr": self.param_groups[0]["lr"]}
+        """torch.optim.Adam's state_dict layout (what the reference stores under 'optimizer_state',
+        trainers/two_tower.py:209): parameter i of model.parameters() -> {step, exp_avg, exp_avg_sq}, one param group.
+        A parameter Adam has never stepped (state-less in torch) still carries its zero moments here."""
+        state = {}
+        for i, p in enumerate(self.params):
+            m, v = self._moments(p)
+            state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": m.detach().clone(),
+                        "exp_avg_sq": v.detach().clone()}
+        group = {"lr": self.param_groups[0]["lr"], "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "decoupled_weight_decay": False, "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd: Dict[str, Any]) -> None:
+        """Accepts the layout above, i.e. also a state_dict saved by torch.optim.Adam over the same model (the reference
+        trainer's checkpoints).  Parameters missing from `state` (never stepped) keep zero moments."""
+        group = sd["param_groups"][0]
+        self.param_groups[0]["lr"] = group["lr"]
+        self.betas, self.eps, self.wd = tuple(group["betas"]), group["eps"], group["weight_decay"]
+        steps = []
+        for slot, i in enumerate(group["params"]):
+            st = sd["state"].get(i, sd["state"].get(str(i)))
+            m, v = self._moments(self.params[slot])
+            if st is None:
+                m.zero_()
+                v.zero_()
+                continue
+            m.copy_(st["exp_avg"].to(m.device))
+            v.copy_(st["exp_avg_sq"].to(v.device))
+            steps.append(int(float(st["step"])))
+        self.step_count = max(steps) if steps else 0
+        if self.dev_state is not None:
+            self.dev_state["step_host"] = None
+            self.dev_state["lr_host"] = None
 
 
 class TwoTowerTrainer:
@@ -254,6 +329,8 @@ class TwoTowerTrainer:
             total += self.train_step(uf, pf, nf)   # no per-step host sync; one .item() per epoch
             num_batches += 1
         avg_loss = float(total.item()) / num_batches if num_batches > 0 else 0.0
+        from . import ops
+        ops.check_index_errors(self.device)     # an out-of-range categorical id raises IndexError, as nn.Embedding does
         self.train_losses.append(avg_loss)
         return avg_loss
 
@@ -269,6 +346,15 @@ class TwoTowerTrainer:
             p = self.model.get_item_embeddings({"numerical": pf, "categorical": {}})
             total += self.model.in_batch_negative_loss(u, p)
             num_batches += 1
+        dp = getattr(self.model, "dp", None)
+        if dp is not None:
+            # data parallel: in_batch_negative_loss returns this replica's SHARE of the global-batch loss, and the
+            # scheduler / early stopping below must decide identically on every replica (a per-rank value lets the
+            # learning rates diverge and replicas leave train() at different epochs, which deadlocks the collectives)
+            counts = dp.gather_counts(num_batches)
+            if len(set(counts)) != 1:
+                raise RuntimeError(f"data-parallel validation needs the same number of batches on every replica, got {counts}")
+            total = dp.global_loss(total)
         avg_loss = float(total.item()) / num_batches if num_batches > 0 else 0.0
         self.val_losses.append(avg_loss)
         return avg_loss

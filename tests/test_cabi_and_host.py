@@ -118,7 +118,7 @@ def _gloo_worker(rank, world, port, tmp):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
-    from b200rec.dist import ShardedFlatIndex, allreduce_mean_, shard_bounds
+    from b200rec.dist import ShardedFlatIndex, shard_bounds
     from oracle.flat_ip import IndexFlatIP, merge_topk
     dist.init_process_group("gloo", rank=rank, world_size=world)
     rng = np.random.default_rng(5)
@@ -152,9 +152,6 @@ def _gloo_worker(rank, world, port, tmp):
     full.add(cat)
     rs, ri = full.search(qry, k)
     ok = np.array_equal(i.numpy(), ri) and np.allclose(s.numpy(), rs, atol=1e-6)
-    g = torch.full((10,), float(rank + 1))
-    allreduce_mean_(g)
-    ok = ok and torch.allclose(g, torch.full((10,), (1 + world) / 2.0))
     with open(os.path.join(tmp, f"ok{rank}"), "w") as fh:
         fh.write("1" if ok else "0")
     dist.destroy_process_group()
@@ -202,6 +199,10 @@ def test_retrieval_batcher_groups_concurrent_requests():
         def __init__(self):
             self.index, self.total_queries, self.total_latency = Index(), 0, 0.0
 
+        def account(self, seconds, calls=1):                      # RetrievalEngine's bookkeeping contract (seconds)
+            self.total_queries += calls
+            self.total_latency += seconds
+
     async def run():
         model, engine = Model(), Engine()
         b = RetrievalBatcher(model, engine, max_batch=4, max_wait_ms=5.0)
@@ -212,6 +213,8 @@ def test_retrieval_batcher_groups_concurrent_requests():
         for i, ((ids, scores, m), (_, k)) in enumerate(zip(out, reqs)):
             assert ids == [[f"item_{i}_{j}" for j in range(k)]] and len(scores[0]) == k and m["num_results"] == k
         assert engine.total_queries == 10 and b.batches == 3
+        # per-request latency in SECONDS: every request is charged the shared search it waited for
+        assert abs(engine.total_latency - sum(m["latency_ms"] for _, _, m in out) / 1e3) < 1e-9
         engine.index.fail = True
         res = await asyncio.gather(*[b.recommend(f, k) for f, k in reqs[:3]], return_exceptions=True)
         assert all(isinstance(r, ValueError) for r in res)
@@ -282,3 +285,62 @@ def test_feed_requires_cuda_and_big_enough_pools():
     with pytest.raises(RuntimeError, match="no CPU path"):
         DeviceInteractionFeed(np.zeros(4, np.int64), np.zeros(4, np.int64), np.ones(4), np.zeros((2, 3), np.float32),
                               np.zeros((5, 2), np.float32), {}, device="cpu")
+
+
+def test_ixfi_file_format_round_trip(tmp_path):
+    """Host side of the index persistence: the `.faiss` file is faiss' IndexFlatIP layout
+    ("IxFI", d, ntotal, two dummies, is_trained, metric 0, vector<float>), so faiss.read_index can open what we write
+    and we can open what faiss.write_index wrote (reference retrieval.py:261,284)."""
+    import struct
+    from b200rec.retrieval import read_ixfi, write_ixfi
+    rows = np.arange(35, dtype=np.float32).reshape(7, 5) / 3
+    path = tmp_path / "x.faiss"
+    write_ixfi(path, rows)
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"IxFI" and len(raw) == 4 + 33 + 8 + rows.nbytes
+    assert struct.unpack("<iqqqBi", raw[4:37]) == (5, 7, 1 << 20, 1 << 20, 1, 0)
+    assert struct.unpack("<Q", raw[37:45]) == (35,)
+    assert np.array_equal(read_ixfi(path), rows)
+    open(path, "wb").write(b"IxF2" + raw[4:])
+    with pytest.raises(ValueError, match="IxFI"):
+        read_ixfi(path)
+    open(path, "wb").write(raw[:-8])
+    with pytest.raises(ValueError, match="truncated"):
+        read_ixfi(path)
+    bad_metric = raw[:33] + struct.pack("<i", 1) + raw[37:]
+    open(path, "wb").write(bad_metric)
+    with pytest.raises(ValueError, match="metric_type"):
+        read_ixfi(path)
+
+
+def test_flat_index_host_logic_without_a_gpu():
+    """id mapping, the filter_ids post-pass and the engine bookkeeping with a stand-in for the device index."""
+    from b200rec.retrieval import B200FlatIndex, RetrievalEngine
+
+    class Fake:
+        ntotal = 6
+
+        def search(self, q, k, normalize=False):
+            n = len(q)
+            idx = np.tile(np.array([4, 2, 5, 0, 1, 3, -1, -1])[:k], (n, 1))
+            return np.tile(np.linspace(1, 0, 8, dtype=np.float32)[:k], (n, 1)), idx
+
+    eng = RetrievalEngine({"index_type": "b200", "embedding_dim": 4, "top_k": 3})
+    ix = eng.index
+    assert isinstance(ix, B200FlatIndex) and ix.dimension == 4
+    ix.index, ix.current_size = Fake(), 6
+    ix.id_map = {i: f"it{i}" for i in range(6)}
+    ix.reverse_id_map = {v: k for k, v in ix.id_map.items()}
+    q = np.zeros((2, 4), np.float32)
+    ids, scores, m = eng.retrieve(q)
+    assert ids == [["it4", "it2", "it5"]] * 2 and m["num_results"] == 6 and not m["cache_hit"]
+    assert ix.search(q, k=8)[0][0] == ["it4", "it2", "it5", "it0", "it1", "it3"]          # -1 slots are dropped
+    ids, scores = ix.search(q[0], k=2, filter_ids=["it5", "it1", "it3", "zzz"])           # post-filter over 2k = 4 rows
+    assert ids == [["it5"]] and np.allclose(scores[0], [np.linspace(1, 0, 8)[2]])          # it1 / it3 lie beyond row 4
+    ids, _ = ix.search(q[0], k=3, filter_ids=["it5", "it1", "it3", "it0"])                # 2k = 6 rows, first 3 survivors
+    assert ids == [["it5", "it0", "it1"]]
+    assert ix.search(q, k=1, filter_ids=["it3"])[0] == [[], []]                           # it3 is outside the 2 best rows
+    del ix.id_map[2]
+    ix._id_array = None
+    assert ix.search(q, k=3)[0][0] == ["it4", "it5"]                                      # unmapped rows are skipped, not refilled
+    assert eng.get_metrics()["total_queries"] == 1 and eng.get_metrics()["index_type"] == "b200"

@@ -18,7 +18,8 @@ def test_gather_concat_and_sparse_grad_match_oracle():
     num = torch.randn(B, 5)
     widths = [50, 64, 3]
     offs = [5, 55, 119]
-    out, err = K.gather_concat(num.to(DEV), [t.to(DEV) for t in tabs], [i.to(DEV) for i in idx], widths, offs, 122, B, DEV)
+    err = torch.zeros((1,), dtype=torch.int32, device=DEV)
+    out = K.gather_concat(num.to(DEV), [t.to(DEV) for t in tabs], [i.to(DEV) for i in idx], widths, offs, 122, B, DEV, err)
     ref = torch.cat([num] + [t[i] for t, i in zip(tabs, idx)], dim=1)
     assert torch.equal(out.cpu(), ref)  # gathers are bit-exact
     assert int(err.item()) == 0
@@ -35,6 +36,41 @@ def test_gather_concat_and_sparse_grad_match_oracle():
         assert torch.allclose(got, dense, atol=1e-4, rtol=1e-5)
 
 
+def test_out_of_range_ids_raise_and_never_touch_other_memory():
+    """nn.Embedding raises IndexError for an id outside the table (reference two_tower.py:46-50,116).  Our gather flags
+    it (ops.check_index_errors raises), and the backward treats such a sample like the padding row: no row >= the table
+    size ever reaches scatter_rows / sparse Adam."""
+    from b200rec import kernels as K, ops
+    from b200rec.two_tower import UserTower
+    torch.manual_seed(0)
+    t = UserTower(4, embedding_dim=16, hidden_layers=[32], dropout_rate=0.0, categorical_features={"f": 10}).to(DEV)
+    ids = torch.tensor([1, 2, 11, 3, -5, 2, 10, 7], device=DEV)           # table has 11 rows: 11 and -5 are invalid
+    out = t(torch.randn(8, 4, device=DEV), {"f": ids})
+    with pytest.raises(IndexError):
+        ops.check_index_errors()
+    ops.check_index_errors()                                               # the flag was consumed
+    guard = torch.zeros(64, 6, device=DEV)                                 # table view inside a larger buffer
+    table = guard[16:27]
+    dY = torch.ones(8, 6, device=DEV)
+    rows, vals, nt = K.embedding_sparse_grad(ids, dY, 6, 11, 0)
+    n = int(nt.item())
+    assert rows[:n].cpu().tolist() == [1, 2, 3, 7, 10]
+    assert vals[:n, 0].cpu().tolist() == [1.0, 2.0, 1.0, 1.0, 1.0]
+    K.scatter_rows(rows, vals, nt, table, accumulate=True)
+    assert guard[:16].abs().sum().item() == 0 and guard[27:].abs().sum().item() == 0
+    out.sum().backward()                                                   # full autograd path stays in bounds too
+    assert torch.isfinite(t.embeddings["f"].weight.grad).all()
+    with pytest.raises(RuntimeError):                                      # one id per row is required
+        t(torch.randn(8, 4, device=DEV), {"f": ids[:5]})
+
+
+def test_explicit_ce_rejects_ragged_negatives():
+    from b200rec import ops
+    u, p = torch.randn(4, 8, device=DEV), torch.randn(4, 8, device=DEV)
+    with pytest.raises(RuntimeError):
+        ops.ExplicitCEFn.apply(u, p, torch.randn(10, 8, device=DEV), None, None, 20.0)
+
+
 def test_flat_adam_matches_torch_adam_with_clipping():
     from b200rec.trainer import FlatAdam
     torch.manual_seed(1)
@@ -43,6 +79,7 @@ def test_flat_adam_matches_torch_adam_with_clipping():
     our_p = [torch.nn.Parameter(p.detach().clone().to(DEV)) for p in ref_p]
     ref_opt = torch.optim.Adam(ref_p, lr=1e-3, weight_decay=1e-5)
     ours = FlatAdam(our_p, lr=1e-3, weight_decay=1e-5, max_grad_norm=1.0)
+    ours.touch_all()           # gradients are copied straight into .grad below (no autograd hooks fire)
     for step in range(5):
         grads = [torch.randn(s) * (3.0 if step % 2 == 0 else 0.01) for s in shapes]
         ref_opt.zero_grad()
@@ -57,6 +94,45 @@ def test_flat_adam_matches_torch_adam_with_clipping():
         assert abs(ours.grad_norm.item() - norm.item()) <= 1e-5 * norm.item()
         for a, b in zip(our_p, ref_p):
             assert torch.allclose(a.detach().cpu(), b.detach(), atol=1e-6, rtol=1e-5)
+
+
+def test_flat_adam_skips_parameters_without_gradient_and_round_trips_torch_state():
+    """torch.optim.Adam leaves a parameter whose grad is None untouched (no update, no weight decay): FlatAdam tracks
+    which flat segments autograd reached.  Its state_dict has torch.optim.Adam's layout and loads one written by torch."""
+    from b200rec.trainer import FlatAdam
+    torch.manual_seed(4)
+    shapes = [(1,), (8, 4), (8,), (3, 8)]
+    ref_p = [torch.nn.Parameter(torch.randn(s)) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone().to(DEV)) for p in ref_p]
+    ref_opt = torch.optim.Adam(ref_p, lr=1e-2, weight_decay=1e-2)
+    ours = FlatAdam(our_p, lr=1e-2, weight_decay=1e-2, max_grad_norm=None)
+    x = torch.randn(5, 4)
+    for _ in range(3):
+        ref_opt.zero_grad()
+        ours.zero_grad()
+        (x @ ref_p[1].T + ref_p[2]).pow(2).sum().backward()               # parameters 0 and 3 are never reached
+        (x.to(DEV) @ our_p[1].T + our_p[2]).pow(2).sum().backward()
+        ref_opt.step()
+        ours.step()
+    for a, b in zip(our_p, ref_p):
+        assert torch.allclose(a.detach().cpu(), b.detach(), atol=1e-6, rtol=1e-5)
+    sd, rsd = ours.state_dict(), ref_opt.state_dict()
+    assert sorted(sd.keys()) == sorted(rsd.keys()) and sd["param_groups"][0]["params"] == rsd["param_groups"][0]["params"]
+    for i in rsd["state"]:
+        assert torch.allclose(sd["state"][i]["exp_avg"].cpu(), rsd["state"][i]["exp_avg"], atol=1e-7)
+        assert torch.allclose(sd["state"][i]["exp_avg_sq"].cpu(), rsd["state"][i]["exp_avg_sq"], atol=1e-9)
+    # resume from the torch optimiser's state: the next step matches torch's next step
+    fresh_p = [torch.nn.Parameter(p.detach().clone().to(DEV)) for p in ref_p]
+    fresh = FlatAdam(fresh_p, lr=1.0, weight_decay=0.0, max_grad_norm=None)
+    fresh.load_state_dict(rsd)
+    ref_opt.zero_grad()
+    fresh.zero_grad()
+    (x @ ref_p[1].T + ref_p[2]).pow(2).sum().backward()
+    (x.to(DEV) @ fresh_p[1].T + fresh_p[2]).pow(2).sum().backward()
+    ref_opt.step()
+    fresh.step()
+    for a, b in zip(fresh_p, ref_p):
+        assert torch.allclose(a.detach().cpu(), b.detach(), atol=1e-6, rtol=1e-5)
 
 
 def test_inbatch_loss_large_batch_and_backward_vs_torch():

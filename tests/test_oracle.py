@@ -253,3 +253,30 @@ def test_flat_ip_oracle_matches_the_reference_recommendation_twin():
     assert np.array_equal(I, g["recs"])
     twin = flat_ip.eval_twin_topk(users[test_users], items, {u: v.tolist() for u, v in train.items()}, test_users.tolist(), k)
     assert [twin[int(u)] for u in test_users.tolist()] == g["recs"].tolist()
+
+
+def _metrics_cases():
+    import json
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics_small.npz"))
+    cases = json.loads(str(g["cases_json"]))
+    for c in cases.values():
+        c["pred"] = {int(k): v for k, v in c["pred"].items()}
+        c["gt"] = {int(k): set(v) for k, v in c["gt"].items()}
+        c["exclude"] = {int(k): set(v) for k, v in c["exclude"].items()} if c["exclude"] else None
+    return cases
+
+
+def test_metrics_oracle_matches_the_reference_evaluator():
+    """oracle/metrics.py (Evaluator.evaluate + per-user helpers restated) reproduces, number for number, what the
+    imported reference computed (tests/golden/make_golden_metrics.py): distinct top-K lists, repeated ids, ragged lists,
+    an exclusion dict, users without / with empty ground truth, ground-truth ids that are never recommended."""
+    from oracle import metrics as M
+    for name, c in _metrics_cases().items():
+        got, mat = M.evaluate(c["pred"], c["gt"], c["k_values"], c["num_items"], c["exclude"])
+        assert got.keys() == c["metrics"].keys()
+        for k, v in c["metrics"].items():
+            assert got[k] == v, (name, k, got[k], v)
+        for j, k in enumerate(sorted(c["k_values"])):
+            assert mat[:, 4 * j].tolist() == c["per_user_recall"][str(k)]
+            assert mat[:, 4 * j + 2].tolist() == c["per_user_ndcg"][str(k)]
