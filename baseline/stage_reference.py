@@ -13,7 +13,7 @@ import shutil
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DST = os.path.join(ROOT, "baseline", "_ref")
-WANT = ["src/models", "src/training", "src/data", "src/evaluation", "scripts/evaluate_model.py",
+WANT = ["src/constants.py", "src/models", "src/training", "src/data", "src/evaluation", "scripts/evaluate_model.py",
         "tests/test_two_tower_model.py", "tests/conftest.py", "ml-1m/users.dat", "ml-1m/movies.dat", "pytest.ini"]
 
 

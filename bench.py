@@ -1,12 +1,22 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the B200 two-tower hot path (contract: one JSON line on rank 0).
+"""bench.py — headline benchmark of the B200 two-tower hot path (contract: ONE JSON line on rank 0).
 
 Primary workload (BASELINE.json config 3): exact inner-product top-100 over a 10 M x 128 bf16 catalogue, query batch
-4096, catalogue row-sharded over the N GPUs of one box (total work fixed => "strong" scaling).  `value` = whole-job
-QPS with queries resident in HBM; `e2e` = the same through the public index API with HOST query / result buffers.
-The `train` block reports BASELINE.json config 2 (1 M users x 100 K items, dim 64, batch 8192, in-batch negatives) as
-train samples/s on rank 0's GPU (N=1 only).  `--impl reference` times the CPU restatement of the reference's path
-(oracle/: numpy sgemm + select standing in for faiss-cpu, which cannot be installed offline).
+4096, catalogue row-sharded over the N GPUs of one box (total work fixed => "strong" scaling).
+  value  = whole-job QPS with the query operand resident in HBM (CUDA events, max over ranks)
+  e2e    = the same through the faiss-shaped plugin call with HOST numpy buffers (`index.search_stream`: numpy queries
+           in, (D, I) numpy out; every batch's host->device and device->host copies are inside the timed region,
+           double-buffered against the neighbouring batches' searches); `e2e_sync_call` = one blocking
+           `index.search(q, k)` per step
+  parity_checked = 32 of the timed 4096 queries re-searched on the host (oracle sgemm + exact select over every shard)
+Extra blocks in the same line (each with its own `roofline` and, at N = 1, `cpu_baseline`):
+  train       config 2  synthetic 1 M users x 100 K items, dim 64, batch 8192 per GPU, in-batch negatives (DP at N > 1)
+  train_ml1m  config 1  MovieLens-1M-shaped step through the device feed;  epoch_ml1m: a full epoch + exact top-100 eval
+  train_cfg4  config 4  50 M / 5 M-row tables, dim 128, batch 8192 per GPU, row-sparse tables (DP at N > 1)
+  serve       config 5  user-tower forward + 100 M x 64 sharded top-1000, Q sweep
+`--impl reference` times the reference's CPU path on the host cores: flat search = faiss-cpu's blocked sgemm + k-select
+restated (oracle/flat_ip.search_blocked; faiss itself is not installable offline), training = the imported reference
+model + its trainer's step body on torch-CPU (baseline/_ref, staged by __graft_entry__.build()).
 
   python bench.py --gpus 1 --steps 20 --warmup 5
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 bench.py --gpus 8
@@ -42,12 +52,19 @@ def _peaks():
         with open(path) as fh:
             p = json.load(fh)
         return {"hbm_gbs": float(p["hbm_gbs"]), "tflops": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
-                "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
-    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+                "tflops_burst": float(p["bf16_tflops"]), "source": "measured (MEASURED_PEAKS.json: sustained bf16, copy bandwidth)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def host_threads() -> int:
+    """All host cores, set explicitly: torchrun exports OMP_NUM_THREADS=1, which would silently throttle the CPU arm."""
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return n
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / power / throttle reasons sampled DURING the timed region."""
 
     def __init__(self, gpu_index: int):
         self.rows = []
@@ -61,7 +78,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "25"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -82,102 +99,281 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], None, set()
+        sm, pw, smax, reasons = [], [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 smax = float(r[1])
+                pw.append(float(r[2]))
                 for name, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_median": float(np.median(pw)) if pw else None,
+                "power_w_max": float(np.max(pw)) if pw else None}
 
 
 # ------------------------------------------------------------------------------------------------ data
-def make_queries_host(seed: int = SEED) -> torch.Tensor:
+def make_queries_host(n: int = N_QUERIES, dim: int = DIM, seed: int = SEED) -> torch.Tensor:
     g = torch.Generator().manual_seed(seed)
-    q = torch.nn.functional.normalize(torch.randn(N_QUERIES, DIM, generator=g), dim=1)
-    return q
+    return torch.nn.functional.normalize(torch.randn(n, dim, generator=g), dim=1)
 
 
-def make_catalogue_shard(lo: int, hi: int, device) -> torch.Tensor:
+def make_catalogue_shard(lo: int, hi: int, device, n_total: int = N_ITEMS, dim: int = DIM, seed: int = SEED) -> torch.Tensor:
     """Rows [lo, hi) of the synthetic catalogue normalize(N(0,1)) -> bf16; generated block-wise from (seed, block) so
     any sharding sees the same global rows."""
-    out = torch.empty((hi - lo, DIM), dtype=torch.bfloat16, device=device)
+    out = torch.empty((hi - lo, dim), dtype=torch.bfloat16, device=device)
     blk = 1 << 20
     b0 = lo // blk
     while b0 * blk < hi:
-        s, e = b0 * blk, min((b0 + 1) * blk, N_ITEMS)
-        g = torch.Generator(device=device).manual_seed(SEED * 1000003 + b0)
-        x = torch.nn.functional.normalize(torch.randn(e - s, DIM, device=device, generator=g), dim=1).to(torch.bfloat16)
+        s, e = b0 * blk, min((b0 + 1) * blk, n_total)
+        g = torch.Generator(device=device).manual_seed(seed * 1000003 + b0)
+        x = torch.nn.functional.normalize(torch.randn(e - s, dim, device=device, generator=g), dim=1).to(torch.bfloat16)
         a, b = max(s, lo), min(e, hi)
         out[a - lo:b - lo] = x[a - s:b - s]
         b0 += 1
     return out
 
 
-# ------------------------------------------------------------------------------------------------ CPU reference arm
+def zipf_ids(rng, n, hi):
+    return np.clip(rng.zipf(1.05, size=n), 1, hi).astype(np.int64)
+
+
+# ------------------------------------------------------------------------------------------------ CPU baselines
 def cpu_retrieval_baseline(rows: int, queries: int, threads: int):
-    """Flat IP top-100 with the oracle (numpy sgemm + exact select) on a bounded sample; QPS scaled to 10 M rows."""
-    from oracle.flat_ip import IndexFlatIP, normalize_L2
-    torch.set_num_threads(threads)
-    rng = np.random.default_rng(SEED)
-    cat = normalize_L2(rng.standard_normal((rows, DIM)).astype(np.float32))
-    qry = normalize_L2(rng.standard_normal((queries, DIM)).astype(np.float32))
-    ix = IndexFlatIP(DIM)
-    ix.add(cat)
+    """Flat IP top-100 the way faiss-cpu lays it out (blocked sgemm + k-select per block, all host cores) on a bounded
+    sample; QPS scaled linearly to 10 M rows (the work per query is proportional to the catalogue)."""
+    from oracle.flat_ip import search_blocked
+    g = torch.Generator().manual_seed(SEED)
+    cat = torch.nn.functional.normalize(torch.randn(rows, DIM, generator=g), dim=1)
+    qry = torch.nn.functional.normalize(torch.randn(queries, DIM, generator=g), dim=1)
+    search_blocked(cat[: 1 << 17], qry[:64], TOPK, threads)   # warm the thread pool
     t0 = time.perf_counter()
-    ix.search(qry, TOPK)
+    search_blocked(cat, qry, TOPK, threads)
     dt = time.perf_counter() - t0
-    qps_full = queries / (dt * (N_ITEMS / rows))
-    return qps_full, dt
+    return queries / (dt * (N_ITEMS / rows)), dt
+
+
+def _reference_modules():
+    """The UNMODIFIED reference model / trainer modules staged under baseline/_ref (None when not staged)."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref, "src", "models", "two_tower.py")):
+        return None
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    import importlib
+    return {"two_tower": importlib.import_module("src.models.two_tower"),
+            "utils": importlib.import_module("src.training.utils"),
+            "trainer": importlib.import_module("src.training.trainers.two_tower")}
+
+
+def cpu_train_baseline_cfg2(threads: int, steps: int = 3):
+    """Config 2 on the host cores: the IMPORTED reference model (1 M / 100 K-row embedding tables at the reference's own
+    row width heuristic min(50, .)) and the step body of its TwoTowerTrainer.train_epoch (trainers/two_tower.py:98-151:
+    towers, in-batch loss, zero_grad, backward, clip_grad_norm_(1.0), Adam(lr 1e-3, wd 1e-5).step) on torch-CPU.  The
+    reference trainer itself feeds no categorical ids, so its step body is driven here with the config-2 id tensors."""
+    mods = _reference_modules()
+    B, NU, NI, FD = 8192, 1_000_000, 100_000, 16
+    rng = np.random.default_rng(SEED)
+    if mods is None:
+        return None
+    tt = mods["two_tower"]
+    torch.manual_seed(SEED)
+    ut = tt.UserTower(FD, 64, [128, 64], 0.2, "relu", {"user_id": NU})
+    it = tt.ItemTower(FD, 64, [128, 64], 0.2, "relu", {"item_id": NI}, use_content_embedding=False)
+    model = tt.TwoTowerModel(ut, it, temperature=0.05)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5)
+    model.train()
+    uf, pf = torch.randn(B, FD), torch.randn(B, FD)
+    uid, iid = torch.from_numpy(zipf_ids(rng, B, NU)), torch.from_numpy(zipf_ids(rng, B, NI))
+
+    def step():
+        u = model.get_user_embeddings({"numerical": uf, "categorical": {"user_id": uid}})
+        p = model.get_item_embeddings({"numerical": pf, "categorical": {"item_id": iid}})
+        loss = model.in_batch_negative_loss(u, p)
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+        opt.step()
+        return float(loss.item())
+
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": B / dt, "unit": "samples/s", "cores": threads, "kind": "reference",
+            "sample": f"{steps} steps of the imported reference TwoTowerModel (baseline/_ref) + its trainer's step body "
+                      f"(in-batch loss, clip, dense Adam) on torch-CPU at batch {B}, tables 1M / 100K rows",
+            "ms_per_step": dt * 1e3}
+
+
+def cpu_train_baseline_ml1m(threads: int, steps: int = 3):
+    """Config 1 step on the host cores: the imported reference TwoTowerTrainer.train_epoch over pre-built batches
+    (batch 1024 x 16 negatives, 0.7 explicit + 0.3 in-batch), i.e. the reference's model time WITHOUT its Python feed."""
+    mods = _reference_modules()
+    if mods is None:
+        return None
+    torch.manual_seed(SEED)
+    model = mods["utils"].create_two_tower_model_for_training(3, 20, {"embedding_dim": 128, "hidden_layers": [256, 128],
+                                                                      "dropout_rate": 0.2, "temperature": 0.05})
+    batches = [{"user_features": torch.randn(1024, 3), "pos_item_features": torch.randn(1024, 20),
+                "neg_item_features": torch.randn(1024, 16, 20)} for _ in range(steps)]
+    tr = mods["trainer"].TwoTowerTrainer(model, batches, [], {"learning_rate": 1e-3, "weight_decay": 1e-5,
+                                                              "checkpoint_dir": "/tmp/b200rec_ref_ckpt"}, device="cpu")
+    tr.train_loader = batches[:1]
+    tr.train_epoch(0)
+    tr.train_loader = batches
+    t0 = time.perf_counter()
+    tr.train_epoch(1)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": 1024 / dt, "unit": "samples/s", "cores": threads, "kind": "reference",
+            "sample": f"{steps} batches through the imported reference TwoTowerTrainer.train_epoch on torch-CPU "
+                      "(batch 1024 x 16 negatives, mixed loss), batches pre-built: model time without the reference's feed",
+            "ms_per_step": dt * 1e3}
 
 
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    rows, queries = 1_000_000, 2048
-    vals = []
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_retrieval_baseline(rows // 4, 32, threads)
-    t_all = time.perf_counter()
+    threads = host_threads()
+    rows, queries = 1_000_000, 1024
     steps = max(1, min(args.steps, 3))
+    vals, t_all = [], time.perf_counter()
     for _ in range(steps):
         qps, dt = cpu_retrieval_baseline(rows, queries, threads)
         vals.append(qps)
     ms = (time.perf_counter() - t_all) / steps * 1e3
     v = float(np.median(vals))
-    sample = (f"{queries} queries x {rows} rows fp32 per step, oracle/flat_ip.py (numpy sgemm + exact select, faiss-cpu "
-              f"restated), QPS scaled linearly to {N_ITEMS} rows")
+    sample = (f"{queries} queries x {rows} rows fp32 per step on {threads} threads (OMP/MKL threads set explicitly), "
+              f"oracle/flat_ip.search_blocked = faiss-cpu's IndexFlatIP layout restated (blocked MKL sgemm + k-select per "
+              f"block + running merge; faiss-cpu is not installable offline), QPS scaled linearly to {N_ITEMS} rows")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "queries/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "exact IP top-100, 10M x 128, query batch 4096 (CPU arm: bounded sample)"},
             "cpu_baseline": {"value": v, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not args.no_train:
+        try:
+            line["train"] = cpu_train_baseline_cfg2(threads)
+            line["train_ml1m"] = cpu_train_baseline_ml1m(threads)
+        except Exception as exc:  # noqa: BLE001 - the retrieval line must still be printed
+            line["train_error"] = repr(exc)[:300]
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------------------------------------ training block
-def run_train_block(device, steps: int, warmup: int, cpu_baseline: bool, world: int = 1, rank: int = 0):
-    """BASELINE config 2: 1 M users x 100 K items, dim 64, batch 8192 PER GPU, in-batch negatives.  world > 1: exact data
-    parallel (b200rec.dist.DataParallel: BatchNorm statistics and in-batch negatives over the global batch, summed
-    gradients) — the same numbers one process would produce on the world x 8192 batch."""
+# ------------------------------------------------------------------------------------------------ helpers
+class Ctx:
+    def __init__(self, device, world, rank):
+        self.device, self.world, self.rank = device, world, rank
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device=self.device)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+
+def timed(ctx: Ctx, fn, steps: int, warmup: int) -> float:
+    """ms per step of fn(i): barrier + synchronize on both sides, CUDA events, max over ranks."""
+    for i in range(warmup):
+        fn(i)
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    ctx.barrier()
+    return ctx.max_over_ranks(e0.elapsed_time(e1) / steps)[0]
+
+
+# ------------------------------------------------------------------------------------------------ parity of the timed run
+def parity_check(ctx: Ctx, index, q_host: torch.Tensor, scores: torch.Tensor, ids: torch.Tensor, n_check: int = 32):
+    """Re-search `n_check` of the timed queries on the HOST: every rank scores its own catalogue shard with the oracle
+    (numpy sgemm + exact select on the bf16-rounded rows upcast to fp32), the per-shard lists are merged on rank 0 and
+    compared with what the GPU path returned for those queries (ids exact except inside score ties within 1e-5)."""
+    import torch.distributed as dist
+    from oracle.flat_ip import IndexFlatIP, merge_topk
+    g = torch.Generator().manual_seed(SEED + 17)
+    pick = torch.randperm(q_host.shape[0], generator=g)[:n_check].sort().values
+    qs = q_host[pick].to(torch.bfloat16).to(torch.float32).numpy()
+    run_s = np.full((n_check, TOPK), -np.finfo(np.float32).max, np.float32)
+    run_i = np.full((n_check, TOPK), -1, np.int64)
+    t0 = time.perf_counter()
+    chunk = 1 << 20
+    for r0 in range(0, index.ntotal, chunk):
+        rows = index._cat[r0:min(index.ntotal, r0 + chunk), : index.d].float().cpu().numpy()
+        ix = IndexFlatIP(index.d, db_block=1 << 17)
+        ix.add(rows)
+        s, i = ix.search(qs, TOPK)
+        i = np.where(i >= 0, i + r0 + index.row_offset, -1)
+        run_s, run_i = merge_topk([run_s, s], [run_i, i], TOPK)
+    if ctx.world > 1:
+        ts, ti = torch.from_numpy(run_s).to(ctx.device), torch.from_numpy(run_i).to(ctx.device)
+        gs = [torch.empty_like(ts) for _ in range(ctx.world)]
+        gi = [torch.empty_like(ti) for _ in range(ctx.world)]
+        dist.all_gather(gs, ts)
+        dist.all_gather(gi, ti)
+        run_s, run_i = merge_topk([x.cpu().numpy() for x in gs], [x.cpu().numpy() for x in gi], TOPK)
+    got_s, got_i = scores[pick.to(scores.device)].cpu().numpy(), ids[pick.to(ids.device)].cpu().numpy()
+    diff = got_i != run_i
+    ties_ok = bool((np.abs(got_s - run_s)[diff] <= 1e-5).all())
+    ok = bool(np.allclose(got_s, run_s, atol=2e-5, rtol=0) and ties_ok and diff.mean() <= 0.01)
+    return {"queries": int(n_check), "ok": ok, "ids_differing_inside_ties": int(diff.sum()),
+            "max_abs_score_diff": float(np.abs(got_s - run_s).max()), "seconds": round(time.perf_counter() - t0, 2),
+            "checker": "oracle/flat_ip.IndexFlatIP over every shard (host), merged on rank 0"}
+
+
+# ------------------------------------------------------------------------------------------------ training blocks
+def _train_roofline(ms: float, flops: float, bytes_: float, note: str):
+    pk = _peaks()
+    t_tensor = flops / (pk["tflops"] * 1e12) * 1e3
+    t_hbm = bytes_ / (pk["hbm_gbs"] * 1e9) * 1e3
+    bound = "hbm" if t_hbm >= t_tensor else "tensor"
+    if bound == "hbm":
+        achieved, peak, unit = bytes_ / (ms * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s"
+    else:
+        achieved, peak, unit = flops / (ms * 1e-3) / 1e12, pk["tflops"], "TFLOP/s"
+    return {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": None,
+            "scope": "whole training step (launch-bound chains of small kernels: no single kernel dominates)",
+            "algorithmic_flops": flops, "algorithmic_bytes": bytes_, "tensor_floor_ms": t_tensor, "hbm_floor_ms": t_hbm,
+            "frac_of_tensor_peak": flops / (ms * 1e-3) / 1e12 / pk["tflops"],
+            "frac_of_hbm_peak": bytes_ / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "note": note, "peak_source": pk["source"]}
+
+
+def _make_cfg_model(device, FD, NU, NI, edim, hidden, E, sparse_tables):
+    from b200rec.training_utils import create_two_tower_model_for_training
+    cfg = {"embedding_dim": E, "hidden_layers": hidden, "dropout_rate": 0.2, "temperature": 0.05,
+           "user_categorical_features": {"user_id": NU}, "item_categorical_features": {"item_id": NI},
+           "embedding_dims": {"user_id": edim, "item_id": edim}, "sparse_tables": sparse_tables}
+    torch.manual_seed(SEED)
+    with torch.device(device):          # parameters are created and initialised on the GPU (a 50 M-row table never
+        model = create_two_tower_model_for_training(FD, FD, cfg)   # visits the host)
+    return model
+
+
+def run_table_train_block(ctx: Ctx, steps: int, warmup: int, cpu_baseline: bool, *, name: str, NU: int, NI: int,
+                          edim: int, hidden, E: int, sparse_tables: bool, check_dp: bool):
+    """One data-parallel training configuration with id-embedding tables (configs 2 and 4): batch 8192 PER GPU,
+    in-batch negatives over the GLOBAL batch, exact data parallel at N > 1 (b200rec.dist.DataParallel)."""
     import torch.distributed as dist
     from b200rec import _native as N
     from b200rec.trainer import TwoTowerTrainer
-    from b200rec.training_utils import create_two_tower_model_for_training
-    B, NU, NI, FD = 8192, 1_000_000, 100_000, 16
-    torch.manual_seed(SEED)
-    cfg = {"embedding_dim": 64, "hidden_layers": [128, 64], "dropout_rate": 0.2, "temperature": 0.05,
-           "user_categorical_features": {"user_id": NU}, "item_categorical_features": {"item_id": NI},
-           "embedding_dims": {"user_id": 64, "item_id": 64}}
-    model = create_two_tower_model_for_training(FD, FD, cfg)
+    device, world, rank = ctx.device, ctx.world, ctx.rank
+    B, FD = 8192, 16
+    model = _make_cfg_model(device, FD, NU, NI, edim, hidden, E, sparse_tables)
     trainer = TwoTowerTrainer(model, [], [], {"learning_rate": 1e-3, "weight_decay": 1e-5,
                                               "checkpoint_dir": "/tmp/b200rec_bench_ckpt"}, device=str(device))
     if world > 1:
@@ -187,72 +383,113 @@ def run_train_block(device, steps: int, warmup: int, cpu_baseline: bool, world: 
     rng = np.random.default_rng(SEED + 1000 * rank)
     torch.manual_seed(SEED + 1000 * rank)   # features differ per replica; parameters were initialised identically above
     pool = 8
-
-    def zipf_ids(n, hi):
-        return np.clip(rng.zipf(1.05, size=n), 1, hi).astype(np.int64)
-
     host = [{"uf": torch.randn(B, FD).pin_memory(), "pf": torch.randn(B, FD).pin_memory(),
-             "uid": torch.from_numpy(zipf_ids(B, NU)).pin_memory(),
-             "iid": torch.from_numpy(zipf_ids(B, NI)).pin_memory()} for _ in range(pool)]
+             "uid": torch.from_numpy(zipf_ids(rng, B, NU)).pin_memory(),
+             "iid": torch.from_numpy(zipf_ids(rng, B, NI)).pin_memory()} for _ in range(pool)]
     dev = [{k: v.to(device) for k, v in b.items()} for b in host]
 
     def step_dev(b):
         return trainer.train_step(b["uf"], b["pf"], None, {"user_id": b["uid"]}, {"item_id": b["iid"]})
 
-    def sync():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    step_dev(dev[0])
+    dp_check = None
+    if world > 1 and check_dp:
+        # step 1 runs without dropout (masks are per replica by design) so that it can be replayed by one process
+        for t in (model.user_tower, model.item_tower):
+            t.dropout_rate = 0.0
+        first_loss = step_dev(dev[0])
+        dp_check = _dp_first_step_check(ctx, first_loss, dev[0], FD, NU, NI, edim, hidden, E, sparse_tables)
+        for t in (model.user_tower, model.item_tower):
+            t.dropout_rate = 0.2
+    else:
+        step_dev(dev[0])
     torch.cuda.synchronize()
     lc0 = N.launch_count()
     step_dev(dev[1])
-    kernels_per_step = N.launch_count() - lc0      # library kernels of one eager step (the graph replays the same nodes)
-    if world == 1:
-        trainer.enable_cuda_graph(warm_steps=1)    # one graph launch per step instead of ~210 host launches
-    for i in range(max(warmup, 3)):
-        step_dev(dev[i % pool])
-    sync()
-    l0 = N.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        step_dev(dev[i % pool])
-    e1.record()
-    sync()
-    ms = e0.elapsed_time(e1) / steps
-    launches = int(kernels_per_step)
+    kernels_per_step = N.launch_count() - lc0      # library kernels of one eager step (a graph replays the same nodes)
+    graph = trainer.enable_cuda_graph(warm_steps=1)
+    ms = timed(ctx, lambda i: step_dev(dev[i % pool]), steps, max(warmup, 3))
     # end to end: host batches (pinned) -> device every step, loss read back every step
+    ctx.barrier()
     t0 = time.perf_counter()
     for i in range(steps):
         b = {k: v.to(device, non_blocking=True) for k, v in host[i % pool].items()}
         float(step_dev(b).item())
-    sync()
-    e2e_ms = (time.perf_counter() - t0) / steps * 1e3
-    if world > 1:
-        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = [float(x) for x in t.tolist()]
+    ctx.barrier()
+    e2e_ms = ctx.max_over_ranks((time.perf_counter() - t0) / steps * 1e3)[0]
+    # algorithmic work of ONE replica's step: towers 6 * sum(in*out) FLOP per sample and pass,
+    # in-batch loss 6 * B_local * B_global * E; bytes = optimiser traffic (28 B per densely updated parameter; row-sparse
+    # tables touch 28 B per element of a touched row) + embedding gather / scatter + activations
+    dims = [FD + edim] + list(hidden) + [E]
+    macs = sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+    flops = 2 * 6 * B * macs + 6.0 * B * (B * world) * E
+    mlp_params = 2 * sum(a * b + b for a, b in zip(dims[:-1], dims[1:]))
+    table_params = (NU + 1 + NI + 1) * edim
+    dense_bytes = 28.0 * (mlp_params + (0 if sparse_tables else table_params))
+    sparse_bytes = (28.0 * 2 * B * edim * world) if sparse_tables else 0.0
+    act_bytes = 4.0 * B * sum(dims) * 2 * 3
+    bytes_ = dense_bytes + sparse_bytes + act_bytes + 2 * B * (8 + 2 * 4 * edim)
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
     out = {"metric": "train samples/s", "value": world * B / ms * 1e3, "unit": "samples/s", "ms_per_step": ms,
            "n_gpus": world, "scaling": "weak",
-           "config": {"workload": f"synthetic 1M users x 100K items, dim 64, batch 8192 per GPU (global {world * B}), "
-                                  "in-batch negatives over the global batch, fp32-grade split-bf16 GEMMs, dense Adam + "
-                                  "clip (reference semantics)" + (", exact data parallel: synced BatchNorm statistics, "
-                                  "all-gathered negatives, summed gradients" if world > 1 else "")},
+           "config": {"workload": f"{name}: {NU} users x {NI} items, id-embedding dim {edim}, E {E}, hidden {list(hidden)}, "
+                                  f"batch {B} per GPU (global {world * B}), in-batch negatives over the global batch, "
+                                  "fp32-grade split-bf16 GEMMs, " +
+                                  ("row-sparse Adam on the touched table rows (dense Adam on the MLP)" if sparse_tables
+                                   else "dense Adam + clip over ALL parameters (reference semantics)") +
+                                  (", exact data parallel: synced BatchNorm statistics, all-gathered negatives, summed "
+                                   "gradients" if world > 1 else "")},
            "e2e": {"value": world * B / e2e_ms * 1e3, "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
                    "d2h_bytes_per_step": 4 * world},
-           "gpu_launches_per_step": int(launches), "cuda_graph": world == 1,
-           "dtype": "f32 (bf16x6 split products, fp32 accumulate)"}
+           "gpu_launches_per_step": int(kernels_per_step), "cuda_graph": bool(graph),
+           "dtype": "f32 (bf16x6 split products, fp32 accumulate)",
+           "roofline": _train_roofline(ms, flops, bytes_, "per replica; bytes dominated by " +
+                                       ("the touched rows' Adam state" if sparse_tables else "dense Adam over both tables"))}
+    if dp_check is not None:
+        out["dp_check"] = dp_check
     if cpu_baseline:
-        out["cpu_baseline"] = cpu_train_baseline(B, FD)
-    del trainer, model
+        try:
+            out["cpu_baseline"] = cpu_train_baseline_cfg2(host_threads())
+        except Exception as exc:  # noqa: BLE001
+            out["cpu_baseline"] = {"error": repr(exc)[:200]}
+    del trainer, model, dev
     torch.cuda.empty_cache()
     return out
 
 
-def run_ml1m_block(device, steps: int, warmup: int, cpu_baseline: bool):
+def _dp_first_step_check(ctx: Ctx, dp_loss, batch, FD, NU, NI, edim, hidden, E, sparse_tables):
+    """The data-parallel loss of step 1 is (a) identical on every rank and (b) what ONE process computes on the
+    concatenated global batch: rank 0 replays the forward of step 1 without data parallelism on an identically
+    initialised model (same seed) and compares."""
+    import torch.distributed as dist
+    world, rank, device = ctx.world, ctx.rank, ctx.device
+    losses = [torch.empty_like(dp_loss.reshape(1)) for _ in range(world)]
+    dist.all_gather(losses, dp_loss.detach().reshape(1))
+    same = all(torch.equal(losses[0], x) for x in losses)
+    gathered = {}
+    for k in ("uf", "pf", "uid", "iid"):
+        parts = [torch.empty_like(batch[k]) for _ in range(world)]
+        dist.all_gather(parts, batch[k])
+        gathered[k] = torch.cat(parts)
+    rel = None
+    if rank == 0:
+        ref = _make_cfg_model(device, FD, NU, NI, edim, hidden, E, sparse_tables).to(device)
+        ref.train()
+        for t in (ref.user_tower, ref.item_tower):
+            t.dropout_rate = 0.0
+        with torch.no_grad():
+            u = ref.get_user_embeddings({"numerical": gathered["uf"], "categorical": {"user_id": gathered["uid"]}})
+            p = ref.get_item_embeddings({"numerical": gathered["pf"], "categorical": {"item_id": gathered["iid"]}})
+            single = ref.in_batch_negative_loss(u, p)
+        rel = abs(float(single.item()) - float(dp_loss.item())) / abs(float(single.item()))
+        del ref
+    torch.cuda.empty_cache()
+    return {"loss_identical_on_all_ranks": bool(same), "rel_diff_vs_single_process_forward": rel,
+            "ok": bool(same and (rel is None or rel <= 1e-6)),
+            "note": "step 1 (dropout off: masks are per replica by design) replayed by ONE process on rank 0 over the "
+                    "all-gathered global batch with an identically initialised model (training-mode BatchNorm)"}
+
+
+def run_ml1m_block(ctx: Ctx, steps: int, warmup: int, cpu_baseline: bool):
     """BASELINE config 1 shape (MovieLens-1M: 6,040 users x 3 features, 3,416 movies x 20 features, 799,688 training
     interactions, batch 1024, 16 sampled negatives, E=128, hidden [256,128], loss 0.7 explicit + 0.3 in-batch) on a
     synthetic interaction table, fed by the device-side feed (b200rec.feed: negative sampling + feature gathers on the
@@ -260,6 +497,7 @@ def run_ml1m_block(device, steps: int, warmup: int, cpu_baseline: bool):
     from b200rec.feed import DeviceInteractionFeed
     from b200rec.trainer import TwoTowerTrainer
     from b200rec.training_utils import create_two_tower_model_for_training
+    device = ctx.device
     NU, NM, NI, B, R = 6040, 3416, 799_688, 1024, 16
     rng = np.random.default_rng(SEED)
     u = rng.integers(0, NU, NI)
@@ -280,72 +518,247 @@ def run_ml1m_block(device, steps: int, warmup: int, cpu_baseline: bool):
     model.train()
     trainer.enable_cuda_graph(warm_steps=2)
     it = iter(feed)
-    nxt = lambda: next(it)
     for _ in range(max(warmup, 3)):
-        b = nxt()
+        b = next(it)
         trainer.train_step(b["user_features"], b["pos_item_features"], b["neg_item_features"])
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
-        b = nxt()
+        b = next(it)
         loss = trainer.train_step(b["user_features"], b["pos_item_features"], b["neg_item_features"])
     float(loss.item())
     dt = (time.perf_counter() - t0) / steps
     feed.check()
+    macs_u = 3 * 256 + 256 * 128 + 128 * 128
+    macs_i = 20 * 256 + 256 * 128 + 128 * 128
+    flops = 6.0 * (B * macs_u + (B + B * R) * macs_i) + 6.0 * B * B * 128 + 6.0 * B * (R + 1) * 128
+    params = sum(p.numel() for p in model.parameters())
+    bytes_ = 28.0 * params + 4.0 * (B * (3 + 256 + 128 + 128) + (B + B * R) * (20 + 256 + 128 + 128)) * 2 * 3
     out = {"metric": "train samples/s", "value": B / dt, "unit": "samples/s", "ms_per_step": dt * 1e3,
            "epoch_s_at_this_rate": NI / B * dt,
            "config": {"workload": "MovieLens-1M shape (synthetic interactions): batch 1024 x 16 sampled negatives, E=128, "
                                   "hidden [256,128], 0.7 explicit + 0.3 in-batch loss; batches built on the GPU by "
                                   "b200rec.feed (negative sampling + feature gathers), step replayed as one CUDA graph, wall clock "
-                                  "including the feed"}}
+                                  "including the feed"},
+           "roofline": _train_roofline(dt * 1e3, flops, bytes_, "5.97 GFLOP / 28 MB per step: microseconds of work, the "
+                                                                   "step is bound by launch latency of its kernel chain")}
     if cpu_baseline:
         from oracle.feed import make_batch
         np.random.seed(SEED)
         t0 = time.perf_counter()
         make_batch(list(range(512)), u, m, lab, uf, mf, pos, NM, R, True)
         per_sample = (time.perf_counter() - t0) / 512
-        out["cpu_baseline"] = {"value": 1.0 / per_sample, "unit": "samples/s", "cores": 1, "kind": "port",
-                               "sample": "512 samples of oracle/feed.py (sample_negative_items + __getitem__ + collate_fn "
-                                         "restated): the reference's FEED alone, one DataLoader worker"}
+        out["cpu_baseline_feed"] = {"value": 1.0 / per_sample, "unit": "samples/s", "cores": 1, "kind": "port",
+                                    "sample": "512 samples of oracle/feed.py (sample_negative_items + __getitem__ + "
+                                              "collate_fn restated): the reference's FEED alone, one DataLoader worker"}
+        try:
+            out["cpu_baseline"] = cpu_train_baseline_ml1m(host_threads())
+        except Exception as exc:  # noqa: BLE001
+            out["cpu_baseline"] = {"error": repr(exc)[:200]}
     del trainer, model, feed
     torch.cuda.empty_cache()
     return out
 
 
-def cpu_train_baseline(B: int, FD: int):
-    """Oracle port of the step's forward + backward (numpy fp32; no optimiser) at the config-2 shape, tables reduced
-    to the touched rows' width (the gather itself is a memcpy on CPU)."""
-    from oracle.two_tower import TowerOracle, in_batch_loss
-    rng = np.random.default_rng(SEED)
+# ------------------------------------------------------------------------------------------------ config 1: epoch + eval
+def synth_ratings(path: str, users_dat: str, movies_dat: str, n: int = 1_000_209, seed: int = SEED) -> None:
+    """ratings.dat is not shipped with the reference (.MISSING_LARGE_BLOBS): synthesise `UserID::MovieID::Rating::
+    Timestamp` rows over the real user / movie ids: Zipf-popular movies, ratings 1-5 skewed to
+    3-5, timestamps 2000-04-25 .. 2003-02-28, fixed seed.  Every user gets >= 20 interactions as in ML-1M."""
+    rng = np.random.default_rng(seed)
+    uids = np.array([int(l.split("::")[0]) for l in open(users_dat, encoding="latin-1") if l.strip()])
+    mids = np.array([int(l.split("::")[0]) for l in open(movies_dat, encoding="latin-1") if l.strip()])
+    pop = 1.0 / np.arange(1, len(mids) + 1) ** 0.9
+    pop /= pop.sum()
+    per_user = np.maximum(20, rng.lognormal(4.6, 0.9, len(uids)).astype(np.int64))
+    per_user = np.minimum(per_user, len(mids) // 2)
+    per_user = (per_user * (n / per_user.sum())).astype(np.int64).clip(20, len(mids) // 2)
+    perm = rng.permutation(len(mids))
+    rows = []
+    for u, c in zip(uids, per_user):
+        m = perm[rng.choice(len(mids), size=int(c), replace=False, p=pop)]
+        r = rng.choice([1, 2, 3, 4, 5], size=int(c), p=[0.06, 0.11, 0.26, 0.35, 0.22])
+        t = rng.integers(956703932, 1046454590, size=int(c))
+        rows.append(np.stack([np.full(int(c), u), mids[m], r, t], axis=1))
+    allr = np.concatenate(rows)
+    with open(path, "w") as fh:
+        fh.write("\n".join("::".join(map(str, row)) for row in allr.tolist()))
+        fh.write("\n")
 
-    def params(inp):
-        p = {}
-        dims = [inp, 128, 64]
-        for l in range(2):
-            p[f"mlp.{4 * l}.weight"] = rng.standard_normal((dims[l + 1], dims[l])).astype(np.float32) * 0.1
-            p[f"mlp.{4 * l}.bias"] = np.zeros(dims[l + 1], np.float32)
-            p[f"mlp.{4 * l + 2}.weight"] = np.ones(dims[l + 1], np.float32)
-            p[f"mlp.{4 * l + 2}.bias"] = np.zeros(dims[l + 1], np.float32)
-            p[f"mlp.{4 * l + 2}.running_mean"] = np.zeros(dims[l + 1], np.float32)
-            p[f"mlp.{4 * l + 2}.running_var"] = np.ones(dims[l + 1], np.float32)
-        p["mlp.8.weight"] = rng.standard_normal((64, 64)).astype(np.float32) * 0.1
-        p["mlp.8.bias"] = np.zeros(64, np.float32)
-        return p
 
-    ut, it = TowerOracle(params(FD + 64), 2, dtype=np.float32), TowerOracle(params(FD + 64), 2, dtype=np.float32)
-    xu = rng.standard_normal((B, FD + 64)).astype(np.float32)
-    xi = rng.standard_normal((B, FD + 64)).astype(np.float32)
-    steps = 3
+def run_epoch_block(ctx: Ctx):
+    """BASELINE config 1 for real: MovieLens-1M (real users.dat / movies.dat, synthesised ratings.dat) through the
+    REFERENCE's own loader once on the host, then one full training epoch on the GPU (device feed + CUDA-graph step)
+    and the exact top-100 evaluation of every test user on the GPU (item tower -> masked fused top-K -> device
+    metrics), checked against the oracle pipeline (numpy towers + np.dot/argsort twin + restated Evaluator) on the same
+    weights.  Needs the staged reference loader (baseline/_ref); skipped otherwise."""
+    mods = _reference_modules()
+    if mods is None:
+        return {"skipped": "reference loader not staged (baseline/_ref missing)"}
+    import importlib
+    import tempfile
+    from b200rec.evaluation import Evaluator
+    from b200rec.feed import DeviceInteractionFeed
+    from b200rec.trainer import TwoTowerTrainer
+    from b200rec.training_utils import create_two_tower_model_for_training
+    ml = importlib.import_module("src.data.movielens")
+    ds_mod = importlib.import_module("src.training.datasets.movielens")
+    ref_root = os.path.join(ROOT, "baseline", "_ref", "ml-1m")
+    t_host = time.perf_counter()
+    with tempfile.TemporaryDirectory() as tmp:
+        for f in ("users.dat", "movies.dat"):
+            os.symlink(os.path.join(ref_root, f), os.path.join(tmp, f))
+        real = os.path.join(ROOT, "ml-1m", "ratings.dat")
+        if os.path.exists(real):
+            os.symlink(real, os.path.join(tmp, "ratings.dat"))
+            ratings_src = "ml-1m/ratings.dat"
+        else:
+            synth_ratings(os.path.join(tmp, "ratings.dat"), os.path.join(tmp, "users.dat"), os.path.join(tmp, "movies.dat"))
+            ratings_src = "synthesised (SURVEY 8c)"
+        data = ml.MovieLensLoader(tmp).load_and_preprocess(split_method="time", val_ratio=0.1, test_ratio=0.1,
+                                                           implicit_threshold=4.0, min_user_interactions=5,
+                                                           min_item_interactions=5)
+    train_ds = ds_mod.MovieLensDataset(data.train_interactions, data.users, data.movies, num_negatives=16, is_training=True)
+    host_s = time.perf_counter() - t_host
+    device = ctx.device
+    torch.manual_seed(SEED)
+    uf, mf = train_ds.user_features, train_ds.movie_features
+    model = create_two_tower_model_for_training(uf.shape[1], mf.shape[1], {"embedding_dim": 128, "hidden_layers": [256, 128],
+                                                                            "dropout_rate": 0.2, "temperature": 0.05})
+    feed = DeviceInteractionFeed.from_dataset(train_ds, batch_size=1024, shuffle=True, seed=SEED, device=str(device))
+    trainer = TwoTowerTrainer(model, feed, [], {"learning_rate": 1e-3, "weight_decay": 1e-5,
+                                                "checkpoint_dir": "/tmp/b200rec_bench_ckpt"}, device=str(device))
+    trainer.enable_cuda_graph(warm_steps=2)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        u, i = ut.forward(xu, training=True), it.forward(xi, training=True)
-        _, du, di = in_batch_loss(u, i, 0.05, want_grad=True)
-        ut.backward(du)
-        it.backward(di)
-    dt = (time.perf_counter() - t0) / steps
-    return {"value": B / dt, "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
-            "sample": f"{steps} steps of oracle/two_tower.py forward+backward+in-batch loss (numpy fp32, no optimiser) "
-                      f"at batch {B}"}
+    loss = trainer.train_epoch(1)
+    torch.cuda.synchronize()
+    epoch_s = time.perf_counter() - t0
+    feed.check()
+    # evaluation protocol of scripts/evaluate_model.py:162-234 / Evaluator.evaluate_model
+    test = data.test_interactions
+    pos_test = test[test["label"] == 1] if "label" in test else test
+    gt = {int(u): set(map(int, g)) for u, g in pos_test.groupby("user_idx")["movie_idx"]}
+    tr = data.train_interactions
+    train_items = {int(u): set(map(int, g)) for u, g in tr.groupby("user_idx")["movie_idx"]}
+    test_users = sorted(gt.keys())
+    n_items = mf.shape[0]
+    ks = [5, 10, 20, 50, 100]
+    ev = Evaluator(k_values=ks, num_items=n_items)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    got = ev.evaluate_model(model, test_users, gt, train_items, uf, mf, list(range(n_items)), batch_size=1024, device=str(device))
+    torch.cuda.synchronize()
+    eval_s = time.perf_counter() - t0
+    # oracle pipeline on the same weights (numpy towers -> np.dot + -inf mask + argsort -> restated Evaluator)
+    from oracle import metrics as OM
+    from oracle.flat_ip import eval_twin_topk
+    from oracle.two_tower import TowerOracle
+    t0 = time.perf_counter()
+    sd = lambda t: {k: v.detach().cpu().numpy() for k, v in t.state_dict().items()}
+    ue = TowerOracle(sd(model.user_tower), 2, dtype=np.float32).forward(uf[test_users], training=False)
+    ie = TowerOracle(sd(model.item_tower), 2, dtype=np.float32).forward(mf, training=False)
+    recs = eval_twin_topk(ue, ie, {u: sorted(v) for u, v in train_items.items()}, test_users, 100)
+    want, _ = OM.evaluate({u: recs[u] for u in test_users}, gt, ks, n_items)
+    cpu_eval_s = time.perf_counter() - t0
+    rows, _ = ev.recommend(model, test_users, train_items, uf, mf, 100, 1024, str(device))
+    rows = rows.cpu().numpy()
+    exact, _ = OM.evaluate({u: rows[j].tolist() for j, u in enumerate(test_users)}, gt, ks, n_items)
+    gd = got.to_dict()
+    lists_equal = float(np.mean([rows[j].tolist() == recs[u] for j, u in enumerate(test_users)]))
+    return {"metric": "train samples/s", "value": len(train_ds) / epoch_s, "unit": "samples/s", "epoch_seconds": epoch_s,
+            "train_rows": len(train_ds), "steps": len(feed), "epoch_mean_loss": loss, "ratings": ratings_src,
+            "host_preprocessing_seconds": host_s, "eval_seconds": eval_s, "eval_users": len(test_users), "n_items": n_items,
+            "metrics": {k: gd[k] for k in ("recall@10", "recall@100", "ndcg@10", "ndcg@100", "hit_rate@10", "mrr", "coverage")},
+            "metrics_identical_to_oracle_on_same_lists": bool(all(gd[k] == v for k, v in exact.items())),
+            "max_abs_metric_diff_vs_cpu_pipeline": float(max(abs(gd[k] - v) for k, v in want.items())),
+            "fraction_of_users_with_identical_top100_list": lists_equal,
+            "cpu_eval_seconds": cpu_eval_s,
+            "config": {"workload": "MovieLens-1M two-tower epoch (reference loader on the host once, device feed + CUDA-graph "
+                                   "step) + exact top-100 eval of every test user with train-item masking on the GPU"}}
+
+
+# ------------------------------------------------------------------------------------------------ config 5: serving loop
+def run_serve_block(ctx: Ctx, steps: int, warmup: int):
+    """BASELINE config 5: user-tower forward on Q users -> 100 M-item x 64-dim bf16 catalogue (row-sharded over the N
+    GPUs, 12.8 GB total) -> sharded exact top-1000 -> merge.  Q = 1024 is the headline; a Q sweep shows the HBM-bound
+    regime (one catalogue scan serves 1 or 128 queries) that request batching (b200rec.serving.RetrievalBatcher) exploits."""
+    from b200rec.dist import ShardedFlatIndex, shard_bounds
+    from b200rec.retrieval import FlatIPDeviceIndex
+    from b200rec.training_utils import create_two_tower_model_for_training
+    device, world, rank = ctx.device, ctx.world, ctx.rank
+    NI5, D5, K5, FU = 100_000_000, 64, 1000, 16
+    lo, hi = shard_bounds(NI5, world, rank)
+    index = FlatIPDeviceIndex(D5, storage="bf16", device=device, row_offset=lo)
+    index.add_bf16_rows(make_catalogue_shard(lo, hi, device, NI5, D5, SEED + 5))
+    sharded = ShardedFlatIndex.from_device_index(index)
+    torch.manual_seed(SEED)
+    with torch.device(device):
+        model = create_two_tower_model_for_training(FU, FU, {"embedding_dim": D5, "hidden_layers": [128, 64],
+                                                              "dropout_rate": 0.2, "temperature": 0.05})
+    model.eval()
+    pk = _peaks()
+    sweep = {}
+    out = None
+    for Q in (1, 16, 128, 1024):
+        feats_host = torch.randn(Q, FU, generator=torch.Generator().manual_seed(SEED + Q)).pin_memory()
+        feats = feats_host.to(device)
+
+        def step(i, feats=feats):
+            with torch.no_grad():
+                emb = model.get_user_embeddings({"numerical": feats, "categorical": {}})
+                q_op = index.prepare_queries(emb, normalize=False)
+                return sharded.search(q_op, K5)
+
+        n_steps = max(3, steps // 2) if Q < 1024 else steps
+        ms = timed(ctx, step, n_steps, max(warmup, 3))
+        n_local = hi - lo
+        flops = 2.0 * Q * n_local * D5
+        bytes_ = n_local * D5 * 2.0 + Q * D5 * 2 + Q * K5 * 12
+        t_hbm, t_tc = bytes_ / (pk["hbm_gbs"] * 1e9) * 1e3, flops / (pk["tflops"] * 1e12) * 1e3
+        bound = "hbm" if t_hbm >= t_tc else "tensor"
+        ach = bytes_ / (ms * 1e-3) / 1e9 if bound == "hbm" else flops / (ms * 1e-3) / 1e12
+        peak = pk["hbm_gbs"] if bound == "hbm" else pk["tflops"]
+        sweep[str(Q)] = {"ms_per_batch": ms, "qps": Q / ms * 1e3, "bound": bound, "frac": ach / peak,
+                         "hbm_floor_ms": t_hbm, "tensor_floor_ms": t_tc}
+        if Q == 1024:
+            # end to end: host user features -> tower -> sharded search -> host results (this replica's share at N > 1)
+            lo_q, hi_q = shard_bounds(Q, world, rank) if world > 1 else (0, Q)
+            d_host = torch.empty((hi_q - lo_q, K5), dtype=torch.float32).pin_memory()
+            i_host = torch.empty((hi_q - lo_q, K5), dtype=torch.int64).pin_memory()
+
+            def e2e_once():
+                f = feats_host.to(device, non_blocking=True)
+                with torch.no_grad():
+                    emb = model.get_user_embeddings({"numerical": f, "categorical": {}})
+                    ds, ii = sharded.search(index.prepare_queries(emb, normalize=False), K5)
+                d_host.copy_(ds[lo_q:hi_q], non_blocking=True)
+                i_host.copy_(ii[lo_q:hi_q], non_blocking=True)
+                torch.cuda.synchronize()
+
+            for _ in range(3):
+                e2e_once()
+            ctx.barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                e2e_once()
+            ctx.barrier()
+            e2e_ms = ctx.max_over_ranks((time.perf_counter() - t0) / steps * 1e3)[0]
+            out = {"metric": "top-1000 exact-IP QPS over 100M items (user tower + sharded retrieval)",
+                   "value": Q / ms * 1e3, "unit": "queries/s", "ms_per_step": ms, "latency_ms_e2e": e2e_ms,
+                   "n_gpus": world, "scaling": "strong", "dtype": "bf16",
+                   "config": {"workload": f"user-tower forward ({FU} features -> [128,64] -> {D5}) + exact IP top-{K5} over "
+                                          f"{NI5} items x {D5}-dim bf16, query batch {Q}, catalogue row-sharded over {world} GPU(s)"},
+                   "e2e": {"value": Q / e2e_ms * 1e3, "unit": "queries/s", "h2d_bytes_per_step": Q * FU * 4 * world,
+                           "d2h_bytes_per_step": Q * K5 * 12},
+                   "roofline": {"bound": bound, "achieved": ach, "peak": peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+                                "frac": ach / peak, "traffic": None, "scope": "whole serving step (tower + sample + search + merge)",
+                                "algorithmic_bytes": bytes_, "flops_per_step": flops, "hbm_floor_ms": t_hbm,
+                                "tensor_floor_ms": t_tc, "peak_source": pk["source"]}}
+    out["q_sweep"] = sweep
+    del sharded, index, model
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ main arm
@@ -355,8 +768,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-train", action="store_true", help="skip the config-2 training block")
+    ap.add_argument("--no-train", action="store_true", help="retrieval only (skip every extra block)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--blocks", default="train,ml1m,epoch,cfg4,serve", help="extra blocks to run (comma separated)")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -369,7 +783,6 @@ def main():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback for the b200rec kernels")
     import torch.distributed as dist
     from b200rec import _native as N
-    from b200rec import kernels as K
     from b200rec.dist import ShardedFlatIndex, shard_bounds
     from b200rec.retrieval import FlatIPDeviceIndex
 
@@ -377,27 +790,26 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    ctx = Ctx(device, world, rank)
     warmup = max(args.warmup, 3)
     steps = max(args.steps, 1)
+    blocks = set() if args.no_train else {b for b in args.blocks.split(",") if b}
+    want_cpu = (not args.no_cpu_baseline) and rank == 0 and world == 1
 
     lo, hi = shard_bounds(N_ITEMS, world, rank)
     index = FlatIPDeviceIndex(DIM, storage="bf16", device=device, row_offset=lo)
     index.add_bf16_rows(make_catalogue_shard(lo, hi, device))
     sharded = ShardedFlatIndex.from_device_index(index)
-    q_host = make_queries_host().pin_memory()
-    q_op = index.prepare_queries(q_host, normalize=False)  # resident bf16 operand for the `value` region
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    q_host = make_queries_host()
+    q_np = q_host.numpy()
+    q_op = index.prepare_queries(q_host.pin_memory(), normalize=False)  # resident bf16 operand for the `value` region
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()  # nvidia-smi needs ~100 ms to produce its first line: start it before the warm-up
     for _ in range(warmup):
         s, i = sharded.search(q_op, TOPK)
-    barrier()
+    ctx.barrier()
     n_before = len(sampler.rows)
     l0 = N.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -405,14 +817,15 @@ def main():
     for _ in range(steps):
         s, i = sharded.search(q_op, TOPK)
     e1.record()
-    barrier()
+    ctx.barrier()
     ms = e0.elapsed_time(e1) / steps
     launches = N.launch_count() - l0
     if rank == 0:
         sampler.rows = sampler.rows[n_before:] or sampler.rows[-3:]
     clocks = sampler.stop() if rank == 0 else None
+    parity = parity_check(ctx, index, q_host, s, i)
 
-    # dominant kernel alone (CUDA events recorded by the library around stream_scores_kernel<topk> on its stream)
+    # dominant kernel alone (CUDA events recorded by the library around the fused kernel on its launching stream)
     import ctypes
     lib = N.lib()
     lib.b200rec_debug_topk_kernel_timing.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
@@ -426,57 +839,78 @@ def main():
     lib.b200rec_debug_topk_kernel_timing(0, None)
     kernel_ms = float(np.mean(kms))
 
-    # end to end through the public API: host fp32 queries -> (D, I) on the host, copies inside the timed region
-    d_host = torch.empty((N_QUERIES, TOPK), dtype=torch.float32).pin_memory()
-    i_host = torch.empty((N_QUERIES, TOPK), dtype=torch.int64).pin_memory()
+    # end to end through the plugin call: HOST numpy queries -> (D, I) numpy; faiss.normalize_L2 + operand cast on the
+    # device; at N > 1 every replica returns its share of the answers (full result on every replica in e2e_sync_call)
+    def run_stream(n):
+        last = None
+        gen = (sharded.search_stream((q_np for _ in range(n)), TOPK, normalize=True, share_results=True) if world > 1
+               else index.search_stream((q_np for _ in range(n)), TOPK, normalize=True))
+        for last in gen:
+            pass
+        return last
 
-    def e2e_once():
-        qo = index.prepare_queries(q_host, normalize=True)   # H2D copy + faiss.normalize_L2 + operand cast
-        ds, ii = sharded.search(qo, TOPK)
-        d_host.copy_(ds, non_blocking=True)
-        i_host.copy_(ii, non_blocking=True)
-        torch.cuda.synchronize()
-
-    for _ in range(3):
-        e2e_once()
-    barrier()
+    run_stream(3)
+    ctx.barrier()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        e2e_once()
-    barrier()
+    d_np, i_np = run_stream(steps)
+    ctx.barrier()
     e2e_ms = (time.perf_counter() - t0) / steps * 1e3
+    lo_q, hi_q = shard_bounds(N_QUERIES, world, rank) if world > 1 else (0, N_QUERIES)
+    e2e_same = bool(np.array_equal(i_np, i[lo_q:hi_q].cpu().numpy()))
 
-    t = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, kernel_ms = [float(x) for x in t.tolist()]
+    def sync_call():
+        return sharded.search_numpy(q_np, TOPK, normalize=True) if world > 1 else index.search(q_np, TOPK, normalize=True)
 
-    train = None
-    cpu = None
-    del sharded, index, q_op
+    for _ in range(2):
+        sync_call()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(3, steps // 2)):
+        sync_call()
+    ctx.barrier()
+    sync_ms = (time.perf_counter() - t0) / max(3, steps // 2) * 1e3
+    ms, e2e_ms, kernel_ms, sync_ms = ctx.max_over_ranks(ms, e2e_ms, kernel_ms, sync_ms)
+
+    del sharded, index, q_op, s, i
     torch.cuda.empty_cache()
-    if not args.no_train:
-        train = run_train_block(device, min(max(steps, 10), 30), warmup, (not args.no_cpu_baseline) and rank == 0 and world == 1,
-                                world, rank)
-    train_ml1m = None
-    if rank == 0 and world == 1 and not args.no_train:
-        train_ml1m = run_ml1m_block(device, 200, 20, not args.no_cpu_baseline)
-    if rank == 0 and world == 1:
-        if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            rows, queries = 1_000_000, 2048
-            v, dt = cpu_retrieval_baseline(rows, queries, threads)
-            cpu = {"value": v, "unit": "queries/s", "cores": threads, "kind": "port",
-                   "sample": f"{queries} queries x {rows} rows fp32 ({dt:.1f} s), oracle/flat_ip.py numpy sgemm + exact "
-                             f"select (faiss-cpu restated), QPS scaled linearly to {N_ITEMS} rows"}
+    extra = {}
+    bsteps = min(max(steps, 10), 30)
+    if "train" in blocks:
+        extra["train"] = run_table_train_block(ctx, bsteps, warmup, want_cpu, name="config 2 (synthetic)", NU=1_000_000,
+                                               NI=100_000, edim=64, hidden=[128, 64], E=64, sparse_tables=False,
+                                               check_dp=True)
+    if "ml1m" in blocks and rank == 0 and world == 1:
+        extra["train_ml1m"] = run_ml1m_block(ctx, 200, 20, want_cpu)
+    if "epoch" in blocks and rank == 0 and world == 1:
+        try:
+            extra["epoch_ml1m"] = run_epoch_block(ctx)
+        except Exception as exc:  # noqa: BLE001 - an optional block must not cost the headline line
+            extra["epoch_ml1m"] = {"error": repr(exc)[:300]}
+    if "cfg4" in blocks:
+        extra["train_cfg4"] = run_table_train_block(ctx, bsteps, warmup, False, name="config 4 (synthetic)", NU=50_000_000,
+                                                    NI=5_000_000, edim=128, hidden=[256, 128], E=128, sparse_tables=True,
+                                                    check_dp=False)
+    if "serve" in blocks:
+        extra["serve"] = run_serve_block(ctx, bsteps, warmup)
+    cpu = None
+    if want_cpu:
+        threads = host_threads()
+        rows, queries = 1_000_000, 1024
+        v, dt = cpu_retrieval_baseline(rows, queries, threads)
+        cpu = {"value": v, "unit": "queries/s", "cores": threads, "kind": "port",
+               "sample": f"{queries} queries x {rows} rows fp32 ({dt:.1f} s) on {threads} threads, oracle/flat_ip.search_blocked "
+                         f"(faiss-cpu's blocked sgemm + k-select layout restated; faiss-cpu is not installable offline), "
+                         f"QPS scaled linearly to {N_ITEMS} rows"}
     if rank == 0:
         peaks = _peaks()
         traffic = None  # DRAM bytes of one launch of the dominant kernel, from the committed ncu --set full capture
-        tpath = os.path.join(ROOT, "profiles", "r01_topk_traffic.json")
-        if world == 1 and os.path.exists(tpath):
-            with open(tpath) as fh:
-                tj = json.load(fh)
-            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        for name in ("r02_topk_traffic.json", "r01_topk_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", name)
+            if world == 1 and os.path.exists(tpath):
+                with open(tpath) as fh:
+                    tj = json.load(fh)
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                break
         n_local = (N_ITEMS + world - 1) // world
         flops = 2.0 * N_QUERIES * n_local * DIM
         achieved = flops / (kernel_ms * 1e-3) / 1e12
@@ -487,16 +921,23 @@ def main():
                                        f"catalogue row-sharded over {world} GPU(s)",
                            "l2": "catalogue shard (>= 320 MB) exceeds L2 between iterations", "seed": SEED},
                 "e2e": {"value": N_QUERIES / e2e_ms * 1e3, "unit": "queries/s",
-                        "h2d_bytes_per_step": N_QUERIES * DIM * 4, "d2h_bytes_per_step": N_QUERIES * TOPK * 12},
-                "gpu_launches": int(launches),
+                        "h2d_bytes_per_step": N_QUERIES * DIM * 4 * world, "d2h_bytes_per_step": N_QUERIES * TOPK * 12,
+                        "api": "index.search_stream(numpy query batches, k) -> (D, I) numpy per batch (pinned double "
+                               "buffering inside the call)", "results_equal_device_path": e2e_same},
+                "e2e_sync_call": {"value": N_QUERIES / sync_ms * 1e3, "unit": "queries/s",
+                                  "api": "index.search(numpy queries, k) -> (D, I) numpy, one blocking call per step"},
+                "gpu_launches": int(launches), "parity_checked": parity,
                 "clocks": clocks,
-                "roofline": {"kernel": "stream_scores_kernel<topk> (scoring GEMM fused with top-K select)",
+                "roofline": {"kernel": "stream_scores2_kernel<2,TopkEpi> (scoring GEMM fused with top-K select)",
                              "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                              "frac": achieved / peaks["tflops"], "traffic": traffic, "kernel_ms": kernel_ms,
+                             "frac_of_burst_peak": achieved / peaks["tflops_burst"],
+                             "step_frac": flops / (ms * 1e-3) / 1e12 / peaks["tflops"],
                              "algorithmic_bytes": n_local * DIM * 2 + N_QUERIES * DIM * 2 + N_QUERIES * TOPK * 12,
                              "flops_per_launch": flops, "peak_source": peaks["source"],
                              "hbm_floor_ms": n_local * DIM * 2 / (peaks["hbm_gbs"] * 1e9) * 1e3},
-                "cpu_baseline": cpu, "train": train, "train_ml1m": train_ml1m}
+                "cpu_baseline": cpu}
+        line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -133,6 +133,36 @@ class IndexFlatIP:
         return D, I
 
 
+def search_blocked(xb, q, k: int, threads: int = 0, db_block: int = 1 << 17, q_block: int = 1024):
+    """The same exact search laid out the way faiss-cpu runs IndexFlatIP for nq >= 20 (exhaustive_inner_product_blas:
+    sgemm over (query block x database block) + a k-selection per block folded into the running result), on all host
+    cores: torch-CPU (MKL) sgemm, torch.topk per block, running merge by a topk over [k running | k new].  This is the
+    CPU BASELINE bench.py times (`cpu_baseline`, `--impl reference`); IndexFlatIP.search above is the readable checker
+    with the deterministic tie order (this one leaves the order among exactly equal scores to torch.topk).
+    xb / q: float32 numpy or torch CPU tensors.  Returns (D, I) numpy."""
+    import torch
+    if threads > 0:
+        torch.set_num_threads(threads)
+    xb = torch.as_tensor(xb)
+    q = torch.as_tensor(q)
+    nq, n = q.shape[0], xb.shape[0]
+    D = torch.full((nq, k), -float(FLT_MAX), dtype=torch.float32)
+    I = torch.full((nq, k), -1, dtype=torch.int64)
+    for q0 in range(0, nq, q_block):
+        qs = q[q0:q0 + q_block]
+        run_s, run_i = D[q0:q0 + q_block], I[q0:q0 + q_block]
+        for b0 in range(0, n, db_block):
+            s = qs @ xb[b0:b0 + db_block].T
+            kk = min(k, s.shape[1])
+            bs, bi = torch.topk(s, kk, dim=1)
+            cat_s = torch.cat([run_s, bs], dim=1)
+            cat_i = torch.cat([run_i, bi + b0], dim=1)
+            top_s, pos = torch.topk(cat_s, k, dim=1)
+            run_s, run_i = top_s, torch.gather(cat_i, 1, pos)
+        D[q0:q0 + q_block], I[q0:q0 + q_block] = run_s, run_i
+    return D.numpy(), I.numpy()
+
+
 class FaissIndexOracle:
     """FaissIndex Flat/cosine-or-IP wrapper semantics (reference retrieval.py:49-226)."""
 

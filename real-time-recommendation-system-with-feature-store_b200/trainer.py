@@ -230,7 +230,7 @@ class TwoTowerTrainer:
         self.val_losses: List[float] = []
 
     # ------------------------------------------------------------------ CUDA-graph replay of the hot step
-    def enable_cuda_graph(self, warm_steps: int = 2) -> None:
+    def enable_cuda_graph(self, warm_steps: int = 2) -> bool:
         """Replay the training step as ONE CUDA graph per input shape (the eager step is ~210 kernel launches and
         host-launch-bound at ~18 us each).  The first `warm_steps` calls of a shape run eagerly, the next one is
         captured; shapes that differ (the ragged last batch) keep running eagerly.  What changes from step to step lives
@@ -240,6 +240,10 @@ class TwoTowerTrainer:
         self._graphs: Dict[Any, Any] = {}
         self._graph_seen: Dict[Any, int] = {}
         self.optimizer.enable_device_state()
+        return self._graph_capturable()
+
+    def _graph_capturable(self) -> bool:
+        return getattr(self.model, "dp", None) is None
 
     def _graph_key(self, uf, pf, nf, uc, ic):
         cat = lambda d: tuple((k, tuple(v.shape), v.dtype) for k, v in (d or {}).items())
@@ -287,7 +291,7 @@ class TwoTowerTrainer:
                    neg_item_features: Optional[torch.Tensor] = None,
                    user_categorical: Optional[Dict[str, torch.Tensor]] = None,
                    item_categorical: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
-        if getattr(self, "_graphs", None) is not None and getattr(self.model, "dp", None) is None:
+        if getattr(self, "_graphs", None) is not None and self._graph_capturable():
             key = self._graph_key(user_features, pos_item_features, neg_item_features, user_categorical, item_categorical)
             seen = self._graph_seen.get(key, 0)
             self._graph_seen[key] = seen + 1

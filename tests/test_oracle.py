@@ -280,3 +280,21 @@ def test_metrics_oracle_matches_the_reference_evaluator():
         for j, k in enumerate(sorted(c["k_values"])):
             assert mat[:, 4 * j].tolist() == c["per_user_recall"][str(k)]
             assert mat[:, 4 * j + 2].tolist() == c["per_user_ndcg"][str(k)]
+
+
+def test_blocked_baseline_search_equals_the_checker_on_tie_free_data():
+    """oracle.flat_ip.search_blocked (threaded sgemm + topk, what bench.py times as the CPU baseline) returns the same
+    ids and scores as the deterministic checker IndexFlatIP.search when no two scores are equal."""
+    rng = np.random.default_rng(8)
+    cat = rng.standard_normal((5000, 24)).astype(np.float32)
+    qry = rng.standard_normal((70, 24)).astype(np.float32)
+    ix = flat_ip.IndexFlatIP(24)
+    ix.add(cat)
+    rD, rI = ix.search(qry, 30)
+    D, I = flat_ip.search_blocked(cat, qry, 30, db_block=700, q_block=32)
+    assert np.array_equal(I, rI) and np.allclose(D, rD, atol=1e-5)
+    D, I = flat_ip.search_blocked(cat[:20], qry, 30)          # k > ntotal: -1 / -FLT_MAX padding
+    assert (I[:, 20:] == -1).all() and (D[:, 20:] == -flat_ip.FLT_MAX).all()
+    small = flat_ip.IndexFlatIP(24)
+    small.add(cat[:20])
+    assert np.array_equal(I[:, :20], small.search(qry, 30)[1][:, :20])

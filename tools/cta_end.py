@@ -24,6 +24,7 @@ print("unit durations us:", " ".join(f"{x:.0f}" for x in d))
 print("per-warp (entries, appends, slow kcycles): CTA144:", " ".join(f"({ends[300+3*w]},{ends[301+3*w]},{ends[302+3*w]//1000})" for w in range(8)), " CTA145:", " ".join(f"({ends[300+3*w]},{ends[301+3*w]},{ends[302+3*w]//1000})" for w in range(8, 16)), " CTA0:", " ".join(f"({ends[300+3*w]},{ends[301+3*w]},{ends[302+3*w]//1000})" for w in range(16, 24)))
 for u in (0, 36, 72):
     os.environ["B200REC_STATS_UNIT"] = str(u)
+    lib.b200rec_debug_reload_env()
     lib.b200rec_debug_topk_stats16(buf, 1)
     KR.flat_ip_topk(cat, qry, k, workspace=ws); torch.cuda.synchronize()
     lib.b200rec_debug_topk_stats16(buf, 0)

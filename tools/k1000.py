@@ -8,6 +8,7 @@ qry = torch.nn.functional.normalize(torch.randn(Q, D, device="cuda", generator=g
 ws = torch.empty(KR.topk_workspace_bytes(N, D, Q, k), dtype=torch.uint8, device="cuda")
 for fl in os.environ.get("FLUSHES", "32,64,128,256,512").split(","):
     os.environ["B200REC_TOPK_FLUSH"] = fl
+    KR.N.lib().b200rec_debug_reload_env()   # knobs are read once per process otherwise
     for _ in range(2): KR.flat_ip_topk(cat, qry, k, workspace=ws)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

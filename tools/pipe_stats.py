@@ -29,6 +29,8 @@ def run(tag):
           f"cycles/entry {buf[8]/max(buf[9],1):.0f}, group re-reads/entry {buf[10]/max(buf[9],1):.2f}, helper busy {buf[3]/148/4/1e6:.3f} Mcyc/warp, lock-miss {buf[4]}, epi mailbox wait {buf[2]/148/8/1e6:.3f} Mcyc/warp", flush=True)
     print(f"   rare path per entry: find groups {buf[11]/max(buf[9],1):.0f} cyc, TMEM re-read {buf[12]/max(buf[9],1):.0f} cyc, tests+append {buf[13]/max(buf[9],1):.0f} cyc", flush=True)
 os.environ["B200REC_TOPK_DEBUG"] = "2"
+lib.b200rec_debug_reload_env()   # knobs are read once per process otherwise
 run("full+stats")
 os.environ["B200REC_TOPK_DEBUG"] = "1"; os.environ["B200REC_STREAM_STATS"] = "1"
+lib.b200rec_debug_reload_env()
 run("reject-all+stats")
