@@ -225,6 +225,22 @@ int b200rec_sample_negatives(const int64_t* user_of_row, int64_t B, const int64_
                              int64_t n_users, int64_t num_items, int num_negatives, uint64_t seed, uint64_t row_base,
                              int64_t* out_items, int* err_flag, void* stream);
 
+/* ---- fused in-batch loss backward (csrc/inbatch_grad.cu; flash-style: logits recomputed in TMEM, never in HBM) ----
+ * dU[b,:] = sum_j G[b,j] V[j,:],  dV[j,:] = sum_b G[b,j] U[b,:],  G = coef * (*coef_dev) * (exp(<u_b,v_j>*inv_t - lse[b])
+ * - [j == diag0 + b]) — the gradient of mean-CE(U V^T / T, arange) that autograd derives for reference
+ * src/models/two_tower.py:470-477.  u_op / v_op: split-bf16 row operands as b200rec_split_bf16 writes them
+ * ([B | NI, blocks * pad64(E)]); ut_op / vt_op: operands of the TRANSPOSES ([E, blocks * pad64(B | NI)]).
+ * *_pieces_host[p]: block index of piece p (0 = h, 1 = m, 2 = l) inside an operand row.  nprod_s = 1 | 3 | 6 piece
+ * products recompute the logits, nprod_g = 1 | 3 form the two gradient GEMMs.  E must be 64 or 128
+ * (b200rec_inbatch_grad_supported tells; callers fall back to the chunked GEMM path otherwise).  dU / dV are written
+ * completely (no accumulation), rows 16-byte aligned. */
+int b200rec_inbatch_grad_supported(int64_t B, int64_t NI, int E, int nprod_s, int nprod_g);
+int b200rec_inbatch_grad(const void* u_op, int64_t ld_u, const int32_t* u_pieces_host, const void* v_op, int64_t ld_v,
+                         const int32_t* v_pieces_host, const void* ut_op, int64_t ld_ut, const int32_t* ut_pieces_host,
+                         const void* vt_op, int64_t ld_vt, const int32_t* vt_pieces_host, int64_t B, int64_t NI, int E,
+                         int nprod_s, int nprod_g, float inv_t, const float* lse, int64_t diag0, float coef,
+                         const float* coef_dev, float* dU, int64_t ld_du, float* dV, int64_t ld_dv, void* stream);
+
 /* ---- on-device ranking metrics (csrc/eval_metrics.cu; replaces the per-user Python of Evaluator.evaluate,
  * reference src/evaluation/metrics.py:240-319 with helpers :74-231) ----
  * pred int64 [Q, K] (ld_pred): ranked item ROWS per user as the top-K kernel emits them (-1 = empty slot);

@@ -68,6 +68,9 @@ SIGNATURES = {
     "b200rec_sumsq": (_I, [_P, _I64, _P, _P]),
     "b200rec_clip_coef": (_I, [_P, _F, _P, _P, _P]),
     "b200rec_adam_dense": (_I, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _F, _P, _P]),
+    "b200rec_inbatch_grad_supported": (_I, [_I64, _I64, _I, _I, _I]),
+    "b200rec_inbatch_grad": (_I, [_P, _I64, _P, _P, _I64, _P, _P, _I64, _P, _P, _I64, _P, _I64, _I64, _I, _I, _I, _F, _P, _I64,
+                                  _F, _P, _P, _I64, _P, _I64, _P]),
     "b200rec_eval_metrics": (_I, [_P, _I64, _I, _I64, _P, _I64, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I64, _I, _P, _P]),
     "b200rec_sparse_adam": (_I, [_P, _P, _P, _I64, _I, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P, _P]),
 }

@@ -1,0 +1,444 @@
+// Fused backward of the in-batch negative loss (K3, reference src/models/two_tower.py:453-479: S = U.V^T / T,
+// CE(S, arange) — what torch autograd turns into softmax(S) - onehot followed by two GEMMs).  Flash-style: the logits
+// tile is RECOMPUTED on the tensor cores (tcgen05, accumulator in TMEM), turned into G = coef * (exp(S/T - lse) - onehot)
+// in registers, written to shared memory as a split-bf16 MMA operand and immediately contracted with the other side's
+// embeddings into the gradient accumulator (also TMEM).  Neither S, nor the probabilities, nor G ever reach HBM: the
+// kernel reads 2 x (B + NI) x E operands and writes the two [rows, E] gradients.
+//
+//   out[r, :] = sum_c G[r, c] * Y[c, :]      rows r from X (a 128-row tile resident in shared memory), columns c from Y
+//   mode U: X = U, Y = V, lse indexed by row,    one-hot at c == r + diag0          ->  dU
+//   mode V: X = V, Y = U, lse indexed by column, one-hot at c == r - diag0          ->  dV
+// Both modes run in ONE launch (work units of equal length: a 128-row X tile x a range of 64-column Y tiles; when a
+// tile's columns are split over several units — data parallel: 8192 local users x 65536 gathered items — the partial
+// gradients are combined with fp32 atomics into a pre-zeroed output).
+//
+// Per CTA: warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warp 2 TMEM allocator, warps 4-11 epilogue
+// (thread = TMEM lane x 32-column half of the 64-column logits tile).  Pipeline per Y tile t:
+//   TMA: Y operand pieces (for S) + Y^T pieces (for the gradient GEMM) -> stage t % NST            full / empty
+//   MMA: S(t+1) = X . Y(t+1)^T  (split-bf16 products h.h + m.h + h.m [+ l.h + h.l + m.m])           s_full / s_empty
+//   epi: S(t) -> G(t) pieces (h, m) in shared memory, SW128 K-major                                 g_full / g_empty
+//   MMA: OUT[t % NACC] += G(t) . Y^T(t)   (NACC accumulators: tcgen05 adds with truncation, short chains stay exact)
+// fp32-grade numerics as everywhere in this library: operands are exact sums of bf16 pieces, products of pieces are
+// exact in the tensor core, only the dropped piece products (<= 2^-17 relative for 3 products) and fp32 accumulation
+// remain.
+#include "host_util.h"
+#include "tc_common.cuh"
+#include "../../include/b200rec.h"
+
+namespace b200 {
+
+constexpr int IG_THREADS = 12 * 32;
+constexpr int IG_BM = 128;        // X rows per unit
+constexpr int IG_BN = 64;         // Y rows (logit columns) per tile
+constexpr int IG_MAX_UNIT_TILES = 128;   // <= 8192 columns per unit: bounds the accumulator chains (see NACC)
+constexpr int IG_SMEM_LIMIT = 232448;
+
+struct IgSide {
+  int rows;            // rows of X in this mode
+  int ycols;           // rows of Y (= logit columns)
+  int x_tiles;         // ceil(rows / 128)
+  int splits;          // units per X tile
+  int tiles_per_unit;  // Y tiles per unit
+  int dshift;          // one-hot column = global row + dshift
+  int lse_by_col;
+  int xp[3];           // 64-column block index of pieces h, m, l inside X's operand rows
+  int yp[3];           // same for Y's operand rows
+  int tp[2];           // block index of pieces h, m inside Y^T's operand rows (block width = ytw columns)
+  int ytw;             // pad64(ycols): columns per piece block of the transposed operand
+  float* out;
+  long long ld_out;
+};
+
+struct IgArgs {
+  IgSide side[2];
+  int units_u;         // units of mode U come first
+  int E;               // embedding width (64 or 128)
+  int KB;              // pad64(E) / 64
+  int nprod_s;         // 1, 3 or 6 piece products for the logits recompute
+  int nprod_g;         // 1 or 3 piece products for the gradient GEMM
+  int nst;             // TMA stages
+  int ng;              // G buffers
+  int nacc;            // OUT accumulators
+  int atomic_u, atomic_v;
+  float scale_log2;    // inv_t * log2(e)
+  float coef;          // inv_t / total_rows (times *coef_dev when given)
+  const float* coef_dev;
+  const float* lse;    // [B] fp32 (natural log)
+};
+
+// piece products, smallest first (they are added in this order): (x piece, y piece)
+__device__ __constant__ int IG_PROD6[6][2] = {{1, 1}, {2, 0}, {0, 2}, {1, 0}, {0, 1}, {0, 0}};
+
+__global__ void __launch_bounds__(IG_THREADS, 1)
+inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_constant__ CUtensorMap tm_uy,
+                    const __grid_constant__ CUtensorMap tm_ut, const __grid_constant__ CUtensorMap tm_vx,
+                    const __grid_constant__ CUtensorMap tm_vy, const __grid_constant__ CUtensorMap tm_vt,
+                    const IgArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mode = (int)blockIdx.x >= a.units_u ? 1 : 0;
+  const IgSide& sd = a.side[mode];
+  const int unit = mode ? (int)blockIdx.x - a.units_u : (int)blockIdx.x;
+  const int x_tile = unit / sd.splits, split = unit - x_tile * sd.splits;
+  const int y_tiles_total = (sd.ycols + IG_BN - 1) / IG_BN;
+  const int t_begin = split * sd.tiles_per_unit;
+  int T = y_tiles_total - t_begin;
+  if (T > sd.tiles_per_unit) T = sd.tiles_per_unit;
+  const CUtensorMap* tmx = mode ? &tm_vx : &tm_ux;   // X operand, box 128 rows
+  const CUtensorMap* tmy = mode ? &tm_uy : &tm_vy;   // Y operand, box 64 rows
+  const CUtensorMap* tmt = mode ? &tm_ut : &tm_vt;   // Y^T operand, box E rows
+
+  const int ps = a.nprod_s == 1 ? 1 : (a.nprod_s == 3 ? 2 : 3);   // pieces held for the logits GEMM
+  const int pg = a.nprod_g == 1 ? 1 : 2;                          // pieces of G / Y^T
+  const int x_bytes = ps * a.KB * (IG_BM * 128);
+  const int ys_bytes = ps * a.KB * (IG_BN * 128);                  // Y pieces of one stage
+  const int yt_bytes = pg * (a.E * 128);                           // Y^T pieces of one stage (one 64-column k-block)
+  const int stage_bytes = ys_bytes + yt_bytes;
+  const int g_bytes = pg * (IG_BM * 128);
+  uint8_t* x_smem = smem;
+  uint8_t* st_smem = x_smem + x_bytes;
+  uint8_t* g_smem = st_smem + a.nst * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(g_smem + a.ng * g_bytes);
+  uint64_t* full_bar = bars;            // [4]
+  uint64_t* empty_bar = bars + 4;       // [4]
+  uint64_t* s_full = bars + 8;          // [2]
+  uint64_t* s_empty = bars + 10;        // [2]
+  uint64_t* g_full = bars + 12;         // [2]
+  uint64_t* g_empty = bars + 14;        // [2]
+  uint64_t* x_full = bars + 16;
+  uint64_t* out_full = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(tmx);
+    tma_prefetch_desc(tmy);
+    tma_prefetch_desc(tmt);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&s_empty[b], 8);
+      mbar_init(&g_full[b], 8);
+      mbar_init(&g_empty[b], 1);
+    }
+    mbar_init(x_full, 1);
+    mbar_init(out_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t OUT_COL = 2 * IG_BN;   // TMEM columns: S0 [0,64) | S1 [64,128) | OUT accumulators [128, 128 + nacc*E)
+
+  if (T > 0) {
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      if (elect_one()) {
+        mbar_arrive_expect_tx(x_full, x_bytes);
+        for (int p = 0; p < ps; ++p)
+          for (int kb = 0; kb < a.KB; ++kb)
+            tma_load_2d(x_smem + (p * a.KB + kb) * (IG_BM * 128), tmx, x_full, (sd.xp[p] * a.KB + kb) * 64, x_tile * IG_BM);
+      }
+      __syncwarp();
+      for (int t = 0; t < T; ++t) {
+        const int st = t % a.nst;
+        mbar_wait(&empty_bar[st], ((t / a.nst) & 1) ^ 1);
+        if (elect_one()) {
+          uint8_t* dst = st_smem + st * stage_bytes;
+          const int yrow = (t_begin + t) * IG_BN;
+          mbar_arrive_expect_tx(&full_bar[st], stage_bytes);
+          for (int p = 0; p < ps; ++p)
+            for (int kb = 0; kb < a.KB; ++kb)
+              tma_load_2d(dst + (p * a.KB + kb) * (IG_BN * 128), tmy, &full_bar[st], (sd.yp[p] * a.KB + kb) * 64, yrow);
+          for (int p = 0; p < pg; ++p)
+            tma_load_2d(dst + ys_bytes + p * (a.E * 128), tmt, &full_bar[st], sd.tp[p] * sd.ytw + yrow, 0);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, elected lane)
+      const uint32_t idesc_s = umma_idesc_bf16(IG_BM, IG_BN);
+      const uint32_t idesc_o = umma_idesc_bf16(IG_BM, (uint32_t)a.E);
+      const uint64_t desc_base = umma_desc_k_sw128(0);
+      const uint32_t x_lo = (smem_u32(x_smem) & 0x3FFFFu) >> 4;
+      const uint32_t st_lo = (smem_u32(st_smem) & 0x3FFFFu) >> 4;
+      const uint32_t g_lo = (smem_u32(g_smem) & 0x3FFFFu) >> 4;
+      const int p0 = 6 - a.nprod_s;   // first entry of IG_PROD6 used: 6 -> 0, 3 -> 3, 1 -> 5
+      mbar_wait(x_full, 0);
+      tc_fence_after();
+      auto issue_s = [&](int t) {
+        const int st = t % a.nst, buf = t & 1;
+        mbar_wait(&full_bar[st], (t / a.nst) & 1);
+        mbar_wait(&s_empty[buf], ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d_addr = tmem_base + buf * IG_BN;
+          bool first = true;
+          for (int pr = p0; pr < 6; ++pr) {
+            const int xa = IG_PROD6[pr][0], yb = IG_PROD6[pr][1];
+            for (int kb = 0; kb < a.KB; ++kb) {
+              const uint64_t a_desc = desc_base + (x_lo + (((xa * a.KB + kb) * (IG_BM * 128)) >> 4));
+              const uint64_t b_desc = desc_base + (st_lo + ((st * stage_bytes + (yb * a.KB + kb) * (IG_BN * 128)) >> 4));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc_s, first ? 0u : 1u);
+                first = false;
+              }
+            }
+          }
+          umma_commit(&s_full[buf]);
+        }
+        __syncwarp();
+      };
+      auto issue_o = [&](int t) {
+        const int st = t % a.nst, gb = t % a.ng, acc = t % a.nacc;
+        mbar_wait(&g_full[gb], (t / a.ng) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d_addr = tmem_base + OUT_COL + acc * a.E;
+          bool first = t < a.nacc;
+          // products (G piece, Y^T piece): m.h, h.m, h.h  (or h.h alone)
+          for (int pr = (a.nprod_g == 3 ? 0 : 2); pr < 3; ++pr) {
+            const int ga = pr == 0 ? 1 : 0, yb = pr == 1 ? 1 : 0;
+            const uint64_t a_desc = desc_base + (g_lo + ((gb * g_bytes + ga * (IG_BM * 128)) >> 4));
+            const uint64_t b_desc = desc_base + (st_lo + ((st * stage_bytes + ys_bytes + yb * (a.E * 128)) >> 4));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc_o, first ? 0u : 1u);
+              first = false;
+            }
+          }
+          umma_commit(&g_empty[gb]);
+          umma_commit(&empty_bar[st]);
+          if (t == T - 1) umma_commit(out_full);
+        }
+        __syncwarp();
+      };
+      issue_s(0);
+      for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) issue_s(t + 1);   // the tensor core recomputes the next logits tile while the epilogue builds G(t)
+        issue_o(t);
+      }
+    } else if (warp >= 4) {
+      // ---------------------------------------------------------------- epilogue: logits -> G pieces -> gradient rows
+      const int ew = warp - 4;
+      const int quarter = warp & 3;          // TMEM lanes 32*quarter .. +31 are accessible to this warp
+      const int half = ew >> 2;              // 32-column half of the logits tile
+      const int row_l = quarter * 32 + lane;
+      const long long row_g = (long long)x_tile * IG_BM + row_l;
+      const bool row_ok = row_g < sd.rows;
+      const float LOG2E = 1.4426950408889634f;
+      float coef = a.coef;
+      if (a.coef_dev != nullptr) coef *= __ldg(a.coef_dev);
+      const float nl_row = (!sd.lse_by_col && row_ok) ? -__ldg(a.lse + row_g) * LOG2E : 0.f;
+      const long long hot = row_g + sd.dshift;   // global column of this row's positive (may fall outside [0, ycols))
+      for (int t = 0; t < T; ++t) {
+        const int buf = t & 1, gb = t % a.ng;
+        const long long c0 = (long long)(t_begin + t) * IG_BN + half * 32;
+        float nl_col[32];
+        if (sd.lse_by_col) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const long long c = c0 + i;
+            nl_col[i] = -__ldg(a.lse + (c < sd.ycols ? c : sd.ycols - 1)) * LOG2E;
+          }
+        }
+        mbar_wait(&s_full[buf], (t >> 1) & 1);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * IG_BN + half * 32, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[buf]);
+        float gv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const long long c = c0 + i;
+          const float nl = sd.lse_by_col ? nl_col[i] : nl_row;
+          const float p = exp2f(fmaf(__uint_as_float(v[i]), a.scale_log2, nl));
+          const float gg = coef * (p - (c == hot ? 1.f : 0.f));
+          gv[i] = (c < sd.ycols && row_ok) ? gg : 0.f;
+        }
+        // G(t) -> shared memory, K-major SW128: row r at r*128 B, 16-byte chunk j stored at position j ^ (r & 7)
+        mbar_wait(&g_empty[gb], ((t / a.ng) & 1) ^ 1);
+        uint8_t* gbase = g_smem + gb * g_bytes + row_l * 128;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t hw[4], mw[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float f0 = gv[ch * 8 + 2 * j], f1 = gv[ch * 8 + 2 * j + 1];
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+            const float2 hf = __bfloat1622float2(h2);
+            const __nv_bfloat162 m2 = __floats2bfloat162_rn(f0 - hf.x, f1 - hf.y);
+            hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            mw[j] = *reinterpret_cast<const uint32_t*>(&m2);
+          }
+          const int pos = ((half * 4 + ch) ^ (row_l & 7)) * 16;
+          *reinterpret_cast<uint4*>(gbase + pos) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          if (pg == 2) *reinterpret_cast<uint4*>(gbase + IG_BM * 128 + pos) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+        }
+        fence_proxy_async_smem();   // generic-proxy stores above must be visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&g_full[gb]);
+      }
+      // gradient rows: sum the NACC accumulators with round-to-nearest adds, store (or add when the tile was split)
+      mbar_wait(out_full, 0);
+      tc_fence_after();
+      const int ncol = a.E / 2;   // columns of OUT per thread
+      const int used = T < a.nacc ? T : a.nacc;
+      const bool atomic = mode ? a.atomic_v != 0 : a.atomic_u != 0;
+      float* orow = sd.out + row_g * sd.ld_out + half * ncol;
+#pragma unroll 1
+      for (int c = 0; c < ncol; c += 32) {
+        uint32_t o[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + OUT_COL + half * ncol + c;
+        tmem_ld_32x32(taddr, o);
+        tmem_ld_wait();
+        for (int ac = 1; ac < used; ++ac) {
+          uint32_t w[32];
+          tmem_ld_32x32(taddr + ac * a.E, w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(w[j]));
+        }
+        if (row_ok) {
+          if (atomic) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(orow + c + j, __uint_as_float(o[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(orow + c + j) = make_float4(__uint_as_float(o[j]), __uint_as_float(o[j + 1]),
+                                                                     __uint_as_float(o[j + 2]), __uint_as_float(o[j + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int ig_plan(IgArgs& a, int64_t B, int64_t NI, int E, int nprod_s, int nprod_g, int& smem_bytes) {
+  if (E != 64 && E != 128) return fail("inbatch_grad: fused path needs E = 64 or 128 (got %d)", E);
+  if (nprod_s != 1 && nprod_s != 3 && nprod_s != 6) return fail("inbatch_grad: nprod_s must be 1, 3 or 6");
+  if (nprod_g != 1 && nprod_g != 3) return fail("inbatch_grad: nprod_g must be 1 or 3");
+  a.E = E;
+  a.KB = E / 64;
+  a.nprod_s = nprod_s;
+  a.nprod_g = nprod_g;
+  const int ps = nprod_s == 1 ? 1 : (nprod_s == 3 ? 2 : 3), pg = nprod_g == 1 ? 1 : 2;
+  const int x_bytes = ps * a.KB * (IG_BM * 128), stage = ps * a.KB * (IG_BN * 128) + pg * (E * 128), g_bytes = pg * (IG_BM * 128);
+  const int fixed = 1024 + 256 + x_bytes;
+  a.ng = 2;
+  a.nst = (IG_SMEM_LIMIT - fixed - a.ng * g_bytes) / stage;
+  if (a.nst < 2) {
+    a.ng = 1;
+    a.nst = (IG_SMEM_LIMIT - fixed - a.ng * g_bytes) / stage;
+  }
+  if (a.nst < 2) return fail("inbatch_grad: E = %d with %d piece products does not fit the resident tile", E, nprod_s);
+  if (a.nst > 4) a.nst = 4;
+  a.nacc = (512 - 2 * IG_BN) / E;
+  if (a.nacc > 4) a.nacc = 4;
+  smem_bytes = fixed + a.nst * stage + a.ng * g_bytes;
+  // units of equal length: L = tiles of the shorter column range, capped (accumulator chains, tail balance)
+  const int64_t tu = (NI + IG_BN - 1) / IG_BN, tv = (B + IG_BN - 1) / IG_BN;
+  int64_t L = tu < tv ? tu : tv;
+  if (L > IG_MAX_UNIT_TILES) L = IG_MAX_UNIT_TILES;
+  if (L < 1) L = 1;
+  IgSide& su = a.side[0];
+  IgSide& sv = a.side[1];
+  su.rows = (int)B, su.ycols = (int)NI, su.x_tiles = (int)((B + IG_BM - 1) / IG_BM);
+  su.splits = (int)((tu + L - 1) / L), su.tiles_per_unit = (int)((tu + su.splits - 1) / su.splits);
+  sv.rows = (int)NI, sv.ycols = (int)B, sv.x_tiles = (int)((NI + IG_BM - 1) / IG_BM);
+  sv.splits = (int)((tv + L - 1) / L), sv.tiles_per_unit = (int)((tv + sv.splits - 1) / sv.splits);
+  a.units_u = su.x_tiles * su.splits;
+  a.atomic_u = su.splits > 1;
+  a.atomic_v = sv.splits > 1;
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200rec_inbatch_grad_supported(int64_t B, int64_t NI, int E, int nprod_s, int nprod_g) {
+  IgArgs a;
+  int smem = 0;
+  if (B <= 0 || NI <= 0 || B > INT32_MAX / 2 || NI > INT32_MAX / 2) return 0;
+  return ig_plan(a, B, NI, E, nprod_s, nprod_g, smem) == 0 ? 1 : 0;
+}
+
+extern "C" int b200rec_inbatch_grad(const void* u_op, int64_t ld_u, const int32_t* u_pieces_host, const void* v_op,
+                                    int64_t ld_v, const int32_t* v_pieces_host, const void* ut_op, int64_t ld_ut,
+                                    const int32_t* ut_pieces_host, const void* vt_op, int64_t ld_vt,
+                                    const int32_t* vt_pieces_host, int64_t B, int64_t NI, int E, int nprod_s, int nprod_g,
+                                    float inv_t, const float* lse, int64_t diag0, float coef, const float* coef_dev,
+                                    float* dU, int64_t ld_du, float* dV, int64_t ld_dv, void* stream) {
+  if (!u_op || !v_op || !ut_op || !vt_op || !lse || !dU || !dV) return fail("inbatch_grad: null pointer");
+  if (!u_pieces_host || !v_pieces_host || !ut_pieces_host || !vt_pieces_host) return fail("inbatch_grad: null piece table");
+  if (B <= 0 || NI <= 0 || B > INT32_MAX / 2 || NI > INT32_MAX / 2) return fail("inbatch_grad: bad sizes");
+  if (diag0 < 0 || diag0 + B > NI) return fail("inbatch_grad: positives [diag0, diag0 + B) must lie inside the item rows");
+  if ((ld_du & 3) || (ld_dv & 3) || (reinterpret_cast<uintptr_t>(dU) & 15) || (reinterpret_cast<uintptr_t>(dV) & 15))
+    return fail("inbatch_grad: gradient rows must be 16-byte aligned");
+  IgArgs a;
+  int smem = 0;
+  if (ig_plan(a, B, NI, E, nprod_s, nprod_g, smem)) return 1;
+  const int ps = nprod_s == 1 ? 1 : (nprod_s == 3 ? 2 : 3), pg = nprod_g == 1 ? 1 : 2;
+  const int64_t padB = (B + 63) / 64 * 64, padNI = (NI + 63) / 64 * 64;
+  IgSide& su = a.side[0];
+  IgSide& sv = a.side[1];
+  int max_u = 0, max_v = 0, max_ut = 0, max_vt = 0;
+  for (int p = 0; p < 3; ++p) {
+    su.xp[p] = sv.yp[p] = p < ps ? u_pieces_host[p] : 0;
+    su.yp[p] = sv.xp[p] = p < ps ? v_pieces_host[p] : 0;
+    if (p < ps) max_u = max_u > u_pieces_host[p] ? max_u : u_pieces_host[p], max_v = max_v > v_pieces_host[p] ? max_v : v_pieces_host[p];
+  }
+  for (int p = 0; p < 2; ++p) {
+    su.tp[p] = p < pg ? vt_pieces_host[p] : 0;   // mode U contracts with V^T
+    sv.tp[p] = p < pg ? ut_pieces_host[p] : 0;
+    if (p < pg) max_vt = max_vt > vt_pieces_host[p] ? max_vt : vt_pieces_host[p], max_ut = max_ut > ut_pieces_host[p] ? max_ut : ut_pieces_host[p];
+  }
+  if ((max_u + 1) * a.KB * 64 > ld_u || (max_v + 1) * a.KB * 64 > ld_v) return fail("inbatch_grad: piece block outside the operand row");
+  if ((max_ut + 1) * padB > ld_ut || (max_vt + 1) * padNI > ld_vt) return fail("inbatch_grad: piece block outside the transposed operand row");
+  su.ytw = (int)padNI, sv.ytw = (int)padB;
+  su.dshift = (int)diag0, sv.dshift = -(int)diag0;
+  su.lse_by_col = 0, sv.lse_by_col = 1;
+  su.out = dU, su.ld_out = ld_du, sv.out = dV, sv.ld_out = ld_dv;
+  a.scale_log2 = inv_t * 1.4426950408889634f;
+  a.coef = coef;
+  a.coef_dev = coef_dev;
+  a.lse = lse;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUtensorMap ux, uy, ut, vx, vy, vt;
+  if (make_tmap_bf16_2d(&ux, u_op, (uint64_t)B, (uint64_t)ld_u, (uint64_t)ld_u, IG_BM)) return 1;
+  if (make_tmap_bf16_2d(&uy, u_op, (uint64_t)B, (uint64_t)ld_u, (uint64_t)ld_u, IG_BN)) return 1;
+  if (make_tmap_bf16_2d(&ut, ut_op, (uint64_t)E, (uint64_t)ld_ut, (uint64_t)ld_ut, (uint32_t)E)) return 1;
+  if (make_tmap_bf16_2d(&vx, v_op, (uint64_t)NI, (uint64_t)ld_v, (uint64_t)ld_v, IG_BM)) return 1;
+  if (make_tmap_bf16_2d(&vy, v_op, (uint64_t)NI, (uint64_t)ld_v, (uint64_t)ld_v, IG_BN)) return 1;
+  if (make_tmap_bf16_2d(&vt, vt_op, (uint64_t)E, (uint64_t)ld_vt, (uint64_t)ld_vt, (uint32_t)E)) return 1;
+  if (a.atomic_u) B200_CUDA_OK(cudaMemset2DAsync(dU, sizeof(float) * (size_t)ld_du, 0, sizeof(float) * (size_t)E, (size_t)B, st));
+  if (a.atomic_v) B200_CUDA_OK(cudaMemset2DAsync(dV, sizeof(float) * (size_t)ld_dv, 0, sizeof(float) * (size_t)E, (size_t)NI, st));
+  static int smem_set = 0;
+  if (smem_set < smem) {
+    B200_CUDA_OK(cudaFuncSetAttribute(inbatch_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM_LIMIT));
+    smem_set = IG_SMEM_LIMIT;
+  }
+  const int units = a.units_u + sv.x_tiles * sv.splits;
+  inbatch_grad_kernel<<<units, IG_THREADS, smem, st>>>(ux, uy, ut, vx, vy, vt, a);
+  B200_LAUNCH_OK("inbatch_grad_kernel");
+  return 0;
+}

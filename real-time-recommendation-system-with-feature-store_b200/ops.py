@@ -335,9 +335,24 @@ class InBatchCEFn(Function):
         inv_t, terms, diag_offset, total_rows = ctx.cfg
         B, NI, E = u.shape[0], i.shape[0], u.shape[1]
         gdev = _c32(g).reshape(1)
+        gterms = _bwd_terms(terms)                                    # gradient GEMMs: 3 piece products (1 in bf16 mode)
+        # fused flash-style backward (csrc/inbatch_grad.cu): the logits never reach HBM.  The recompute uses the same
+        # number of piece products as the gradient GEMMs (3: error ~2^-17 per product before exp(), far inside the
+        # gradient tolerance; B200REC_BWD_TERMS=6 recomputes with the 6 fp32-grade products when the tile fits).
+        nps = 1 if terms == 1 else (6 if gterms == 6 else 3)
+        npg = 1 if terms == 1 else 3
+        if os.environ.get("B200REC_INBATCH_BWD") != "chunked" and K.inbatch_grad_supported(B, NI, E, nps, npg):
+            du = torch.empty_like(u)
+            di = torch.empty_like(i)
+            tt = 1 if terms == 1 else 3
+            ut = K.split_bf16(u, tt, 0, transpose=True)               # [E, tt*pad64(B)]  pieces h (, m)
+            it = K.split_bf16(i, tt, 0, transpose=True)               # [E, tt*pad64(NI)]
+            K.inbatch_grad(uo, K.PIECE_BLOCKS[(terms, 0)], io, K.PIECE_BLOCKS[(terms, 1)], ut, K.PIECE_BLOCKS[(tt, 0)],
+                           it, K.PIECE_BLOCKS[(tt, 0)], B, NI, E, nps, npg, inv_t, lse, diag_offset, inv_t / total_rows,
+                           gdev, du, di)
+            return du, di, None, None, None, None
         du = torch.empty_like(u)
         di = torch.zeros_like(i)
-        gterms = _bwd_terms(terms)                                    # gradient GEMMs; the logits recompute keeps `terms`
         it = K.split_bf16(i, gterms, 1, transpose=True)              # operand of I^T: [E, terms*kpad(NI)]
         for r0 in range(0, B, InBatchCEFn.CHUNK):
             r1 = min(B, r0 + InBatchCEFn.CHUNK)

@@ -153,6 +153,38 @@ def test_inbatch_loss_large_batch_and_backward_vs_torch():
         assert (ic.grad.cpu().double() - ir.grad).abs().max() <= gtol * ir.grad.abs().max()
 
 
+@pytest.mark.parametrize("B,G,E,rank", [(1024, 4, 64, 2), (2048, 8, 64, 7), (700, 3, 128, 1), (8192, 2, 128, 0)])
+def test_fused_inbatch_backward_with_gathered_negatives(B, G, E, rank):
+    """The data-parallel shape of the in-batch loss (two_tower.py:453-479 on the all-gathered item batch): B local users
+    against NI = G*B items, positives at rows [rank*B, rank*B + B).  Column ranges longer than one work unit are split
+    and combined with atomics (csrc/inbatch_grad.cu); fused path == chunked path == fp64 torch."""
+    import os
+    from b200rec import ops
+    torch.manual_seed(B + G)
+    NI = G * B + (37 if B == 700 else 0)
+    u = torch.nn.functional.normalize(torch.randn(B, E), dim=1)
+    v = torch.nn.functional.normalize(torch.randn(NI, E), dim=1)
+    v[rank * B:rank * B + B] = torch.nn.functional.normalize(v[rank * B:rank * B + B] + 0.7 * u, dim=1)
+    ur, vr = u.clone().double().requires_grad_(), v.clone().double().requires_grad_()
+    logits = ur @ vr.T * 20.0
+    ref = (torch.logsumexp(logits, 1) - logits[torch.arange(B), rank * B + torch.arange(B)]).sum() / (G * B)
+    (ref * 3.0).backward()
+    res = {}
+    for mode in ("fused", "chunked"):
+        os.environ["B200REC_INBATCH_BWD"] = mode
+        try:
+            uc, vc = u.clone().to(DEV).requires_grad_(), v.clone().to(DEV).requires_grad_()
+            loss = ops.InBatchCEFn.apply(uc, vc, 20.0, 6, rank * B, G * B)
+            (loss * 3.0).backward()
+        finally:
+            os.environ.pop("B200REC_INBATCH_BWD", None)
+        assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+        assert (uc.grad.cpu().double() - ur.grad).abs().max() <= 1e-4 * ur.grad.abs().max(), mode
+        assert (vc.grad.cpu().double() - vr.grad).abs().max() <= 1e-4 * vr.grad.abs().max(), mode
+        res[mode] = (uc.grad.cpu(), vc.grad.cpu())
+    assert (res["fused"][0] - res["chunked"][0]).abs().max() <= 1e-4 * ur.grad.abs().max()
+
+
 def test_bf16_mode_within_budget():
     from b200rec.training_utils import create_two_tower_model_for_training
     torch.manual_seed(3)
