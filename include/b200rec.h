@@ -29,8 +29,9 @@ int64_t b200rec_launch_count(void);
  * fp32 -> bf16 tensor-core operand [rows, terms*kpad] (zero padded to kpad columns per block).
  *   x = h + m + l exactly (h = bf16(x), m = bf16(x-h), l = bf16(x-h-m))
  *   terms 1: [h] | [h]                  plain bf16 (2e-2 budget of the bf16 mode)
- *   terms 3: [h m h] | [h h m]          (~2^-17 per product)
- *   terms 6: [h h m h l m] | [h m h l h m]   fp32-grade products (drops only m*l, l*m, l*l)
+ *   terms 3: [h m h] | [m h h]          (~2^-17 per product)
+ *   terms 6: [m l h m h h] | [m h l h m h]   fp32-grade products (drops only m*l, l*m, l*l)
+ *   (smallest piece products first: tcgen05 accumulates with truncation, late small addends would be lost)
  * side 0 = left operand pattern, side 1 = right operand pattern.  transpose != 0 reads src as [cols, rows].
  * Feeds the GEMM that replaces ATen addmm / matmul (src/models/two_tower.py:62,70,129,276,470). */
 int b200rec_split_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld_src, int transpose, void* dst,
@@ -92,6 +93,14 @@ int b200rec_topk_sample_fanout(const void* catalogue, int64_t N, int64_t ld, con
 int b200rec_topk_merge(const float* scores, const int64_t* ids, int parts, int64_t Q, int k_in, int k_out,
                        int64_t scores_part_stride, int64_t ids_part_stride, float* out_scores, int64_t* out_ids,
                        void* stream);
+/* Exact fp32 re-scoring of candidate rows (csrc/rescore.cu): scores[q, j] = <queries[q, :d], rows[ids[q, j] - row_offset, :d]>
+ * with fp32 FMAs (-FLT_MAX where ids[q, j] < 0).  The "fp32" storage of the drop-in index (reference
+ * src/serving/retrieval.py:171 on an fp32 IndexFlatIP) selects k + margin candidates with split-bf16 tensor-core
+ * products (~2^-17) and re-scores them from the fp32 rows it keeps, so scores and order are those of an fp32 CPU search;
+ * b200rec_topk_merge (parts = 1) then orders the candidates (score desc, id asc) and keeps k. */
+int b200rec_rescore_fp32(const float* queries, int64_t ld_q, const float* rows, int64_t ld_rows, int64_t n_rows,
+                         int64_t row_offset, int d, const int64_t* ids, int64_t Q, int k_in, float* scores,
+                         void* stream);
 
 /* ---------------------------------------------------------------- embedding bags (csrc/embedding.cu)
  * out[b, 0:num_cols] = numerical[b, :]; out[b, col_off[f] : +width[f]] = table_f[idx_f[b], :width[f]].

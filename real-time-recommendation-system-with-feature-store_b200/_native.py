@@ -36,6 +36,7 @@ SIGNATURES = {
     "b200rec_flat_ip_topk_fanout": (_I, [_P, _I64, _I64, _P, _I64, _I, _I64, _P, _I, _P, _P, _P, _SZ, _P]),
     "b200rec_topk_sample_fanout": (_I, [_P, _I64, _I64, _P, _I64, _I, _I, _I, _I, _P, _P, _SZ, _P]),
     "b200rec_topk_merge": (_I, [_P, _P, _I, _I64, _I, _I, _I64, _I64, _P, _P, _P]),
+    "b200rec_rescore_fp32": (_I, [_P, _I64, _P, _I64, _I64, _I64, _I, _P, _I64, _I, _P, _P]),
     "b200rec_gather_concat": (_I, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P, _I, _I64, _P, _I64, _P, _P]),
     "b200rec_train_step_begin": (_I, [_P, _P, _F, _F, _P, _U64, _P]),
     "b200rec_adam_dense_dev": (_I, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P, _P]),

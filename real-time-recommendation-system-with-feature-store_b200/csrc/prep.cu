@@ -2,9 +2,12 @@
 // optionally expanded into split-bf16 terms so that a bf16 GEMM reproduces fp32 products).
 //   x = h + m + l exactly, h = bf16(x), m = bf16(x-h), l = bf16(x-h-m)
 //   terms 1: left [h]            right [h]
-//   terms 3: left [h l h]        right [h h l]          (error ~2^-17 per product)
-//   terms 6: left [h h m h l m]  right [h m h l h m]    (drops only m*l, l*m, l*l: ~2^-24, i.e. fp32 grade)
+//   terms 3: left [h m h]        right [m h h]          (products h.m, m.h, h.h: error ~2^-17 per product)
+//   terms 6: left [m l h m h h]  right [m h l h m h]    (drops only m*l, l*m, l*l: ~2^-24, i.e. fp32 grade)
 // Each block is kpad columns wide (zero padded), so left . right^T over K = terms*kpad is the fp32 product sum.
+// Blocks are ordered SMALLEST piece product first: a tcgen05 accumulator chain adds with truncation, so every add made
+// while the partial sum is still ~2^-8 (or 2^-16) of the final value costs nothing, and only the last h.h blocks
+// truncate at full magnitude (E = 128, 6 terms: 8 full-magnitude adds instead of 48; the bias of a logit fell 6x).
 // HBM-bound elementwise kernels: one warp per row, coalesced loads, 2-byte stores coalesced along the row.
 #include "host_util.h"
 #include "tc_common.cuh"
@@ -24,11 +27,10 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16&
 __device__ __forceinline__ int part_of(int terms, int side, int t) {
   if (terms == 1) return 0;
   if (terms == 3) {
-    // left [h l h], right [h h l]  ("l" here is the first residual = m)
-    const int L[3] = {0, 1, 0}, R[3] = {0, 0, 1};
+    const int L[3] = {0, 1, 0}, R[3] = {1, 0, 0};
     return side == 0 ? L[t] : R[t];
   }
-  const int L6[6] = {0, 0, 1, 0, 2, 1}, R6[6] = {0, 1, 0, 2, 0, 1};
+  const int L6[6] = {1, 2, 0, 1, 0, 0}, R6[6] = {1, 0, 2, 0, 1, 0};
   return side == 0 ? L6[t] : R6[t];
 }
 

@@ -166,6 +166,19 @@ def topk_merge(scores: torch.Tensor, ids: torch.Tensor, k_out: int) -> Tuple[tor
     return out_s, out_i
 
 
+def rescore_fp32(queries: torch.Tensor, rows: torch.Tensor, ids: torch.Tensor, row_offset: int = 0) -> torch.Tensor:
+    """Exact fp32 inner products of candidate rows: queries fp32 [Q, d], rows fp32 [n, d], ids int64 [Q, k_in] (global
+    ids, < 0 = empty) -> scores fp32 [Q, k_in] (-FLT_MAX at empty slots)."""
+    assert queries.dtype == torch.float32 and rows.dtype == torch.float32 and ids.dtype == torch.int64
+    assert queries.stride(1) == 1 and rows.stride(1) == 1 and ids.is_contiguous()
+    q, k_in = ids.shape
+    out = torch.empty((q, k_in), dtype=torch.float32, device=ids.device)
+    N.check(N.lib().b200rec_rescore_fp32(N.ptr(queries), queries.stride(0), N.ptr(rows), rows.stride(0), rows.shape[0],
+                                         row_offset, queries.shape[1], N.ptr(ids), q, k_in, N.ptr(out), N.stream()),
+            "rescore_fp32")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ embedding bags
 import ctypes as _C  # noqa: E402
 
@@ -320,7 +333,7 @@ def inbatch_lse(u_op, i_op, B: int, NI: int, inv_t: float):
 
 
 # block index of pieces (h, m, l) inside an operand row written by split_bf16(terms, side) — csrc/prep.cu part_of()
-PIECE_BLOCKS = {(1, 0): (0,), (1, 1): (0,), (3, 0): (0, 1), (3, 1): (0, 2), (6, 0): (0, 2, 4), (6, 1): (0, 1, 3)}
+PIECE_BLOCKS = {(1, 0): (0,), (1, 1): (0,), (3, 0): (0, 1), (3, 1): (1, 0), (6, 0): (2, 0, 1), (6, 1): (1, 0, 2)}
 
 
 def inbatch_grad_supported(B: int, NI: int, E: int, nprod_s: int, nprod_g: int) -> bool:

@@ -58,7 +58,7 @@ def check_index_errors(device=None) -> None:
 
 def _bwd_terms(terms: int) -> int:
     """Split-bf16 terms of the GRADIENT GEMMs (dgrad, wgrad, the two in-batch gradient products) when the forward runs
-    fp32-grade (6 terms).  3 terms ([h l h] x [h h l]: products accurate to ~2^-17, fp32 accumulation) halve their
+    fp32-grade (6 terms).  3 terms ([h m h] x [m h h]: products accurate to ~2^-17, fp32 accumulation) halve their
     FLOPs and operand traffic; the golden parity tests (per-step losses, embeddings, gradients and parameters against the
     reference at 1e-5) hold with them, and the logits recompute that feeds exp() keeps 6.  B200REC_BWD_TERMS=6 restores
     fp32-grade gradient products."""

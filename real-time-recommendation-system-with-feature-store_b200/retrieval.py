@@ -54,9 +54,18 @@ class FlatIPDeviceIndex:
     """faiss.IndexFlatIP on one B200: rows appended with `add`, exact `search`.
 
     storage "bf16": rows rounded to bf16 (BASELINE config 3; scores are exact fp32 sums of the rounded products).
-    storage "fp32": rows kept as split-bf16 x3 operands, i.e. fp32-grade products (|err| ~ 1e-6 * |score|), for the
-    reference-scale catalogues where ids must match a CPU fp32 search except at ties within 1e-5.
+    storage "fp32": for the reference-scale catalogues where scores and ids must be those of a CPU fp32 search.  Rows
+    are kept twice: as fp32 and as split-bf16 x3 tensor-core operands.  The fused pass selects k + RESCORE_MARGIN
+    candidates with 3 piece products (|err| <= ~1e-5 * |q||x|), `b200rec_rescore_fp32` recomputes those candidates'
+    inner products with fp32 FMAs from the fp32 rows and a final select orders them (score desc, row asc): scores are
+    fp32-exact (~1e-7), ids differ from an fp32 CPU search only where fp32 summation order itself decides.
     """
+
+    @staticmethod
+    def rescore_margin(k: int) -> int:
+        """Extra candidates the tensor-core pass hands to the exact fp32 re-scoring: enough that the true top-k are
+        inside unless more than this many rows lie within the 3-product error of the k-th score."""
+        return max(16, k // 4)
 
     def __init__(self, d: int, storage: str = "fp32", device: Optional[torch.device] = None, row_offset: int = 0):
         if storage not in ("bf16", "fp32"):
@@ -133,8 +142,11 @@ class FlatIPDeviceIndex:
         if qt.shape[1] != self.d:
             raise ValueError(f"expected [nq, {self.d}] queries, got {tuple(qt.shape)}")
         qt = qt.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
-        _, _, qop = K.normalize_rows(qt, normalize=normalize, faiss_rule=True, want_f32=False, want_norms=False,
-                                     terms=self.terms, side=0)
+        keep = self.storage == "fp32"
+        y, _, qop = K.normalize_rows(qt, normalize=normalize, faiss_rule=True, want_f32=keep and normalize,
+                                     want_norms=False, terms=self.terms, side=0)
+        if keep:
+            qop._b200_f32 = y if normalize else qt       # the fp32 queries travel with their operand (exact re-scoring)
         return qop
 
     def _workspace(self, nq: int, k: int) -> torch.Tensor:
@@ -172,8 +184,20 @@ class FlatIPDeviceIndex:
                 return out
             return (torch.full((nq, k), -FLT_MAX, dtype=torch.float32, device=self.device),
                     torch.full((nq, k), -1, dtype=torch.int64, device=self.device))
-        return K.flat_ip_topk(self._cat[: self.ntotal], q_op, k, self.row_offset, exclude_indptr, exclude_rows,
-                              self._workspace(nq, k), tau_init, out)
+        q32 = getattr(q_op, "_b200_f32", None) if self._f32 is not None else None
+        if q32 is None:
+            return K.flat_ip_topk(self._cat[: self.ntotal], q_op, k, self.row_offset, exclude_indptr, exclude_rows,
+                                  self._workspace(nq, k), tau_init, out)
+        k_in = min(k + self.rescore_margin(k), max(k, min(self.ntotal, 2048)))
+        _, cand = K.flat_ip_topk(self._cat[: self.ntotal], q_op, k_in, self.row_offset, exclude_indptr, exclude_rows,
+                                 self._workspace(nq, k_in), None)   # tau_init bounds the k-th score, not the k_in-th
+        exact = K.rescore_fp32(q32, self._f32[: self.ntotal], cand, self.row_offset)
+        d, i = K.topk_merge(exact.unsqueeze(0), cand.unsqueeze(0), k)
+        if out is not None:
+            out[0].copy_(d)
+            out[1].copy_(i)
+            return out
+        return d, i
 
     def search(self, q, k: int, normalize: bool = False) -> Tuple[np.ndarray, np.ndarray]:
         """faiss contract: (D float32 [nq,k] descending, I int64 [nq,k]) as numpy arrays — `index.search(q, k)` of

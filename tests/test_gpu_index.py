@@ -14,11 +14,12 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def _same(got, want, atol=2e-6):
+def _same(got, want, atol=2e-6, rtol=1e-6):
+    """ids identical; scores equal up to fp32 summation order (the goldens are numpy sgemm, ours fp32 FMA chains)."""
     assert got[0] == want[0], "item ids differ"
     assert len(got[1]) == len(want[1])
     for a, b in zip(got[1], want[1]):
-        assert len(a) == len(b) and np.allclose(a, b, rtol=0, atol=atol)
+        assert len(a) == len(b) and np.allclose(a, b, rtol=rtol, atol=atol)
 
 
 @pytest.mark.parametrize("metric", ["cosine", "ip"])
@@ -102,8 +103,9 @@ def test_save_load_round_trip_and_ixfi_header(tmp_path):
 @pytest.mark.parametrize("D,N,Q,k", [(128, 20000, 70, 100), (64, 5000, 300, 10), (100, 3000, 5, 50)])
 def test_fp32_storage_matches_the_fp32_oracle(D, N, Q, k):
     """The DEFAULT storage of the drop-in class: split-bf16 x3 catalogue rows (ld = 3 * pad64(D): KB = 6 k-blocks at
-    D = 128), fp32-grade scores on inputs that are NOT bf16-representable.  ids equal the fp32 oracle's except inside
-    groups of scores tied within 1e-5 (north_star tolerance); scores within 1e-5."""
+    D = 128) select k + margin candidates, which are re-scored exactly in fp32 (csrc/rescore.cu), on inputs that are NOT
+    bf16-representable.  Scores within 1e-6 of the fp32 oracle; ids equal except inside groups of scores tied within
+    1e-6 (fp32 summation order; the north_star tolerance is 1e-5)."""
     from b200rec.retrieval import FlatIPDeviceIndex
     from oracle.flat_ip import IndexFlatIP, normalize_L2
     rng = np.random.default_rng(D + N)
@@ -118,13 +120,18 @@ def test_fp32_storage_matches_the_fp32_oracle(D, N, Q, k):
     ref.add(cat)
     rD, rI = ref.search(qry, k)
     assert Dg.dtype == np.float32 and Ig.dtype == np.int64 and Dg.shape == (Q, k)
-    assert np.abs(Dg - rD).max() <= 1e-5
+    assert np.abs(Dg - rD).max() <= 1e-6
     assert (np.diff(Dg, axis=1) <= 0).all()
     bad = np.argwhere(Ig != rI)
     for q, j in bad:
         exact = float(cat[Ig[q, j]].astype(np.float64) @ qry[q].astype(np.float64))
-        assert abs(exact - rD[q, j]) <= 1e-5, f"query {q} rank {j}: id {Ig[q, j]} ({exact}) vs {rI[q, j]} ({rD[q, j]})"
-    assert len(bad) <= 0.01 * Ig.size
+        assert abs(exact - rD[q, j]) <= 1e-6, f"query {q} rank {j}: id {Ig[q, j]} ({exact}) vs {rI[q, j]} ({rD[q, j]})"
+    assert len(bad) <= 0.002 * Ig.size
+    # without the fp32 queries attached the same index answers from the 3-product tensor-core scores alone (1e-5 grade)
+    q_op = ix.prepare_queries(qry)
+    del q_op._b200_f32
+    Dc, Ic = ix.search_device(q_op, k)
+    assert np.abs(Dc.cpu().numpy() - rD).max() <= 1e-5 and (Ic.cpu().numpy() == rI).mean() >= 0.98
     assert np.allclose(ix.reconstruct_n(0, 7), cat[:7], atol=0)                       # fp32 rows are kept exactly
 
 

@@ -119,8 +119,9 @@ def test_flat_adam_skips_parameters_without_gradient_and_round_trips_torch_state
     sd, rsd = ours.state_dict(), ref_opt.state_dict()
     assert sorted(sd.keys()) == sorted(rsd.keys()) and sd["param_groups"][0]["params"] == rsd["param_groups"][0]["params"]
     for i in rsd["state"]:
-        assert torch.allclose(sd["state"][i]["exp_avg"].cpu(), rsd["state"][i]["exp_avg"], atol=1e-7)
-        assert torch.allclose(sd["state"][i]["exp_avg_sq"].cpu(), rsd["state"][i]["exp_avg_sq"], atol=1e-9)
+        # the gradients come from the 3-product split-bf16 GEMMs (~2^-17 per product): moments agree to ~1e-5 relative
+        assert torch.allclose(sd["state"][i]["exp_avg"].cpu(), rsd["state"][i]["exp_avg"], rtol=1e-4, atol=1e-6)
+        assert torch.allclose(sd["state"][i]["exp_avg_sq"].cpu(), rsd["state"][i]["exp_avg_sq"], rtol=1e-4, atol=1e-8)
     # resume from the torch optimiser's state: the next step matches torch's next step
     fresh_p = [torch.nn.Parameter(p.detach().clone().to(DEV)) for p in ref_p]
     fresh = FlatAdam(fresh_p, lr=1.0, weight_decay=0.0, max_grad_norm=None)
@@ -169,6 +170,8 @@ def test_fused_inbatch_backward_with_gathered_negatives(B, G, E, rank):
     logits = ur @ vr.T * 20.0
     ref = (torch.logsumexp(logits, 1) - logits[torch.arange(B), rank * B + torch.arange(B)]).sum() / (G * B)
     (ref * 3.0).backward()
+    # the loss is a DIFFERENCE of O(10) terms (strong positives: lse ~ pos): 1e-5 relative to the terms that are summed
+    scale = max(abs(ref.item()), torch.logsumexp(logits, 1).abs().mean().item() / G)
     res = {}
     for mode in ("fused", "chunked"):
         os.environ["B200REC_INBATCH_BWD"] = mode
@@ -178,7 +181,7 @@ def test_fused_inbatch_backward_with_gathered_negatives(B, G, E, rank):
             (loss * 3.0).backward()
         finally:
             os.environ.pop("B200REC_INBATCH_BWD", None)
-        assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+        assert abs(loss.item() - ref.item()) <= 1e-5 * scale, (loss.item(), ref.item())
         assert (uc.grad.cpu().double() - ur.grad).abs().max() <= 1e-4 * ur.grad.abs().max(), mode
         assert (vc.grad.cpu().double() - vr.grad).abs().max() <= 1e-4 * vr.grad.abs().max(), mode
         res[mode] = (uc.grad.cpu(), vc.grad.cpu())
