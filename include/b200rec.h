@@ -161,6 +161,48 @@ int b200rec_colsum(const float* x, int64_t B, int64_t H, int64_t ld, float* out,
 int b200rec_normalize_bwd(const float* dE, const float* E, const float* norms, int64_t B, int64_t D, float* dO,
                           void* stream);
 
+/* ---------------------------------------------------------------- fused tower-MLP layers (csrc/mlp_fused.cuh)
+ * One launch per Linear and direction.  A hidden block [Linear -> activation -> BatchNorm1d -> Dropout] (reference
+ * src/models/two_tower.py:60-66,200-206) is described by its tensors; the kernels apply the block's transform while
+ * they BUILD the tensor-core operand of the next GEMM (no split-bf16 copies, no separate BN / activation / dropout
+ * passes) and reduce the batch statistics the next launch needs in their epilogue.
+ *   np = bf16 pieces per operand: 3 (6 piece products, fp32 grade), 2 (3 products, ~2^-17), 1 (plain bf16). */
+typedef struct b200rec_bn_block {
+  const float* z;                 /* [rows, H] pre-activations (output of the block's Linear) */
+  int64_t ldz;
+  int32_t H;                      /* <= 512 */
+  int32_t act;                    /* 0 relu, 1 gelu, 2 leaky_relu(0.1), 3 tanh, 4 sigmoid, 5 identity */
+  int32_t training;               /* batch statistics (sums) + dropout, or running statistics */
+  int32_t update_running;         /* forward: apply the momentum update + count the batch (done once, by one CTA) */
+  const double* sums;             /* training: [2H] sum act(z), sum act(z)^2 over B_stat rows */
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  int64_t* num_batches_tracked;   /* may be NULL */
+  float eps, momentum, drop_p;
+  uint64_t seed;
+  int64_t B_stat;                 /* rows the statistics cover (the global batch under data parallel) */
+} b200rec_bn_block;
+/* out[B,N] = input . w[N,K]^T + bias, input = x (lower == NULL) or Dropout(BN(act(lower->z))).
+ * out_sums != NULL: [2N] += sum act_out(out), sum act_out(out)^2 (pre-zeroed; the statistics of this layer's own block).
+ * normalize != 0 (last layer, N <= 128): out = F.normalize(out) (two_tower.py:132,279), norms[B] = max(||row||, 1e-12). */
+int b200rec_mlp_forward(const float* x, int64_t ldx, const b200rec_bn_block* lower, const float* w, int64_t ldw,
+                        const float* bias, int64_t B, int N, int K, int np, float* out, int64_t ldo, int out_act,
+                        double* out_sums, int normalize, float* norms, void* stream);
+/* dx[B,K] = dz . w, dz = dy (own == NULL: last layer) or the BatchNorm/activation/dropout backward of `own` applied to
+ * dy with own_bsums = [2N] sum g, sum g*xhat.  lower_bsums != NULL: [2K] += the same two sums for the block below
+ * (g = dx * its dropout mask), ready for the next launch. */
+int b200rec_mlp_dgrad(const float* dy, int64_t lddy, const b200rec_bn_block* own, const double* own_bsums, const float* w,
+                      int64_t ldw, int64_t B, int N, int K, int np, float* dx, int64_t lddx,
+                      const b200rec_bn_block* lower, double* lower_bsums, void* stream);
+/* dw[N,K] += dz^T . input, db[N] += colsum(dz) (fp32 atomics into pre-zeroed or accumulating buffers);
+ * dgamma / dbeta [N] += own_bsums_local (NULL = own_bsums) halves. */
+int b200rec_mlp_wgrad(const float* dy, int64_t lddy, const b200rec_bn_block* own, const double* own_bsums,
+                      const double* own_bsums_local, const float* x, int64_t ldx, const b200rec_bn_block* lower,
+                      int64_t B, int N, int K, int np, float* dw, int64_t lddw, float* db, float* dgamma, float* dbeta,
+                      void* stream);
+
 /* ---------------------------------------------------------------- losses (csrc/loss_ops.cu, csrc/inbatch_lse.cu)
  * In-batch softmax cross-entropy (two_tower.py:467-479), forward fused with the logits GEMM: the B x NI logits live
  * only in TMEM.  U_op [B, ld] / I_op [NI, ld] are split-bf16 operands (left / right patterns).  Output per row:

@@ -37,6 +37,9 @@ SIGNATURES = {
     "b200rec_topk_sample_fanout": (_I, [_P, _I64, _I64, _P, _I64, _I, _I, _I, _I, _P, _P, _SZ, _P]),
     "b200rec_topk_merge": (_I, [_P, _P, _I, _I64, _I, _I, _I64, _I64, _P, _P, _P]),
     "b200rec_rescore_fp32": (_I, [_P, _I64, _P, _I64, _I64, _I64, _I, _P, _I64, _I, _P, _P]),
+    "b200rec_mlp_forward": (_I, [_P, _I64, _P, _P, _I64, _P, _I64, _I, _I, _I, _P, _I64, _I, _P, _I, _P, _P]),
+    "b200rec_mlp_dgrad": (_I, [_P, _I64, _P, _P, _P, _I64, _I64, _I, _I, _I, _P, _I64, _P, _P, _P]),
+    "b200rec_mlp_wgrad": (_I, [_P, _I64, _P, _P, _P, _P, _I64, _P, _I64, _I, _I, _I, _P, _I64, _P, _P, _P, _P]),
     "b200rec_gather_concat": (_I, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P, _I, _I64, _P, _I64, _P, _P]),
     "b200rec_train_step_begin": (_I, [_P, _P, _F, _F, _P, _U64, _P]),
     "b200rec_adam_dense_dev": (_I, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P, _P]),
@@ -75,6 +78,14 @@ SIGNATURES = {
     "b200rec_eval_metrics": (_I, [_P, _I64, _I, _I64, _P, _I64, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I64, _I, _P, _P]),
     "b200rec_sparse_adam": (_I, [_P, _P, _P, _I64, _I, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P, _P]),
 }
+
+
+class BnBlock(C.Structure):
+    """b200rec_bn_block (include/b200rec.h)."""
+    _fields_ = [("z", _P), ("ldz", _I64), ("H", C.c_int32), ("act", C.c_int32), ("training", C.c_int32),
+                ("update_running", C.c_int32), ("sums", _P), ("gamma", _P), ("beta", _P), ("running_mean", _P),
+                ("running_var", _P), ("num_batches_tracked", _P), ("eps", _F), ("momentum", _F), ("drop_p", _F),
+                ("seed", _U64), ("B_stat", _I64)]
 
 
 def lib():

@@ -4,74 +4,10 @@
 // Reference order is Linear -> activation -> BatchNorm1d -> Dropout (src/models/two_tower.py:56-72,196-212).
 #include "host_util.h"
 #include "tc_common.cuh"
+#include "tower_math.cuh"
 #include "../../include/b200rec.h"
 
 namespace b200 {
-
-// ------------------------------------------------------------------ activations (two_tower.py:77-86)
-__device__ __forceinline__ float act_fwd(int act, float z) {
-  switch (act) {
-    case 0: return z > 0.f ? z : 0.f;                                      // relu
-    case 1: return 0.5f * z * (1.0f + erff(z * 0.70710678118654752440f));  // gelu (erf form, torch default)
-    case 2: return z > 0.f ? z : 0.1f * z;                                 // leaky_relu(0.1)
-    case 3: return tanhf(z);
-    case 4: return 1.0f / (1.0f + expf(-z));
-    default: return z;
-  }
-}
-__device__ __forceinline__ float act_grad(int act, float z) {
-  switch (act) {
-    case 0: return z > 0.f ? 1.f : 0.f;
-    case 1: {
-      const float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752440f));
-      const float pdf = 0.39894228040143267794f * expf(-0.5f * z * z);
-      return cdf + z * pdf;
-    }
-    case 2: return z > 0.f ? 1.f : 0.1f;
-    case 3: {
-      const float t = tanhf(z);
-      return 1.f - t * t;
-    }
-    case 4: {
-      const float s = 1.0f / (1.0f + expf(-z));
-      return s * (1.f - s);
-    }
-    default: return 1.f;
-  }
-}
-
-// ------------------------------------------------------------------ counter-based dropout mask (Philox-4x32-10)
-__device__ __forceinline__ uint4 philox4(uint64_t seed, uint64_t ctr) {
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x9E3779B9u, c3 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-    const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-    c0 = h1 ^ c1 ^ k0;
-    c1 = l1;
-    c2 = h0 ^ c3 ^ k1;
-    c3 = l0;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-  return make_uint4(c0, c1, c2, c3);
-}
-// Per-step salt of every dropout seed, set on the device by b200rec_train_step_begin.  A training step captured in a
-// CUDA graph replays with the kernel arguments of the capture, so what must change from step to step (the dropout
-// streams here, Adam's bias corrections in optim.cu) lives in device memory.  0 (never set) in eager training.
-__device__ unsigned long long g_seed_salt = 0ull;
-
-// keep-scale of element (row, col): 0 when dropped, 1/(1-p) when kept; p == 0 -> 1
-__device__ __forceinline__ float drop_scale(float p, uint64_t seed, int64_t row, int64_t col, int64_t H) {
-  if (p <= 0.f) return 1.f;
-  seed ^= g_seed_salt;
-  const uint64_t idx = (uint64_t)row * (uint64_t)H + (uint64_t)col;
-  const uint4 r = philox4(seed, idx >> 2);
-  const uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
-  const float u = (float)(w >> 8) * (1.0f / 16777216.0f);
-  return u >= p ? 1.0f / (1.0f - p) : 0.f;
-}
 
 // ------------------------------------------------------------------ column statistics
 // sums[0:H] += sum_b f1(b,h), sums[H:2H] += sum_b f2(b,h)  (fp64)
@@ -433,3 +369,6 @@ extern "C" int b200rec_act_dropout_bwd(const float* dy, int64_t ld_dy, const flo
   B200_LAUNCH_OK("act_dropout_bwd_kernel");
   return 0;
 }
+
+// fused per-layer kernels (same translation unit: they share g_seed_salt with the kernels above)
+#include "mlp_fused.cuh"

@@ -286,6 +286,56 @@ def bn_backward_dp(dy, z, act: int, mean, invstd, gamma, drop_p: float, seed: in
     return dz, dgamma, dbeta
 
 
+# ------------------------------------------------------------------------------------------------ fused MLP layers
+class BnBlock:
+    """One hidden block [Linear -> act -> BatchNorm1d -> Dropout] as the fused layer kernels see it (b200rec_bn_block):
+    the block's pre-activations z, its batch statistics (fp64 sums) or running statistics, affine and dropout stream."""
+
+    def __init__(self, z, act: int, training: bool, sums, gamma, beta, running_mean, running_var, nbt, eps: float,
+                 momentum: float, drop_p: float, seed: int, b_stat: int, update_running: bool = False):
+        self.z, self.sums, self.gamma, self.beta = z, sums, gamma, beta
+        self.running_mean, self.running_var, self.nbt = running_mean, running_var, nbt
+        self.c = N.BnBlock(N.ptr(z), z.stride(0), z.shape[1], act, int(training), int(update_running), N.ptr(sums),
+                           N.ptr(gamma), N.ptr(beta), N.ptr(running_mean), N.ptr(running_var), N.ptr(nbt), eps, momentum,
+                           drop_p if training else 0.0, seed & 0xFFFFFFFFFFFFFFFF, b_stat)
+
+    def ref(self, update_running: Optional[bool] = None):
+        if update_running is not None:
+            self.c.update_running = int(update_running)
+        return _C.byref(self.c)
+
+
+def mlp_forward(x: Optional[torch.Tensor], lower: Optional[BnBlock], w, bias, out: torch.Tensor, np_: int, out_act: int = 5,
+                out_sums: Optional[torch.Tensor] = None, normalize: bool = False, norms: Optional[torch.Tensor] = None,
+                update_running: bool = False) -> torch.Tensor:
+    """out[B,N] = input . w^T + bias (input = x or the output of block `lower`), one launch (csrc/mlp_fused.cuh)."""
+    B, Nn, Kk = out.shape[0], w.shape[0], w.shape[1]
+    N.check(N.lib().b200rec_mlp_forward(N.ptr(x), x.stride(0) if x is not None else 0,
+                                        lower.ref(update_running) if lower is not None else None, N.ptr(w), w.stride(0),
+                                        N.ptr(bias), B, Nn, Kk, np_, N.ptr(out), out.stride(0), out_act, N.ptr(out_sums),
+                                        int(normalize), N.ptr(norms), N.stream()), "mlp_forward")
+    return out
+
+
+def mlp_dgrad(dy, own: Optional[BnBlock], own_bsums, w, dx, np_: int, lower: Optional[BnBlock] = None,
+              lower_bsums: Optional[torch.Tensor] = None) -> torch.Tensor:
+    B, Nn, Kk = dy.shape[0], w.shape[0], w.shape[1]
+    N.check(N.lib().b200rec_mlp_dgrad(N.ptr(dy), dy.stride(0), own.ref() if own is not None else None, N.ptr(own_bsums),
+                                      N.ptr(w), w.stride(0), B, Nn, Kk, np_, N.ptr(dx), dx.stride(0),
+                                      lower.ref() if lower is not None else None, N.ptr(lower_bsums), N.stream()),
+            "mlp_dgrad")
+    return dx
+
+
+def mlp_wgrad(dy, own: Optional[BnBlock], own_bsums, own_bsums_local, x, lower: Optional[BnBlock], np_: int, dw, db,
+              dgamma=None, dbeta=None) -> None:
+    B, Nn, Kk = dy.shape[0], dw.shape[0], dw.shape[1]
+    N.check(N.lib().b200rec_mlp_wgrad(N.ptr(dy), dy.stride(0), own.ref() if own is not None else None, N.ptr(own_bsums),
+                                      N.ptr(own_bsums_local), N.ptr(x), x.stride(0) if x is not None else 0,
+                                      lower.ref() if lower is not None else None, B, Nn, Kk, np_, N.ptr(dw), dw.stride(0),
+                                      N.ptr(db), N.ptr(dgamma), N.ptr(dbeta), N.stream()), "mlp_wgrad")
+
+
 def act_dropout(z, act: int, drop_p: float, seed: int):
     B, H = z.shape
     y = torch.empty_like(z)

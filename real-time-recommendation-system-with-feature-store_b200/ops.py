@@ -139,6 +139,122 @@ class ActBNDropFn(Function):
         return dz, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 
+def _grad_target(p: torch.Tensor, needed: bool):
+    """Where a fused backward kernel accumulates the gradient of parameter p: its pre-allocated .grad (FlatAdam's flat
+    buffer, zeroed by zero_grad — the kernel adds with atomics, so a tower that runs twice per step simply adds twice)
+    or a fresh zero tensor handed back to autograd.  Returns (buffer, value_to_return_from_backward)."""
+    if not needed:
+        return None, None
+    g = p.grad
+    if (isinstance(g, torch.Tensor) and g.shape == p.shape and g.dtype == torch.float32 and g.is_contiguous()
+            and getattr(p, "_b200_touch", None) is not None):
+        touch = p._b200_touch
+        touch[0]._mark(touch[1])
+        return g, None
+    buf = torch.zeros_like(p, dtype=torch.float32)
+    return buf, buf
+
+
+class MLPSpec:
+    """Non-tensor description of one tower MLP call for TowerMLPFn (activation, mode, dropout streams, BN buffers)."""
+
+    def __init__(self, act: int, training: bool, drop_p: float, seeds, bns, np_fwd: int, np_bwd: int, dp=None):
+        self.act, self.training, self.drop_p, self.seeds, self.bns = act, training, drop_p, seeds, bns
+        self.np_fwd, self.np_bwd, self.dp = np_fwd, np_bwd, dp
+
+
+class TowerMLPFn(Function):
+    """[Linear -> act -> BatchNorm1d -> Dropout] x L -> Linear -> F.normalize (two_tower.py:56-72,128-132) with ONE
+    kernel launch per Linear in the forward and two (weight gradient, data gradient) in the backward
+    (csrc/mlp_fused.cuh).  Inputs: x, spec, then per hidden layer (W, b, gamma, beta) and (W, b) of the last Linear.
+    Parameter gradients are accumulated in place when the optimiser pre-allocated them."""
+
+    @staticmethod
+    def forward(ctx, x, spec: MLPSpec, *params):
+        require_cuda(x, *params)
+        x = _c32(x)
+        L = len(spec.bns)
+        B, dev = x.shape[0], x.device
+        training = spec.training
+        dp = spec.dp if training else None
+        b_stat = B * (dp.world if dp is not None else 1)
+        widths = [params[4 * l].shape[0] for l in range(L)]
+        # forward statistics and backward sums of every block in one zero-filled buffer: [fwd_0 | bwd_0 | fwd_1 | ...]
+        # (eval mode needs no forward statistics; its backward sums still give dgamma / dbeta)
+        scratch = torch.zeros((max(4 * sum(widths), 1),), dtype=torch.float64, device=dev) \
+            if (training or any(ctx.needs_input_grad)) else None
+        off, fsum, bsum = 0, [], []
+        for h in widths:
+            fsum.append(scratch[off:off + 2 * h] if training else None)
+            bsum.append(scratch[off + 2 * h:off + 4 * h] if scratch is not None else None)
+            off += 4 * h
+        blocks, lower, inp = [], None, x
+        for l in range(L):
+            w, b, gamma, beta = params[4 * l:4 * l + 4]
+            bn = spec.bns[l]
+            z = torch.empty((B, widths[l]), dtype=torch.float32, device=dev)
+            K.mlp_forward(inp, lower, w, b, z, spec.np_fwd, spec.act, fsum[l], update_running=training)
+            if dp is not None:
+                dp.reduce_sums(fsum[l])
+            lower = K.BnBlock(z, spec.act, training, fsum[l], gamma, beta, bn.running_mean, bn.running_var,
+                              bn.num_batches_tracked, bn.eps, bn.momentum if bn.momentum is not None else 0.1,
+                              spec.drop_p, spec.seeds[l], b_stat)
+            blocks.append(lower)
+            inp = None
+        w, b = params[4 * L], params[4 * L + 1]
+        e = torch.empty((B, w.shape[0]), dtype=torch.float32, device=dev)
+        norms = torch.empty((B,), dtype=torch.float32, device=dev)
+        K.mlp_forward(inp, lower, w, b, e, spec.np_fwd, 5, None, normalize=True, norms=norms, update_running=training)
+        ctx.save_for_backward(x, e, norms)
+        ctx.spec, ctx.params, ctx.blocks, ctx.bsum, ctx.scratch = spec, params, blocks, bsum, scratch
+        return e
+
+    @staticmethod
+    def backward(ctx, de):
+        x, e, norms = ctx.saved_tensors
+        spec, params, blocks, bsum = ctx.spec, ctx.params, ctx.blocks, ctx.bsum
+        L = len(blocks)
+        B, dev = x.shape[0], x.device
+        npb = spec.np_bwd
+        dp = spec.dp if spec.training else None
+        need = ctx.needs_input_grad
+        grads = [None] * len(params)
+        dy = K.normalize_bwd(_c32(de), e, norms)                      # gradient wrt the last Linear's output
+        local = [None] * L
+        dx0 = None
+        for l in range(L, -1, -1):
+            own = blocks[l] if l < L else None
+            own_b = bsum[l] if l < L else None
+            lower = blocks[l - 1] if l > 0 else None
+            base = 4 * l
+            w = params[base]
+            has_b = params[base + 1] is not None
+            dw, grads[base] = _grad_target(w, need[2 + base])
+            if dw is None:
+                dw = torch.zeros_like(w)
+            db, grads[base + 1] = _grad_target(params[base + 1], has_b and need[3 + base])
+            dgamma = dbeta = None
+            if l < L:
+                dgamma, grads[base + 2] = _grad_target(params[base + 2], need[4 + base])
+                dbeta, grads[base + 3] = _grad_target(params[base + 3], need[5 + base])
+                if (dgamma is None) != (dbeta is None):               # the kernel writes both or none
+                    dgamma = dgamma if dgamma is not None else torch.zeros_like(params[base + 2])
+                    dbeta = dbeta if dbeta is not None else torch.zeros_like(params[base + 3])
+            K.mlp_wgrad(dy, own, own_b, local[l] if l < L else None, x if l == 0 else None, lower, npb, dw, db, dgamma, dbeta)
+            if l > 0 or need[0]:
+                k_in = w.shape[1]
+                dx = torch.empty((B, k_in), dtype=torch.float32, device=dev)
+                want_sums = l > 0
+                K.mlp_dgrad(dy, own, own_b, w, dx, npb, lower if want_sums else None, bsum[l - 1] if want_sums else None)
+                if want_sums and dp is not None:
+                    local[l - 1] = bsum[l - 1].clone()               # dgamma / dbeta add this replica's part only
+                    dp.reduce_sums(bsum[l - 1])
+                dy = dx
+                if l == 0:
+                    dx0 = dx
+        return (dx0, None, *grads)
+
+
 class ActDropFn(Function):
     """y = Dropout(act(z)) (content_projection, two_tower.py:184-191)."""
 

@@ -110,9 +110,36 @@ class _TowerBase(nn.Module):
             feats = torch.cat([feats, extra], dim=-1)  # content branch only (low-traffic path)
         return feats
 
+    def _fused_ok(self) -> bool:
+        """The fused per-layer kernels (csrc/mlp_fused.cuh) stage one block's per-feature constants in shared memory
+        (<= 512 features) and normalise rows that live in one tile (embedding_dim <= 128); wider towers run the
+        unfused kernel chain below (B200REC_MLP=unfused forces it, for A/B checks)."""
+        import os
+        if os.environ.get("B200REC_MLP") == "unfused":
+            return False
+        widths = [self.mlp[4 * l].out_features for l in range(self._num_hidden)]
+        return all(w <= 512 for w in widths) and self.mlp[4 * self._num_hidden].out_features <= 128
+
     def _run_mlp(self, x: torch.Tensor) -> torch.Tensor:
         terms = _TERMS[self.precision]
         act = _act_id(self.activation)
+        if self._fused_ok():
+            if self.training and x.shape[0] < 2 and self._num_hidden > 0:
+                raise ValueError(f"Expected more than 1 value per channel when training, got input size "
+                                 f"{[x.shape[0], self.mlp[0].out_features]}")
+            p = self.dropout_rate if self.training else 0.0
+            seeds = [self._next_seed() if p > 0 else 0 for _ in range(self._num_hidden)]
+            bns = [self.mlp[4 * l + 2] for l in range(self._num_hidden)]
+            params = []
+            for l in range(self._num_hidden):
+                lin, bn = self.mlp[4 * l], self.mlp[4 * l + 2]
+                params += [lin.weight, lin.bias, bn.weight, bn.bias]
+            last = self.mlp[4 * self._num_hidden]
+            params += [last.weight, last.bias]
+            np_fwd = 3 if terms == 6 else 1
+            np_bwd = {6: 3, 3: 2, 1: 1}[ops._bwd_terms(terms)]
+            spec = ops.MLPSpec(act, self.training, p, seeds, bns, np_fwd, np_bwd, getattr(self, "dp", None))
+            return ops.TowerMLPFn.apply(x, spec, *params)
         for l in range(self._num_hidden):
             lin, bn = self.mlp[4 * l], self.mlp[4 * l + 2]
             z = ops.LinearFn.apply(x, lin.weight, lin.bias, terms)

@@ -199,3 +199,83 @@ def test_bf16_mode_within_budget():
     m.precision = "bf16"
     b = m.get_user_embeddings({"numerical": x})
     assert (a - b).abs().max().item() <= 2e-2 * a.abs().max().item()
+
+
+def _torch_tower(t, dtype=torch.float64):
+    """The reference module chain (two_tower.py:56-72) rebuilt from a b200rec tower's parameters, on the CPU in fp64."""
+    import copy
+    mlp = copy.deepcopy(t.mlp).cpu().to(dtype)
+    for m in mlp:
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    return mlp
+
+
+@pytest.mark.parametrize("B,K0,hidden,E,act", [(300, 20, [64, 48], 64, "relu"), (1000, 3, [256, 128], 128, "gelu"),
+                                               (257, 130, [100], 32, "tanh"), (64, 80, [512, 256, 128], 128, "leaky_relu"),
+                                               (129, 16, [], 64, "relu"), (2048, 80, [128, 64], 64, "sigmoid")])
+def test_fused_mlp_layers_match_torch_fp64(B, K0, hidden, E, act):
+    """csrc/mlp_fused.cuh (one launch per Linear and direction) against the torch module chain in fp64: embeddings,
+    input gradient, every parameter gradient, BatchNorm running statistics and batch counter; train and eval mode."""
+    from b200rec.two_tower import UserTower
+    torch.manual_seed(B + K0)
+    t = UserTower(K0, embedding_dim=E, hidden_layers=hidden, dropout_rate=0.0, activation=act).to(DEV)
+    for m in t.modules():
+        if isinstance(m, torch.nn.Linear):
+            m.bias.data.normal_(0, 0.1)
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.2)
+    assert t._fused_ok()
+    ref = _torch_tower(t)
+    x = torch.randn(B, K0)
+    R = torch.randn(B, E)
+    for training in (True, False):
+        t.train(training)
+        ref.train(training)
+        xg = x.clone().to(DEV).requires_grad_()
+        e = t(xg)
+        (e * R.to(DEV)).sum().backward()
+        xr = x.clone().double().requires_grad_()
+        er = torch.nn.functional.normalize(ref(xr), p=2, dim=-1)
+        (er * R.double()).sum().backward()
+        assert (e.detach().cpu().double() - er.detach()).abs().max() <= 1e-5
+        scale = lambda g: max(g.abs().max().item(), 1e-6)
+        assert (xg.grad.cpu().double() - xr.grad).abs().max() <= 2e-4 * scale(xr.grad)
+        ours = dict(t.mlp.named_parameters())
+        for name, p in ref.named_parameters():
+            assert (ours[name].grad.cpu().double() - p.grad).abs().max() <= 2e-4 * scale(p.grad), (training, name)
+            ours[name].grad = None
+            p.grad = None
+        for (n1, b1), (n2, b2) in zip(t.mlp.named_buffers(), ref.named_buffers()):
+            assert n1 == n2
+            assert torch.allclose(b1.cpu().double(), b2.double(), rtol=1e-5, atol=1e-6), (training, n1)
+
+
+def test_fused_mlp_equals_unfused_chain_with_dropout(monkeypatch):
+    """Same dropout streams in both paths: the fused kernels reproduce the unfused kernel chain (prep + GEMM + BN
+    kernels) on a dropout > 0 training step, forward and backward, and the item tower's two passes accumulate."""
+    from b200rec.two_tower import ItemTower
+    torch.manual_seed(5)
+    t = ItemTower(20, embedding_dim=128, hidden_layers=[256, 128], dropout_rate=0.3, use_content_embedding=False).to(DEV)
+    t.train()
+    x1, x2 = torch.randn(700, 20, device=DEV), torch.randn(1300, 20, device=DEV)
+    R1, R2 = torch.randn(700, 128, device=DEV), torch.randn(1300, 128, device=DEV)
+    out = {}
+    state = {k: v.clone() for k, v in t.state_dict().items()}
+    for mode in ("fused", "unfused"):
+        monkeypatch.setenv("B200REC_MLP", mode)
+        t.load_state_dict(state)
+        t._seed_counter = 0
+        for p in t.parameters():
+            p.grad = None
+        a, b = t(x1), t(x2)                     # two passes of one tower (positives, negatives): gradients add up
+        ((a * R1).sum() + (b * R2).sum()).backward()
+        out[mode] = (a.detach().clone(), b.detach().clone(), {n: p.grad.clone() for n, p in t.named_parameters()},
+                     {n: v.clone() for n, v in t.named_buffers()})
+    f, u = out["fused"], out["unfused"]
+    assert (f[0] - u[0]).abs().max().item() <= 2e-6 and (f[1] - u[1]).abs().max().item() <= 2e-6
+    for n in f[2]:
+        assert (f[2][n] - u[2][n]).abs().max().item() <= 2e-4 * max(u[2][n].abs().max().item(), 1e-6), n
+    for n in f[3]:
+        assert torch.allclose(f[3][n].double(), u[3][n].double(), rtol=1e-5, atol=1e-6), n

@@ -1,20 +1,26 @@
-"""A few config-2 training steps (1M users x 100K items, dim 64, batch 8192, in-batch negatives) for ncu captures."""
-import sys, numpy as np, torch
+"""A few training steps for ncu captures: SHAPE=cfg2 (1M users x 100K items, dim 64, batch 8192, in-batch negatives) or
+SHAPE=ml1m (batch 1024 x 16 explicit negatives, E 128, hidden [256,128], mixed loss)."""
+import os, sys, numpy as np, torch
 sys.path.insert(0, ".")
 from b200rec.trainer import TwoTowerTrainer
 from b200rec.training_utils import create_two_tower_model_for_training
-B, NU, NI, FD = 8192, 1_000_000, 100_000, 16
 torch.manual_seed(1234)
-cfg = {"embedding_dim": 64, "hidden_layers": [128, 64], "dropout_rate": 0.2, "temperature": 0.05,
-       "user_categorical_features": {"user_id": NU}, "item_categorical_features": {"item_id": NI},
-       "embedding_dims": {"user_id": 64, "item_id": 64}}
-model = create_two_tower_model_for_training(FD, FD, cfg)
+rng = np.random.default_rng(1234)
+if os.environ.get("SHAPE", "cfg2") == "cfg2":
+    B, NU, NI, FD = 8192, 1_000_000, 100_000, 16
+    cfg = {"embedding_dim": 64, "hidden_layers": [128, 64], "dropout_rate": 0.2, "temperature": 0.05,
+           "user_categorical_features": {"user_id": NU}, "item_categorical_features": {"item_id": NI},
+           "embedding_dims": {"user_id": 64, "item_id": 64}}
+    model = create_two_tower_model_for_training(FD, FD, cfg)
+    z = lambda n, hi: torch.from_numpy(np.clip(rng.zipf(1.05, size=n), 1, hi).astype(np.int64)).cuda()
+    args = (torch.randn(B, FD).cuda(), torch.randn(B, FD).cuda(), None, {"user_id": z(B, NU)}, {"item_id": z(B, NI)})
+else:
+    B, R, FU, FI = 1024, 16, 3, 20
+    model = create_two_tower_model_for_training(FU, FI, {"embedding_dim": 128, "hidden_layers": [256, 128], "dropout_rate": 0.2})
+    args = (torch.randn(B, FU).cuda(), torch.randn(B, FI).cuda(), torch.randn(B, R, FI).cuda())
 tr = TwoTowerTrainer(model, [], [], {"checkpoint_dir": "/tmp/b200rec_prof"}, device="cuda")
 model.train()
-rng = np.random.default_rng(1234)
-z = lambda n, hi: torch.from_numpy(np.clip(rng.zipf(1.05, size=n), 1, hi).astype(np.int64)).cuda()
-uf, pf, uid, iid = torch.randn(B, FD).cuda(), torch.randn(B, FD).cuda(), z(B, NU), z(B, NI)
 for _ in range(3):
-    loss = tr.train_step(uf, pf, None, {"user_id": uid}, {"item_id": iid})
+    loss = tr.train_step(*args)
 torch.cuda.synchronize()
 print("ok", float(loss))
