@@ -100,10 +100,6 @@ struct MfArgs {
   float* dbeta;
 };
 
-// piece products in the order they are issued (smallest first) and the accumulator class they add into
-//   class 0 = small (m.m, l.h, h.l), 1 = mid (m.h, h.m), 2 = h.h (alternating between two accumulators per chunk)
-__device__ __constant__ int MF_PROD[6][3] = {{1, 1, 0}, {2, 0, 0}, {0, 2, 0}, {1, 0, 1}, {0, 1, 1}, {0, 0, 2}};
-
 __device__ __forceinline__ void mf_store_unit(uint8_t* base, int piece_stride, int np, int r, int ch, const float (&v)[8]) {
   uint32_t hw[4], mw[4], lw[4];
 #pragma unroll
@@ -126,37 +122,54 @@ __device__ __forceinline__ void mf_store_unit(uint8_t* base, int piece_stride, i
   if (np >= 3) *reinterpret_cast<uint4*>(p + 2 * piece_stride) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }
 
-// rows x 64 operand tile: f(r, c0, v) yields the 8 contraction elements c0..c0+7 of tile row r.
+// rows x 64 operand tile in two phases per pair of units, so that the global loads of both units are in flight before
+// any of them is consumed: ld(r, c0, raw) issues UNCONDITIONAL loads (indices clamped into range), tf(r, c0, raw, v)
+// turns them into the 8 contraction elements c0..c0+7 of tile row r (zero outside the matrix).  With loads inside
+// bounds-checked branches the compiler serialised them: 8 dependent L2 round trips per unit.
 // trans = 0: consecutive threads walk along the contraction (contiguous in the source); 1: along the tile rows.
-template <class F>
-__device__ __forceinline__ void mf_load_tile(uint8_t* base, int piece_stride, int np, int rows, int trans, F f) {
+template <int NRAW, class L, class T>
+__device__ __forceinline__ void mf_load_tile(uint8_t* base, int piece_stride, int np, int rows, int trans, L ld, T tf) {
   const int units = rows * 8;
-#pragma unroll 2
-  for (int u = threadIdx.x; u < units; u += MF_THREADS) {
-    int r, ch;
+  for (int u0 = threadIdx.x; u0 < units; u0 += 2 * MF_THREADS) {
+    const bool has1 = u0 + MF_THREADS < units;
+    const int u1 = has1 ? u0 + MF_THREADS : u0;
+    int r0, ch0, r1, ch1;
     if (trans) {
-      ch = u / rows;
-      r = u - ch * rows;
+      ch0 = u0 / rows, r0 = u0 - ch0 * rows;
+      ch1 = u1 / rows, r1 = u1 - ch1 * rows;
     } else {
-      r = u >> 3;
-      ch = u & 7;
+      r0 = u0 >> 3, ch0 = u0 & 7;
+      r1 = u1 >> 3, ch1 = u1 & 7;
     }
+    float raw0[NRAW], raw1[NRAW];
+    ld(r0, ch0 * 8, raw0);
+    ld(r1, ch1 * 8, raw1);
     float v[8];
-    f(r, ch * 8, v);
-    mf_store_unit(base, piece_stride, np, r, ch, v);
+    tf(r0, ch0 * 8, raw0, v);
+    mf_store_unit(base, piece_stride, np, r0, ch0, v);
+    if (has1) {
+      tf(r1, ch1 * 8, raw1, v);
+      mf_store_unit(base, piece_stride, np, r1, ch1, v);
+    }
   }
 }
 
-// 8 consecutive floats of a row (zero beyond `limit`), 128-bit loads when the address allows
-__device__ __forceinline__ void mf_ld8(const float* row, int c, int limit, float (&v)[8]) {
-  if (c + 8 <= limit && ((reinterpret_cast<uintptr_t>(row + c) & 15) == 0)) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(row + c));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(row + c + 4));
+// 8 consecutive floats row[c..c+7], unconditional: vec (row base 16-byte aligned, limit % 8 == 0) -> two 128-bit loads of
+// a unit that is entirely inside or entirely outside [0, limit) (outside: unit 0 is loaded and ignored); otherwise eight
+// scalar loads with clamped indices.  The caller zeroes what lies outside.
+__device__ __forceinline__ void mf_ld8(const float* row, int c, int limit, bool vec, float* v) {
+  if (vec) {
+    const int cc = c < limit ? c : 0;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(row + cc));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(row + cc + 4));
     v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (c + j < limit) ? __ldg(row + c + j) : 0.f;
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(row + (c + j < limit ? c + j : limit - 1));
   }
+}
+__device__ __forceinline__ bool mf_vec_ok(const float* base, long long ld, int limit) {
+  return ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && ((ld & 3) == 0) && ((limit & 7) == 0);
 }
 
 struct MfStats {       // per-feature constants of a block in shared memory
@@ -194,48 +207,11 @@ __device__ __forceinline__ float mf_act(int act, float z) { return RELU ? fmaxf(
 template <bool RELU>
 __device__ __forceinline__ float mf_act_grad(int act, float z) { return RELU ? (z > 0.f ? 1.f : 0.f) : act_grad_slow(act, z); }
 
-// mean / invstd of a block from its fp64 sums (training) or its running statistics (eval); the designated CTA also
-// applies nn.BatchNorm1d's momentum update (unbiased variance) and counts the batch.
-__device__ __forceinline__ void mf_block_stats(const MfBlock& k, float* s_mean, float* s_invstd, bool designated) {
-  for (int h = threadIdx.x; h < k.H; h += MF_THREADS) {
-    float m, is;
-    if (k.training) {
-      const double n = (double)k.B_stat;
-      const double mm = k.sums[h] / n;
-      double var = k.sums[k.H + h] / n - mm * mm;
-      if (var < 0.0) var = 0.0;
-      m = (float)mm;
-      is = (float)(1.0 / sqrt(var + (double)k.eps));
-      if (designated && k.update_running && k.running_mean) {
-        const double unbiased = k.B_stat > 1 ? var * n / (n - 1.0) : var;
-        k.running_mean[h] = (float)((1.0 - k.momentum) * (double)k.running_mean[h] + (double)k.momentum * mm);
-        k.running_var[h] = (float)((1.0 - k.momentum) * (double)k.running_var[h] + (double)k.momentum * unbiased);
-      }
-    } else {
-      m = k.running_mean[h];
-      is = 1.0f / sqrtf(k.running_var[h] + k.eps);
-    }
-    s_mean[h] = m;
-    s_invstd[h] = is;
-  }
-  if (designated && k.training && k.update_running && k.nbt && threadIdx.x == 0) *k.nbt += 1;
-}
-
 // y = Dropout(BN(act(z)))[b, h]:  act(z) * scale[h] + shift[h], times the keep-scale
 template <bool RELU, bool DROP>
 __device__ __forceinline__ float mf_fwd_val(const MfBlock& k, const MfStats& s, const MfDrop& d, long long b, int h, float zz) {
   const float y = fmaf(mf_act<RELU>(k.act, zz), s.p2[h], s.p3[h]);
   return y * mf_keep<DROP>(d, b, h);
-}
-template <bool RELU, bool DROP>
-__device__ __forceinline__ void mf_fwd8(const MfBlock& k, const MfStats& s, const MfDrop& d, long long b, int h0, float (&v)[8]) {
-  mf_ld8(k.z + b * k.ldz, h0, k.H, v);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int h = h0 + j < k.H ? h0 + j : 0;
-    const float y = mf_fwd_val<RELU, DROP>(k, s, d, b, h, v[j]);
-    v[j] = (h0 + j < k.H) ? y : 0.f;
-  }
 }
 // dz[b, n] = act'(z) * gamma*invstd * (g - sum(g)/n - xhat * sum(g*xhat)/n), g = dy * keep-scale  (training)
 template <bool RELU, bool DROP>
@@ -265,6 +241,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const MfArgs a
   uint64_t* acc_bar = bars + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
   float* s_part = reinterpret_cast<float*>(bars + 4);              // [MF_EPI][128] row partials (normalise / db)
+  float* s_bias = s_part + MF_EPI * 128;                           // [128] bias of this tile's out features (forward)
 
   MF_STAMP(0);
   if (warp == 1 && lane == 0) {
@@ -276,35 +253,77 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const MfArgs a
   if (warp == 2) tmem_alloc(tmem_slot, 512);
 
   // ---------------------------------------------------------------- per-feature constants of the blocks involved
+  // (one pass per block: all global loads of a feature are issued before the fp64 arithmetic that needs them)
   const bool cta0 = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   MfDrop dlo{}, dow{};
   if (a.has_lower) {
-    dlo = mf_drop(a.lower);
-    mf_block_stats(a.lower, lo.mean, lo.invstd, cta0 && MODE == 0);
-  }
-  if (a.has_own) {
-    dow = mf_drop(a.own);
-    mf_block_stats(a.own, ow.mean, ow.invstd, false);
-  }
-  __syncthreads();
-  if (a.has_lower) {
-    for (int h = threadIdx.x; h < a.lower.H; h += MF_THREADS) {
-      const float sc = lo.invstd[h] * __ldg(a.lower.gamma + h);
+    const MfBlock& k = a.lower;
+    dlo = mf_drop(k);
+    const bool upd = cta0 && MODE == 0 && k.training && k.update_running && k.running_mean;
+    for (int h = threadIdx.x; h < k.H; h += MF_THREADS) {
+      const float gam = __ldg(k.gamma + h), bet = __ldg(k.beta + h);
+      float m, is;
+      if (k.training) {
+        const double s1 = k.sums[h], s2 = k.sums[k.H + h];
+        const double n = (double)k.B_stat;
+        const double mm = s1 / n;
+        double var = s2 / n - mm * mm;
+        if (var < 0.0) var = 0.0;
+        m = (float)mm;
+        is = (float)(1.0 / sqrt(var + (double)k.eps));
+        if (upd) {   // nn.BatchNorm1d's momentum update with the unbiased variance, once per forward
+          const double unbiased = k.B_stat > 1 ? var * n / (n - 1.0) : var;
+          k.running_mean[h] = (float)((1.0 - k.momentum) * (double)k.running_mean[h] + (double)k.momentum * mm);
+          k.running_var[h] = (float)((1.0 - k.momentum) * (double)k.running_var[h] + (double)k.momentum * unbiased);
+        }
+      } else {
+        m = k.running_mean[h];
+        is = 1.0f / sqrtf(k.running_var[h] + k.eps);
+      }
+      lo.mean[h] = m;
+      lo.invstd[h] = is;
+      const float sc = is * gam;
       lo.p2[h] = sc;
-      lo.p3[h] = __ldg(a.lower.beta + h) - lo.mean[h] * sc;
+      lo.p3[h] = bet - m * sc;
     }
+    if (upd && k.nbt && threadIdx.x == 0) *k.nbt += 1;
   }
   if (a.has_own) {
-    const double inv_n = 1.0 / (double)a.own.B_stat;
-    for (int n = threadIdx.x; n < a.own.H; n += MF_THREADS) {
-      ow.p2[n] = __ldg(a.own.gamma + n) * ow.invstd[n];
-      ow.p3[n] = a.own.training ? (float)(a.own_bsums[n] * inv_n) : 0.f;
-      ow.p4[n] = a.own.training ? (float)(a.own_bsums[a.own.H + n] * inv_n) : 0.f;
-      if (MODE == 2 && cta0 && a.dgamma && a.own_bsums_local) {   // BatchNorm affine gradients: dbeta = sum g, dgamma = sum g*xhat
-        a.dbeta[n] += (float)a.own_bsums_local[n];
-        a.dgamma[n] += (float)a.own_bsums_local[a.own.H + n];
+    const MfBlock& k = a.own;
+    dow = mf_drop(k);
+    const double inv_n = 1.0 / (double)k.B_stat;
+    const bool affine = MODE == 2 && cta0 && a.dgamma && a.own_bsums_local;
+    for (int n = threadIdx.x; n < k.H; n += MF_THREADS) {
+      const float gam = __ldg(k.gamma + n);
+      double b1 = 0.0, b2 = 0.0, l1 = 0.0, l2 = 0.0;
+      if (k.training) b1 = a.own_bsums[n], b2 = a.own_bsums[k.H + n];
+      if (affine) l1 = a.own_bsums_local[n], l2 = a.own_bsums_local[k.H + n];
+      float m, is;
+      if (k.training) {
+        const double nn = (double)k.B_stat;
+        const double mm = k.sums[n] / nn;
+        double var = k.sums[k.H + n] / nn - mm * mm;
+        if (var < 0.0) var = 0.0;
+        m = (float)mm;
+        is = (float)(1.0 / sqrt(var + (double)k.eps));
+      } else {
+        m = k.running_mean[n];
+        is = 1.0f / sqrtf(k.running_var[n] + k.eps);
+      }
+      ow.mean[n] = m;
+      ow.invstd[n] = is;
+      ow.p2[n] = gam * is;
+      ow.p3[n] = (float)(b1 * inv_n);      // eval mode: 0
+      ow.p4[n] = (float)(b2 * inv_n);
+      if (affine) {                        // BatchNorm affine gradients: dbeta = sum g, dgamma = sum g*xhat
+        a.dbeta[n] += (float)l1;
+        a.dgamma[n] += (float)l2;
       }
     }
+  }
+  if (MODE == 0 && threadIdx.x < 128) {
+    const int n = blockIdx.y * NT + threadIdx.x;
+    s_bias[threadIdx.x] = (a.bias != nullptr && n < a.N) ? __ldg(a.bias + n) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -346,85 +365,112 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const MfArgs a
     uint8_t* bbase = abase + np * a_piece;
     if constexpr (MODE == 0) {
       // A[r, c] = input[m0 + r, c0 + c]
-      mf_load_tile(abase, a_piece, np, 128, 0, [&](int r, int c, float (&v)[8]) {
-        const long long b = m0 + r;
-        if (b >= a.B) {
+      const float* src = a.has_lower ? a.lower.z : a.x;
+      const long long lds = a.has_lower ? a.lower.ldz : a.ldx;
+      const bool va = mf_vec_ok(src, lds, a.K), vb = mf_vec_ok(a.w, a.ldw, a.K);
+      mf_load_tile<8>(abase, a_piece, np, 128, 0,
+          [&](int r, int c, float* raw) {
+            const long long b = m0 + r < a.B ? m0 + r : a.B - 1;
+            mf_ld8(src + b * lds, c0 + c, a.K, va, raw);
+          },
+          [&](int r, int c, const float* raw, float (&v)[8]) {
+            const long long b = m0 + r;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = 0.f;
-        } else if (a.has_lower) {
-          mf_fwd8<RELU, DROP>(a.lower, lo, dlo, b, c0 + c, v);
-        } else {
-          mf_ld8(a.x + b * a.ldx, c0 + c, a.K, v);
-        }
-      });
+            for (int j = 0; j < 8; ++j) {
+              const int k = c0 + c + j;
+              const bool ok = b < a.B && k < a.K;
+              const float y = a.has_lower ? mf_fwd_val<RELU, DROP>(a.lower, lo, dlo, b, ok ? k : 0, raw[j]) : raw[j];
+              v[j] = ok ? y : 0.f;
+            }
+          });
       // B[r, c] = W[n0 + r, c0 + c]
-      mf_load_tile(bbase, b_piece, np, NT, 0, [&](int r, int c, float (&v)[8]) {
-        const int n = n0 + r;
-        if (n >= a.N) {
+      mf_load_tile<8>(bbase, b_piece, np, NT, 0,
+          [&](int r, int c, float* raw) {
+            const int n = n0 + r < a.N ? n0 + r : a.N - 1;
+            mf_ld8(a.w + (long long)n * a.ldw, c0 + c, a.K, vb, raw);
+          },
+          [&](int r, int c, const float* raw, float (&v)[8]) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = 0.f;
-        } else {
-          mf_ld8(a.w + (long long)n * a.ldw, c0 + c, a.K, v);
-        }
-      });
+            for (int j = 0; j < 8; ++j) v[j] = (n0 + r < a.N && c0 + c + j < a.K) ? raw[j] : 0.f;
+          });
     } else if constexpr (MODE == 1) {
       // A[r, c] = dz[m0 + r, c0 + c]
-      mf_load_tile(abase, a_piece, np, 128, 0, [&](int r, int c, float (&v)[8]) {
-        const long long b = m0 + r;
-        if (b >= a.B) {
+      const bool vd = mf_vec_ok(a.dy, a.lddy, a.N), vz = a.has_own && mf_vec_ok(a.own.z, a.own.ldz, a.N);
+      mf_load_tile<16>(abase, a_piece, np, 128, 0,
+          [&](int r, int c, float* raw) {
+            const long long b = m0 + r < a.B ? m0 + r : a.B - 1;
+            mf_ld8(a.dy + b * a.lddy, c0 + c, a.N, vd, raw);
+            if (a.has_own) mf_ld8(a.own.z + b * a.own.ldz, c0 + c, a.N, vz, raw + 8);
+          },
+          [&](int r, int c, const float* raw, float (&v)[8]) {
+            const long long b = m0 + r;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = 0.f;
-          return;
-        }
-        mf_ld8(a.dy + b * a.lddy, c0 + c, a.N, v);
-        if (a.has_own) {
-          float zz[8];
-          mf_ld8(a.own.z + b * a.own.ldz, c0 + c, a.N, zz);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int n = c0 + c + j < a.N ? c0 + c + j : 0;
-            const float d = mf_bwd1<RELU, DROP>(a.own, ow, dow, v[j], zz[j], b, n);
-            v[j] = (c0 + c + j < a.N) ? d : 0.f;
-          }
-        }
-      });
+            for (int j = 0; j < 8; ++j) {
+              const int n = c0 + c + j;
+              const bool ok = b < a.B && n < a.N;
+              const float d = a.has_own ? mf_bwd1<RELU, DROP>(a.own, ow, dow, raw[j], raw[8 + j], b, ok ? n : 0) : raw[j];
+              v[j] = ok ? d : 0.f;
+            }
+          });
       // B[r, c] = W[c0 + c, n0 + r]   (transposed read: consecutive threads -> consecutive in-features)
-      mf_load_tile(bbase, b_piece, np, NT, 1, [&](int r, int c, float (&v)[8]) {
-        const int k = n0 + r;
+      mf_load_tile<8>(bbase, b_piece, np, NT, 1,
+          [&](int r, int c, float* raw) {
+            const int k = n0 + r < a.K ? n0 + r : a.K - 1;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int n = c0 + c + j;
-          v[j] = (k < a.K && n < a.N) ? __ldg(a.w + (long long)n * a.ldw + k) : 0.f;
-        }
-      });
+            for (int j = 0; j < 8; ++j) {
+              const int n = c0 + c + j < a.N ? c0 + c + j : a.N - 1;
+              raw[j] = __ldg(a.w + (long long)n * a.ldw + k);
+            }
+          },
+          [&](int r, int c, const float* raw, float (&v)[8]) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (n0 + r < a.K && c0 + c + j < a.N) ? raw[j] : 0.f;
+          });
     } else {
       // A[r, c] = dz[c0 + c, m0 + r]   (out features along the tile rows, batch along the contraction)
-      mf_load_tile(abase, a_piece, np, 128, 1, [&](int r, int c, float (&v)[8]) {
-        const int n = m0 + r;
+      mf_load_tile<16>(abase, a_piece, np, 128, 1,
+          [&](int r, int c, float* raw) {
+            const int n = m0 + r < a.N ? m0 + r : a.N - 1;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const long long b = c0 + c + j;
-          float d = 0.f;
-          if (n < a.N && b < a.B) {
-            d = __ldg(a.dy + b * a.lddy + n);
-            if (a.has_own) d = mf_bwd1<RELU, DROP>(a.own, ow, dow, d, __ldg(a.own.z + b * a.own.ldz + n), b, n);
-          }
-          v[j] = d;
-          dbacc += d;
-        }
-      });
+            for (int j = 0; j < 8; ++j) {
+              const long long b = c0 + c + j < a.B ? c0 + c + j : a.B - 1;
+              raw[j] = __ldg(a.dy + b * a.lddy + n);
+              if (a.has_own) raw[8 + j] = __ldg(a.own.z + b * a.own.ldz + n);
+            }
+          },
+          [&](int r, int c, const float* raw, float (&v)[8]) {
+            const int n = m0 + r;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const long long b = c0 + c + j;
+              const bool ok = n < a.N && b < a.B;
+              const float d = a.has_own ? mf_bwd1<RELU, DROP>(a.own, ow, dow, raw[j], raw[8 + j], b, ok ? n : 0) : raw[j];
+              v[j] = ok ? d : 0.f;
+              dbacc += v[j];
+            }
+          });
       // B[r, c] = input[c0 + c, n0 + r]
-      mf_load_tile(bbase, b_piece, np, NT, 1, [&](int r, int c, float (&v)[8]) {
-        const int k = n0 + r;
+      const float* src = a.has_lower ? a.lower.z : a.x;
+      const long long lds = a.has_lower ? a.lower.ldz : a.ldx;
+      mf_load_tile<8>(bbase, b_piece, np, NT, 1,
+          [&](int r, int c, float* raw) {
+            const int k = n0 + r < a.K ? n0 + r : a.K - 1;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const long long b = c0 + c + j;
-          float x = 0.f;
-          if (b < a.B && k < a.K)
-            x = a.has_lower ? mf_fwd_val<RELU, DROP>(a.lower, lo, dlo, b, k, __ldg(a.lower.z + b * a.lower.ldz + k)) : __ldg(a.x + b * a.ldx + k);
-          v[j] = x;
-        }
-      });
+            for (int j = 0; j < 8; ++j) {
+              const long long b = c0 + c + j < a.B ? c0 + c + j : a.B - 1;
+              raw[j] = __ldg(src + b * lds + k);
+            }
+          },
+          [&](int r, int c, const float* raw, float (&v)[8]) {
+            const int k = n0 + r;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const long long b = c0 + c + j;
+              const bool ok = b < a.B && k < a.K;
+              const float x = a.has_lower ? mf_fwd_val<RELU, DROP>(a.lower, lo, dlo, b, ok ? k : 0, raw[j]) : raw[j];
+              v[j] = ok ? x : 0.f;
+            }
+          });
     }
     if (ci < 4) MF_STAMP(2 + 3 * ci);
     fence_proxy_async_smem();   // generic-proxy stores above -> visible to the tensor core's async-proxy reads
@@ -432,23 +478,32 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const MfArgs a
     if (ci < 4) MF_STAMP(3 + 3 * ci);
     if (warp == 0) {
       tc_fence_after();
-      const int nprod = np == 1 ? 1 : (np == 2 ? 3 : 6);
       uint32_t u = used;
       if (elect_one()) {
         const uint32_t a_lo = smem_lo + ((st * stage_bytes) >> 4);
         const uint32_t b_lo = a_lo + ((np * a_piece) >> 4);
-        for (int pr = 6 - nprod; pr < 6; ++pr) {
-          const int pa = MF_PROD[pr][0], pb = MF_PROD[pr][1], cls = MF_PROD[pr][2];
-          const int acc = cls == 2 ? 2 + (ci & 1) : cls;
-          const uint64_t a_desc = desc_base + (a_lo + ((pa * a_piece) >> 4));
-          const uint64_t b_desc = desc_base + (b_lo + ((pb * b_piece) >> 4));
+        const uint32_t ap = a_piece >> 4, bp = b_piece >> 4;
+        // piece products, smallest first: class 0 = small (m.m, l.h, h.l), 1 = mid (m.h, h.m), 2/3 = h.h (even / odd chunks)
+        auto product = [&](int pa, int pb, int acc) {
+          const uint64_t a_desc = desc_base + (a_lo + pa * ap);
+          const uint64_t b_desc = desc_base + (b_lo + pb * bp);
           const uint32_t d_addr = tmem_base + acc * 128;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             umma_bf16(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc, (u >> acc) & 1u);
             u |= 1u << acc;
           }
+        };
+        if (np == 3) {
+          product(1, 1, 0);
+          product(2, 0, 0);
+          product(0, 2, 0);
         }
+        if (np >= 2) {
+          product(1, 0, 1);
+          product(0, 1, 1);
+        }
+        product(0, 0, 2 + (ci & 1));
         umma_commit(&free_bar[st]);
         if (ci == nchunks - 1) umma_commit(acc_bar);
       }
@@ -496,10 +551,28 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const MfArgs a
     };
     float* stage0 = reinterpret_cast<float*>(smem);
     float* stage1 = stage0 + 128 * (NT + 1);
+    // column sums of a staged [128, NT] tile: thread = (column, which array, quarter of the rows); fp32 partials over 32
+    // rows in four independent chains, merged in fp64 by the atomics (one per thread)
+    auto column_sums = [&](const float* sa, const float* sb, bool square_b, double* dst, int limit) {
+      const int col = threadIdx.x & 127, part = threadIdx.x >> 7, which = part & 1, r0 = (part >> 1) * (256 / MF_EPI);
+      if (col < NT && n0 + col < limit) {
+        const float* sg = which ? sb : sa;
+        float p[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int r = 0; r < 256 / MF_EPI; r += 4) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float v = sg[(r0 + r + q) * (NT + 1) + col];
+            p[q] += (which && square_b) ? v * v : v;
+          }
+        }
+        atomicAdd(dst + which * limit + n0 + col, (double)p[0] + (double)p[1] + (double)p[2] + (double)p[3]);
+      }
+    };
     if constexpr (MODE == 0) {
       const long long b = m0 + row_l;
       const bool row_ok = b < a.B;
-      float* orow = a.out + b * a.ldo;
+      float* orow = a.out + (row_ok ? b : 0) * a.ldo;
       const bool vec_ok = ((a.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
       if (a.normalize) {
         // F.normalize(p=2, eps=1e-12) on rows that live in one tile (N <= NT)
@@ -509,11 +582,8 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const MfArgs a
           load16(g, o);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int n = n0 + g * 16 + j;
-            if (n < a.N) {
-              const float v = o[j] + (a.bias ? __ldg(a.bias + n) : 0.f);
-              ss = fmaf(v, v, ss);
-            }
+            const float v = (n0 + g * 16 + j < a.N) ? o[j] + s_bias[g * 16 + j] : 0.f;
+            ss = fmaf(v, v, ss);
           }
         }
         s_part[half * 128 + row_l] = ss;
@@ -526,13 +596,10 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const MfArgs a
         for (int g = half; g < ngroups; g += MF_EPI) {
           float o[16];
           load16(g, o);
+          const int nb = n0 + g * 16;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = n0 + g * 16 + j;
-            o[j] = n < a.N ? (o[j] + (a.bias ? __ldg(a.bias + n) : 0.f)) / nrm : 0.f;
-          }
+          for (int j = 0; j < 16; ++j) o[j] = (o[j] + s_bias[g * 16 + j]) / nrm;
           if (row_ok) {
-            const int nb = n0 + g * 16;
             if (vec_ok && nb + 16 <= a.N) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(orow + nb + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
@@ -548,12 +615,12 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const MfArgs a
         for (int g = half; g < ngroups; g += MF_EPI) {
           float o[16];
           load16(g, o);
+          if (g == half) MF_STAMP(18);
           const int nb = n0 + g * 16;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int n = nb + j;
-            o[j] = (n < a.N && row_ok) ? o[j] + (a.bias ? __ldg(a.bias + n) : 0.f) : 0.f;
-            if (stats) stage0[row_l * (NT + 1) + g * 16 + j] = (n < a.N && row_ok) ? mf_act<RELU>(a.out_act, o[j]) : 0.f;
+            o[j] += s_bias[g * 16 + j];
+            if (stats) stage0[row_l * (NT + 1) + g * 16 + j] = (nb + j < a.N && row_ok) ? mf_act<RELU>(a.out_act, o[j]) : 0.f;
           }
           if (row_ok) {
             if (vec_ok && nb + 16 <= a.N) {
@@ -566,30 +633,32 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const MfArgs a
             }
           }
         }
+        MF_STAMP(19);
         if (stats) {
           tc_fence_before();
           __syncthreads();
-          const int col = threadIdx.x & 127, part = threadIdx.x >> 7, which = part & 1, r0 = (part >> 1) * (256 / MF_EPI);
-          if (col < NT && n0 + col < a.N) {
-            double s = 0.0;
-            for (int r = r0; r < r0 + 256 / MF_EPI; ++r) {
-              const float v = stage0[r * (NT + 1) + col];
-              s += which ? (double)v * (double)v : (double)v;
-            }
-            atomicAdd(a.out_sums + which * a.N + n0 + col, s);
-          }
+          MF_STAMP(20);
+          column_sums(stage0, stage0, true, a.out_sums, a.N);
         }
       }
     } else if constexpr (MODE == 1) {
       const long long b = m0 + row_l;
       const bool row_ok = b < a.B;
+      const long long bc = row_ok ? b : a.B - 1;
       const bool sums = a.out_sums != nullptr;   // backward sums of the block below: sum g, sum g*xhat
       const bool vec_ok = ((a.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
-      float* orow = a.out + b * a.ldo;
+      const bool vz = sums && mf_vec_ok(a.lower.z, a.lower.ldz, a.K);
+      float* orow = a.out + bc * a.ldo;
       for (int g = half; g < ngroups; g += MF_EPI) {
+        const int kb = n0 + g * 16;
+        float zz[16];
+        if (sums) {   // issued before the TMEM read: the loads fly while the accumulators are fetched
+          mf_ld8(a.lower.z + bc * a.lower.ldz, kb, a.K, vz, zz);
+          mf_ld8(a.lower.z + bc * a.lower.ldz, kb + 8, a.K, vz, zz + 8);
+        }
         float o[16];
         load16(g, o);
-        const int kb = n0 + g * 16;
+        if (g == half) MF_STAMP(18);
         if (row_ok) {
           if (vec_ok && kb + 16 <= a.K) {
 #pragma unroll
@@ -601,34 +670,23 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const MfArgs a
           }
         }
         if (sums) {
-          float zz[16];
-          if (row_ok) {
-            mf_ld8(a.lower.z + b * a.lower.ldz, kb, a.K, *reinterpret_cast<float(*)[8]>(&zz[0]));
-            mf_ld8(a.lower.z + b * a.lower.ldz, kb + 8, a.K, *reinterpret_cast<float(*)[8]>(&zz[8]));
-          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int k = kb + j;
-            float gg = 0.f, gx = 0.f;
-            if (k < a.K && row_ok) {
-              gg = o[j] * mf_keep<DROP>(dlo, b, k);
-              gx = gg * ((mf_act<RELU>(a.lower.act, zz[j]) - lo.mean[k]) * lo.invstd[k]);
-            }
-            stage0[row_l * (NT + 1) + g * 16 + j] = gg;
-            stage1[row_l * (NT + 1) + g * 16 + j] = gx;
+            const bool ok = kb + j < a.K && row_ok;
+            const int k = ok ? kb + j : 0;
+            const float gg = o[j] * mf_keep<DROP>(dlo, bc, k);
+            const float gx = gg * ((mf_act<RELU>(a.lower.act, zz[j]) - lo.mean[k]) * lo.invstd[k]);
+            stage0[row_l * (NT + 1) + g * 16 + j] = ok ? gg : 0.f;
+            stage1[row_l * (NT + 1) + g * 16 + j] = ok ? gx : 0.f;
           }
         }
       }
+      MF_STAMP(19);
       if (sums) {
         tc_fence_before();
         __syncthreads();
-        const int col = threadIdx.x & 127, part = threadIdx.x >> 7, which = part & 1, r0 = (part >> 1) * (256 / MF_EPI);
-        if (col < NT && n0 + col < a.K) {
-          const float* sg = which ? stage1 : stage0;
-          double s = 0.0;
-          for (int r = r0; r < r0 + 256 / MF_EPI; ++r) s += (double)sg[r * (NT + 1) + col];
-          atomicAdd(a.out_sums + which * a.K + n0 + col, s);
-        }
+        MF_STAMP(20);
+        column_sums(stage0, stage1, false, a.out_sums, a.K);
       }
     } else {
       // dW partial of this CTA: staged through shared memory so that one warp adds one row segment with coalesced
@@ -679,7 +737,7 @@ static int mf_block(MfBlock& d, const b200rec_bn_block* s, const char* what) {
 static int mf_launch(MfArgs& a, dim3 grid, cudaStream_t st) {
   const int stage_region = 2 * a.np * (128 * 128 + a.NT * 128);
   const int staging = 2 * 128 * (a.NT + 1) * 4;
-  const int smem = 1024 + (stage_region > staging ? stage_region : staging) + 9 * MF_MAXH * 4 + 64 + MF_EPI * 128 * 4;
+  const int smem = 1024 + (stage_region > staging ? stage_region : staging) + 9 * MF_MAXH * 4 + 64 + MF_EPI * 128 * 4 + 128 * 4;
   if (smem > MF_SMEM_LIMIT) return fail("mlp_fused: %d bytes of shared memory needed", smem);
   // kernel variants: ReLU everywhere (inline, branch-free element loops) or any activation; dropout streams or none
   const bool relu = (!a.has_lower || a.lower.act == 0) && (!a.has_own || a.own.act == 0) && (a.mode != 0 || !a.out_sums || a.out_act == 0);

@@ -155,6 +155,19 @@ def _grad_target(p: torch.Tensor, needed: bool):
     return buf, buf
 
 
+_WGRAD_STREAMS = {}
+
+
+def _wgrad_stream(device: torch.device) -> torch.cuda.Stream:
+    """One side stream per (device, ambient stream): two towers whose backward passes already run on different streams
+    each get their own."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    st = _WGRAD_STREAMS.get(key)
+    if st is None:
+        st = _WGRAD_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
+
+
 class MLPSpec:
     """Non-tensor description of one tower MLP call for TowerMLPFn (activation, mode, dropout streams, BN buffers)."""
 
@@ -222,6 +235,12 @@ class TowerMLPFn(Function):
         dy = K.normalize_bwd(_c32(de), e, norms)                      # gradient wrt the last Linear's output
         local = [None] * L
         dx0 = None
+        # The weight gradient of a layer and its data gradient both start from dy; only the data gradients form a chain.
+        # Weight-gradient launches go to a side stream (fork after dy is ready, join before returning) so the chain
+        # dgrad(L) -> dgrad(L-1) -> ... is the critical path and each wgrad fills SMs the 64-CTA dgrad leaves idle.
+        main = torch.cuda.current_stream()
+        side = _wgrad_stream(dev) if os.environ.get("B200REC_OVERLAP", "1") != "0" else None
+        keep = [dy]
         for l in range(L, -1, -1):
             own = blocks[l] if l < L else None
             own_b = bsum[l] if l < L else None
@@ -240,7 +259,13 @@ class TowerMLPFn(Function):
                 if (dgamma is None) != (dbeta is None):               # the kernel writes both or none
                     dgamma = dgamma if dgamma is not None else torch.zeros_like(params[base + 2])
                     dbeta = dbeta if dbeta is not None else torch.zeros_like(params[base + 3])
-            K.mlp_wgrad(dy, own, own_b, local[l] if l < L else None, x if l == 0 else None, lower, npb, dw, db, dgamma, dbeta)
+            if side is not None and dp is None:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    K.mlp_wgrad(dy, own, own_b, None, x if l == 0 else None, lower, npb, dw, db, dgamma, dbeta)
+            else:
+                K.mlp_wgrad(dy, own, own_b, local[l] if l < L else None, x if l == 0 else None, lower, npb, dw, db, dgamma,
+                            dbeta)
             if l > 0 or need[0]:
                 k_in = w.shape[1]
                 dx = torch.empty((B, k_in), dtype=torch.float32, device=dev)
@@ -250,8 +275,11 @@ class TowerMLPFn(Function):
                     local[l - 1] = bsum[l - 1].clone()               # dgamma / dbeta add this replica's part only
                     dp.reduce_sums(bsum[l - 1])
                 dy = dx
+                keep.append(dx)
                 if l == 0:
                     dx0 = dx
+        if side is not None and dp is None:
+            main.wait_stream(side)
         return (dx0, None, *grads)
 
 

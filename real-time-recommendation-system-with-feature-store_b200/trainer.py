@@ -6,6 +6,7 @@ are already on the device — what bench.py times."""
 from __future__ import annotations
 
 import logging
+import os
 import time
 from pathlib import Path
 from typing import Any, Dict, List, Optional
@@ -306,7 +307,20 @@ class TwoTowerTrainer:
         dp = getattr(model, "dp", None)
         self.optimizer.dp = dp
         self.optimizer.zero_grad()
-        u = model.get_user_embeddings({"numerical": user_features, "categorical": user_categorical or {}})
+        # The two towers are independent until the loss: the user tower runs on a side stream next to the item tower
+        # (autograd replays each tower's backward on the stream of its forward, so the backward overlaps the same way;
+        # every launch of a tower fills less than one wave of the 148 SMs).  Not under data parallel: the BatchNorm
+        # all-reduces of both towers would be issued on one communicator from two streams.
+        overlap = dp is None and os.environ.get("B200REC_OVERLAP", "1") != "0"
+        main = torch.cuda.current_stream()
+        if overlap:
+            side = self._side_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                u = model.get_user_embeddings({"numerical": user_features, "categorical": user_categorical or {}})
+            u.record_stream(main)
+        else:
+            u = model.get_user_embeddings({"numerical": user_features, "categorical": user_categorical or {}})
         p = model.get_item_embeddings({"numerical": pos_item_features, "categorical": item_categorical or {}})
         if neg_item_features is not None:
             batch_size, num_neg, feat_dim = neg_item_features.shape
@@ -318,9 +332,19 @@ class TwoTowerTrainer:
             loss = 0.7 * explicit_loss + 0.3 * in_batch_loss
         else:
             loss = model.in_batch_negative_loss(u, p)
+        if overlap:
+            main.wait_stream(side)       # the loss kernels (main stream) read u
         loss.backward()
+        if overlap:
+            main.wait_stream(side)       # the user tower's gradients were accumulated on the side stream
         self.optimizer.step()
         return dp.global_loss(loss) if dp is not None else loss.detach()
+
+    def _side_stream(self) -> torch.cuda.Stream:
+        st = getattr(self, "_side", None)
+        if st is None:
+            st = self._side = torch.cuda.Stream(device=self.device)
+        return st
 
     def train_epoch(self, epoch: int) -> float:
         self.model.train()

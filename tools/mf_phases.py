@@ -4,7 +4,7 @@ import ctypes, sys, torch
 sys.path.insert(0, ".")
 from b200rec import kernels as K, _native as N
 from b200rec.two_tower import UserTower
-names = {0: "start", 1: "prologue done", 14: "main loop done", 15: "accumulators ready", 16: "epilogue done", 17: "dealloc"}
+names = {0: "start", 1: "prologue done", 14: "main loop done", 15: "accumulators ready", 16: "epilogue done", 17: "dealloc", 18: "first tmem ld", 19: "groups done", 20: "staged+synced"}
 for ci in range(4):
     names[2 + 3 * ci], names[3 + 3 * ci], names[4 + 3 * ci] = f"chunk{ci} loaded", f"chunk{ci} synced", f"chunk{ci} issued"
 def stamps():
@@ -36,5 +36,5 @@ for name, B, K0, hidden, E in (("cfg2 tower", 8192, 80, [128, 64], 64), ("ml1m u
     print("==", name)
     for n, s in log:
         t0 = s[0]
-        seq = sorted((v - t0, i) for i, v in enumerate(s[:18]) if v >= t0 and i in names)
+        seq = sorted((v - t0, i) for i, v in enumerate(s[:21]) if v >= t0 and i in names)
         print(n, " | ".join(f"{names[i]} {d / 1000:.1f}" for d, i in seq))
