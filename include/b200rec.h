@@ -121,6 +121,10 @@ int b200rec_embedding_sparse_grad(const int64_t* idx, int64_t B, const float* dY
  * the reference's optimizer expects. */
 int b200rec_scatter_rows(const int64_t* rows, const float* grad_rows, const int32_t* n_rows, int64_t max_rows,
                          int width, float* dense, int64_t ld, int accumulate, void* stream);
+/* dense[idx[b], :width] += dY[b, :width] (padding row and ids outside [0, table_rows) skipped): the dense gradient of
+ * nn.Embedding accumulated in place with fp32 atomics, one launch (two_tower.py:116 under autograd). */
+int b200rec_scatter_add_rows(const int64_t* idx, int64_t B, const float* dY, int64_t ld_dy, int width,
+                             int64_t padding_idx, int64_t table_rows, float* dense, int64_t ld, void* stream);
 
 /* ---------------------------------------------------------------- tower MLP pieces (csrc/tower_ops.cu)
  * act: 0 relu, 1 gelu(erf), 2 leaky_relu(0.1), 3 tanh, 4 sigmoid, 5 identity  (two_tower.py:77-86).

@@ -249,6 +249,40 @@ extern "C" int b200rec_embedding_sparse_grad(const int64_t* idx, int64_t B, cons
   return 0;
 }
 
+namespace b200 {
+// dense[idx[b], :width] += dY[b, :width] for every sample whose id is a real row (padding row and out-of-range ids
+// contribute nothing): the dense gradient nn.Embedding(sparse=False) produces, accumulated IN PLACE with fp32 atomics —
+// one warp per sample, lanes along the row, so each atomic instruction covers one contiguous 128-byte segment.  Replaces
+// sort + segment sum + scatter (14 launches) when the gradient lands in a pre-zeroed dense buffer anyway; the sorted
+// path stays for row-sparse tables, whose optimizer needs each distinct row exactly once.
+__global__ void __launch_bounds__(256)
+scatter_add_rows_kernel(const int64_t* __restrict__ idx, int64_t B, const float* __restrict__ dY, int64_t ld_dy, int width,
+                        int64_t padding_idx, int64_t table_rows, float* __restrict__ dense, int64_t ld) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += warps) {
+    const int64_t r = __ldg(idx + b);
+    if (r == padding_idx || r < 0 || r >= table_rows) continue;
+    const float* src = dY + b * ld_dy;
+    float* dst = dense + r * ld;
+    for (int c = lane; c < width; c += 32) atomicAdd(dst + c, __ldg(src + c));
+  }
+}
+}  // namespace b200
+
+extern "C" int b200rec_scatter_add_rows(const int64_t* idx, int64_t B, const float* dY, int64_t ld_dy, int width,
+                                        int64_t padding_idx, int64_t table_rows, float* dense, int64_t ld, void* stream) {
+  using namespace b200;
+  if (!idx || !dY || !dense) return fail("scatter_add_rows: null pointer");
+  if (B <= 0 || width <= 0 || table_rows <= 0) return fail("scatter_add_rows: empty input");
+  const int64_t blocks = (B + 7) / 8;
+  const int grid = (int)(blocks < (int64_t)num_sms() * 16 ? blocks : (int64_t)num_sms() * 16);
+  scatter_add_rows_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(idx, B, dY, ld_dy, width, padding_idx,
+                                                                                    table_rows, dense, ld);
+  B200_LAUNCH_OK("scatter_add_rows_kernel");
+  return 0;
+}
+
 extern "C" int b200rec_scatter_rows(const int64_t* rows, const float* grad_rows, const int32_t* n_rows,
                                     int64_t max_rows, int width, float* dense, int64_t ld, int accumulate,
                                     void* stream) {

@@ -12,8 +12,9 @@
 // tile's columns are split over several units — data parallel: 8192 local users x 65536 gathered items — the partial
 // gradients are combined with fp32 atomics into a pre-zeroed output).
 //
-// Per CTA: warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warp 2 TMEM allocator, warps 4-11 epilogue
-// (thread = TMEM lane x 32-column half of the 64-column logits tile).  Pipeline per Y tile t:
+// Per CTA: warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warp 2 TMEM allocator, warps 4-19 epilogue
+// (thread = TMEM lane x 16-column quarter of the 64-column logits tile; with 8 epilogue warps of 32 columns each the
+// exp / split / store work per tile, not the tensor core, set the pace: 2 warps per scheduler could not hide its latency).  Pipeline per Y tile t:
 //   TMA: Y operand pieces (for S) + Y^T pieces (for the gradient GEMM) -> stage t % NST            full / empty
 //   MMA: S(t+1) = X . Y(t+1)^T  (split-bf16 products h.h + m.h + h.m [+ l.h + h.l + m.m])           s_full / s_empty
 //   epi: S(t) -> G(t) pieces (h, m) in shared memory, SW128 K-major                                 g_full / g_empty
@@ -27,7 +28,8 @@
 
 namespace b200 {
 
-constexpr int IG_THREADS = 12 * 32;
+constexpr int IG_EPI_WARPS = 16;                 // epilogue warps: 4 per TMEM lane quarter, 16 logit columns each
+constexpr int IG_THREADS = (4 + IG_EPI_WARPS) * 32;
 constexpr int IG_BM = 128;        // X rows per unit
 constexpr int IG_BN = 64;         // Y rows (logit columns) per tile
 constexpr int IG_MAX_UNIT_TILES = 128;   // <= 8192 columns per unit: bounds the accumulator chains (see NACC)
@@ -122,8 +124,8 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1);
-      mbar_init(&s_empty[b], 8);
-      mbar_init(&g_full[b], 8);
+      mbar_init(&s_empty[b], IG_EPI_WARPS);
+      mbar_init(&g_full[b], IG_EPI_WARPS);
       mbar_init(&g_empty[b], 1);
     }
     mbar_init(x_full, 1);
@@ -230,7 +232,7 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
       // ---------------------------------------------------------------- epilogue: logits -> G pieces -> gradient rows
       const int ew = warp - 4;
       const int quarter = warp & 3;          // TMEM lanes 32*quarter .. +31 are accessible to this warp
-      const int half = ew >> 2;              // 32-column half of the logits tile
+      const int part = ew >> 2;              // 16-column quarter of the logits tile
       const int row_l = quarter * 32 + lane;
       const long long row_g = (long long)x_tile * IG_BM + row_l;
       const bool row_ok = row_g < sd.rows;
@@ -241,26 +243,26 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
       const long long hot = row_g + sd.dshift;   // global column of this row's positive (may fall outside [0, ycols))
       for (int t = 0; t < T; ++t) {
         const int buf = t & 1, gb = t % a.ng;
-        const long long c0 = (long long)(t_begin + t) * IG_BN + half * 32;
-        float nl_col[32];
+        const long long c0 = (long long)(t_begin + t) * IG_BN + part * 16;
+        float nl_col[16];
         if (sd.lse_by_col) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < 16; ++i) {
             const long long c = c0 + i;
             nl_col[i] = -__ldg(a.lse + (c < sd.ycols ? c : sd.ycols - 1)) * LOG2E;
           }
         }
         mbar_wait(&s_full[buf], (t >> 1) & 1);
         tc_fence_after();
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * IG_BN + half * 32, v);
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * IG_BN + part * 16, v);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[buf]);
-        float gv[32];
+        float gv[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 16; ++i) {
           const long long c = c0 + i;
           const float nl = sd.lse_by_col ? nl_col[i] : nl_row;
           const float p = exp2f(fmaf(__uint_as_float(v[i]), a.scale_log2, nl));
@@ -271,7 +273,7 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
         mbar_wait(&g_empty[gb], ((t / a.ng) & 1) ^ 1);
         uint8_t* gbase = g_smem + gb * g_bytes + row_l * 128;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < 2; ++ch) {
           uint32_t hw[4], mw[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -282,7 +284,7 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
             hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
             mw[j] = *reinterpret_cast<const uint32_t*>(&m2);
           }
-          const int pos = ((half * 4 + ch) ^ (row_l & 7)) * 16;
+          const int pos = ((part * 2 + ch) ^ (row_l & 7)) * 16;
           *reinterpret_cast<uint4*>(gbase + pos) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
           if (pg == 2) *reinterpret_cast<uint4*>(gbase + IG_BM * 128 + pos) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
         }
@@ -293,30 +295,30 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
       // gradient rows: sum the NACC accumulators with round-to-nearest adds, store (or add when the tile was split)
       mbar_wait(out_full, 0);
       tc_fence_after();
-      const int ncol = a.E / 2;   // columns of OUT per thread
+      const int ncol = a.E / 4;   // columns of OUT per thread (16 or 32)
       const int used = T < a.nacc ? T : a.nacc;
       const bool atomic = mode ? a.atomic_v != 0 : a.atomic_u != 0;
-      float* orow = sd.out + row_g * sd.ld_out + half * ncol;
+      float* orow = sd.out + row_g * sd.ld_out + part * ncol;
 #pragma unroll 1
-      for (int c = 0; c < ncol; c += 32) {
-        uint32_t o[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + OUT_COL + half * ncol + c;
-        tmem_ld_32x32(taddr, o);
+      for (int c = 0; c < ncol; c += 16) {
+        uint32_t o[16];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + OUT_COL + part * ncol + c;
+        tmem_ld_32x16(taddr, o);
         tmem_ld_wait();
         for (int ac = 1; ac < used; ++ac) {
-          uint32_t w[32];
-          tmem_ld_32x32(taddr + ac * a.E, w);
+          uint32_t w[16];
+          tmem_ld_32x16(taddr + ac * a.E, w);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(w[j]));
+          for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(w[j]));
         }
         if (row_ok) {
           if (atomic) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(orow + c + j, __uint_as_float(o[j]));
+            for (int j = 0; j < 16; ++j) atomicAdd(orow + c + j, __uint_as_float(o[j]));
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
+            for (int j = 0; j < 16; j += 4)
               *reinterpret_cast<float4*>(orow + c + j) = make_float4(__uint_as_float(o[j]), __uint_as_float(o[j + 1]),
                                                                      __uint_as_float(o[j + 2]), __uint_as_float(o[j + 3]));
           }

@@ -217,6 +217,12 @@ def embedding_sparse_grad(idx: torch.Tensor, dY: torch.Tensor, width: int, table
     return rows, grads, n
 
 
+def scatter_add_rows(idx: torch.Tensor, dY: torch.Tensor, width: int, dense: torch.Tensor, padding_idx: int = 0) -> None:
+    """dense[idx[b], :width] += dY[b, :width] with fp32 atomics (padding row and out-of-range ids skipped)."""
+    N.check(N.lib().b200rec_scatter_add_rows(N.ptr(idx), idx.shape[0], N.ptr(dY), dY.stride(0), width, padding_idx,
+                                             dense.shape[0], N.ptr(dense), dense.stride(0), N.stream()), "scatter_add_rows")
+
+
 def scatter_rows(rows, grads, n, dense: torch.Tensor, accumulate: bool = False) -> None:
     N.check(N.lib().b200rec_scatter_rows(N.ptr(rows), N.ptr(grads), N.ptr(n), rows.shape[0], grads.shape[1],
                                          N.ptr(dense), dense.stride(0), int(accumulate), N.stream()), "scatter_rows")

@@ -360,6 +360,18 @@ class GatherConcatFn(Function):
             if not ctx.needs_input_grad[2 + len(idx64) + f]:
                 grads.append(None)
                 continue
+            inplace = (isinstance(table.grad, torch.Tensor) and table.grad.shape == table.shape
+                       and table.grad.dtype == torch.float32 and table.grad.stride(1) == 1)
+            if (inplace and not getattr(table, "_b200_sparse", False)
+                    and os.environ.get("B200REC_EMB_BWD", "atomic") != "sorted"):
+                # the optimiser pre-allocated (and zeroed) the dense gradient: add the sample rows straight into it,
+                # one launch, instead of sort + segment sum + scatter (B200REC_EMB_BWD=sorted keeps the deterministic path)
+                K.scatter_add_rows(idx64[f], dout[:, offs[f]:], widths[f], table.grad, 0)
+                touch = getattr(table, "_b200_touch", None)
+                if touch is not None:
+                    touch[0]._mark(touch[1])
+                grads.append(None)
+                continue
             rows, vals, n = K.embedding_sparse_grad(idx64[f], dout[:, offs[f]:], widths[f], table.shape[0], 0)
             if getattr(table, "_b200_sparse", False):
                 prev = getattr(table, "_b200_sparse_grad", None)
