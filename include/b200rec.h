@@ -242,9 +242,11 @@ int b200rec_sumsq(const float* x, int64_t n, double* out, void* stream);
 int b200rec_clip_coef(const double* sumsq, float max_norm, float* coef, float* norm_out, void* stream);
 /* torch.optim.Adam with L2-coupled weight decay (trainers/two_tower.py:60-64,146) on a flat fp32 buffer;
  * clip_coef_dev (device float, nullable) scales g first.  bias_c1 = 1-beta1^t, bias_c2_sqrt = sqrt(1-beta2^t). */
-int b200rec_adam_dense(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+/* clear_grad != 0: every gradient element that was non-zero is reset to zero after it was consumed (the next step's
+ * zero_grad without a pass over the whole buffer). */
+int b200rec_adam_dense(float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                        float eps, float weight_decay, float bias_c1, float bias_c2_sqrt, const float* clip_coef_dev,
-                       void* stream);
+                       int clear_grad, void* stream);
 /* Row-sparse Adam on the touched rows only (large embedding tables; no weight decay on untouched rows). */
 int b200rec_sparse_adam(float* table, float* exp_avg, float* exp_avg_sq, int64_t ld, int width, const int64_t* rows,
                         const float* grad_rows, const int32_t* n_rows, int64_t max_rows, float lr, float beta1,
@@ -259,8 +261,9 @@ int b200rec_sparse_adam(float* table, float* exp_avg, float* exp_avg_sq, int64_t
  * b200rec_adam_dense / _sparse_adam reading hyper_dev instead of host scalars.  One training stream per process. */
 int b200rec_train_step_begin(int64_t* step_dev, const float* lr_dev, float beta1, float beta2, float* hyper_dev,
                              uint64_t salt_key, void* stream);
-int b200rec_adam_dense_dev(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
-                           float weight_decay, const float* hyper_dev, const float* clip_coef_dev, void* stream);
+int b200rec_adam_dense_dev(float* p, float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
+                           float weight_decay, const float* hyper_dev, const float* clip_coef_dev, int clear_grad,
+                           void* stream);
 int b200rec_sparse_adam_dev(float* table, float* exp_avg, float* exp_avg_sq, int64_t ld, int width, const int64_t* rows,
                             const float* grad_rows, const int32_t* n_rows, int64_t max_rows, float beta1, float beta2,
                             float eps, const float* hyper_dev, const float* clip_coef_dev, void* stream);

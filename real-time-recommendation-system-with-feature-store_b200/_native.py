@@ -42,7 +42,7 @@ SIGNATURES = {
     "b200rec_mlp_wgrad": (_I, [_P, _I64, _P, _P, _P, _P, _I64, _P, _I64, _I, _I, _I, _P, _I64, _P, _P, _P, _P]),
     "b200rec_gather_concat": (_I, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P, _I, _I64, _P, _I64, _P, _P]),
     "b200rec_train_step_begin": (_I, [_P, _P, _F, _F, _P, _U64, _P]),
-    "b200rec_adam_dense_dev": (_I, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P, _P]),
+    "b200rec_adam_dense_dev": (_I, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P, _I, _P]),
     "b200rec_sparse_adam_dev": (_I, [_P, _P, _P, _I64, _I, _P, _P, _P, _I64, _F, _F, _F, _P, _P, _P]),
     "b200rec_gather_rows": (_I, [_P, _I64, _I, _I64, _P, _I64, _P, _I64, _P, _P]),
     "b200rec_sample_negatives": (_I, [_P, _I64, _P, _P, _I64, _I64, _I, _U64, _U64, _P, _P, _P]),
@@ -72,7 +72,7 @@ SIGNATURES = {
     "b200rec_rowdot_bwd": (_I, [_P, _P, _P, _I64, _I64, _F, _P, _P, _P]),
     "b200rec_sumsq": (_I, [_P, _I64, _P, _P]),
     "b200rec_clip_coef": (_I, [_P, _F, _P, _P, _P]),
-    "b200rec_adam_dense": (_I, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _F, _P, _P]),
+    "b200rec_adam_dense": (_I, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _F, _P, _I, _P]),
     "b200rec_inbatch_grad_supported": (_I, [_I64, _I64, _I, _I, _I]),
     "b200rec_inbatch_grad": (_I, [_P, _I64, _P, _P, _I64, _P, _P, _I64, _P, _P, _I64, _P, _I64, _I64, _I, _I, _I, _F, _P, _I64,
                                   _F, _P, _P, _I64, _P, _I64, _P]),

@@ -468,11 +468,11 @@ def clip_coef(acc64, max_norm: float, coef, norm_out=None) -> None:
     N.check(N.lib().b200rec_clip_coef(N.ptr(acc64), max_norm, N.ptr(coef), N.ptr(norm_out), N.stream()), "clip_coef")
 
 
-def adam_dense_(p, g, m, v, lr, beta1, beta2, eps, wd, step: int, clip=None) -> None:
+def adam_dense_(p, g, m, v, lr, beta1, beta2, eps, wd, step: int, clip=None, clear_grad: bool = False) -> None:
     bc1 = 1.0 - beta1 ** step
     bc2s = (1.0 - beta2 ** step) ** 0.5
     N.check(N.lib().b200rec_adam_dense(N.ptr(p), N.ptr(g), N.ptr(m), N.ptr(v), p.numel(), lr, beta1, beta2, eps, wd, bc1,
-                                       bc2s, N.ptr(clip), N.stream()), "adam_dense")
+                                       bc2s, N.ptr(clip), int(clear_grad), N.stream()), "adam_dense")
 
 
 def sparse_adam_(table, m, v, rows, grads, n, lr, beta1, beta2, eps, step: int, clip=None) -> None:
@@ -488,9 +488,9 @@ def train_step_begin(step_dev, lr_dev, beta1: float, beta2: float, hyper_dev, sa
                                              salt_key & 0xFFFFFFFFFFFFFFFF, N.stream()), "train_step_begin")
 
 
-def adam_dense_dev_(p, g, m, v, beta1, beta2, eps, wd, hyper_dev, clip=None) -> None:
+def adam_dense_dev_(p, g, m, v, beta1, beta2, eps, wd, hyper_dev, clip=None, clear_grad: bool = False) -> None:
     N.check(N.lib().b200rec_adam_dense_dev(N.ptr(p), N.ptr(g), N.ptr(m), N.ptr(v), p.numel(), beta1, beta2, eps, wd,
-                                           N.ptr(hyper_dev), N.ptr(clip), N.stream()), "adam_dense_dev")
+                                           N.ptr(hyper_dev), N.ptr(clip), int(clear_grad), N.stream()), "adam_dense_dev")
 
 
 def sparse_adam_dev_(table, m, v, rows, grads, n, beta1, beta2, eps, hyper_dev, clip=None) -> None:

@@ -58,6 +58,7 @@ class FlatAdam:
         self.sparse_state = {id(p): (torch.zeros_like(p.data), torch.zeros_like(p.data)) for p in self.sparse}
         self.lr, self.wd, self.betas, self.eps, self.max_grad_norm = lr, weight_decay, betas, eps, max_grad_norm
         self.step_count = 0
+        self._grad_clean = True
         self._acc = torch.zeros((1,), dtype=torch.float64, device=dev)
         self._coef = torch.ones((1,), dtype=torch.float32, device=dev)
         self.grad_norm = torch.zeros((1,), dtype=torch.float32, device=dev)
@@ -87,7 +88,11 @@ class FlatAdam:
         return runs
 
     def zero_grad(self, set_to_none: bool = False) -> None:
-        self.grad.zero_()
+        # step() resets every gradient it consumed (adam_dense clear_grad) and untouched segments were never written:
+        # the buffer is already zero unless something accumulated into it since the last step
+        if not self._grad_clean:
+            self.grad.zero_()
+        self._grad_clean = False
         self._touched = [False] * len(self.dense)
         for p in self.sparse:
             p._b200_sparse_grad = None
@@ -143,11 +148,12 @@ class FlatAdam:
             K.clip_coef(self._acc, float(self.max_grad_norm), self._coef, self.grad_norm)
             clip = self._coef
         runs = self._runs()
+        self._grad_clean = True          # every run below clears the gradients it consumes; the rest was never written
         if self.dev_state is not None and getattr(self, "use_device_state", False):
             hyper = self.dev_state["hyper"]   # written by K.train_step_begin at the start of this step
             for lo, hi in runs:
                 K.adam_dense_dev_(self.flat[lo:hi], self.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], self.betas[0],
-                                  self.betas[1], self.eps, self.wd, hyper, clip)
+                                  self.betas[1], self.eps, self.wd, hyper, clip, clear_grad=True)
             for p, lists in sparse:
                 m, v = self.sparse_state[id(p)]
                 for rows, vals, n in lists:
@@ -155,7 +161,7 @@ class FlatAdam:
             return
         for lo, hi in runs:
             K.adam_dense_(self.flat[lo:hi], self.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], lr, self.betas[0],
-                          self.betas[1], self.eps, self.wd, self.step_count, clip)
+                          self.betas[1], self.eps, self.wd, self.step_count, clip, clear_grad=True)
         for p, lists in sparse:
             m, v = self.sparse_state[id(p)]
             for rows, vals, n in lists:
@@ -282,7 +288,10 @@ class TwoTowerTrainer:
         for k, v in (ic or {}).items():
             static["ic"][k].copy_(v)
         self.optimizer.sync_device_state()
+        if not self.optimizer._grad_clean:       # something accumulated gradients outside a step: the captured step
+            self.optimizer.grad.zero_()          # (which starts from a clean buffer) must not add to them
         graph.replay()
+        self.optimizer._grad_clean = True
         self.optimizer.step_count += 1
         self.optimizer.dev_state["step_host"] = self.optimizer.step_count   # the graph's first node incremented it
         return loss                      # static tensor: overwritten by the next replay of this shape
