@@ -451,6 +451,7 @@ def run_table_train_block(ctx: Ctx, steps: int, warmup: int, cpu_baseline: bool,
             out["cpu_baseline"] = cpu_train_baseline_cfg2(host_threads())
         except Exception as exc:  # noqa: BLE001
             out["cpu_baseline"] = {"error": repr(exc)[:200]}
+    trainer.release_graphs()
     del trainer, model, dev
     torch.cuda.empty_cache()
     return out
@@ -940,7 +941,18 @@ def main():
         line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
+        import gc
+        import threading
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        # the line is out; a wedged communicator teardown must not turn a finished run into a timeout
+        killer = threading.Timer(60.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
         dist.destroy_process_group()
+        killer.cancel()
 
 
 if __name__ == "__main__":

@@ -281,6 +281,14 @@ class DataParallel:
         model.dp = self
         model.user_tower.dp = self
         model.item_tower.dp = self
+        # Dense id-embedding tables: a step's gradient is non-zero on the rows the GLOBAL batch touched only, so the
+        # replicas exchange (ids, gradient rows) of their samples (world x B x (8 + 4e) bytes) and every replica adds all
+        # of them into its own dense gradient — the same sum an all-reduce of the whole [rows, e] buffer would produce
+        # (282 MB per step for config 2), see ops.GatherConcatFn.backward and FlatAdam.step.
+        for tower in (model.user_tower, model.item_tower):
+            for emb in getattr(tower, "embeddings", {}).values():
+                if not getattr(emb.weight, "_b200_sparse", False):
+                    emb.weight._b200_row_exchange = self
 
     def reduce_sums(self, t: torch.Tensor) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
@@ -288,8 +296,13 @@ class DataParallel:
     def all_gather_rows(self, x: torch.Tensor) -> torch.Tensor:
         return _AllGatherRows.apply(x, self.group)
 
-    def reduce_dense_grad_(self, flat: torch.Tensor) -> None:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+    def reduce_dense_grad_(self, flat: torch.Tensor, runs=None) -> None:
+        """Sum the flat gradient buffer over the replicas; `runs` = [lo, hi) element ranges to reduce (default: all)."""
+        if runs is None:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        for lo, hi in runs:
+            dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
 
     def gather_sparse(self, rows: torch.Tensor, vals: torch.Tensor):
         """(rows [n], vals [n,e]) of this replica -> concatenation over replicas (padding rows stay 0)."""

@@ -366,7 +366,14 @@ class GatherConcatFn(Function):
                     and os.environ.get("B200REC_EMB_BWD", "atomic") != "sorted"):
                 # the optimiser pre-allocated (and zeroed) the dense gradient: add the sample rows straight into it,
                 # one launch, instead of sort + segment sum + scatter (B200REC_EMB_BWD=sorted keeps the deterministic path)
-                K.scatter_add_rows(idx64[f], dout[:, offs[f]:], widths[f], table.grad, 0)
+                ex = getattr(table, "_b200_row_exchange", None)
+                if ex is not None and getattr(table, "_b200_touch", None) is not None:
+                    # data parallel: every replica adds the sample rows of ALL replicas (instead of all-reducing the
+                    # whole dense table gradient afterwards)
+                    ids_all, rows_all = ex.gather_sparse(idx64[f], dout[:, offs[f]:offs[f] + widths[f]].contiguous())
+                    K.scatter_add_rows(ids_all, rows_all, widths[f], table.grad, 0)
+                else:
+                    K.scatter_add_rows(idx64[f], dout[:, offs[f]:], widths[f], table.grad, 0)
                 touch = getattr(table, "_b200_touch", None)
                 if touch is not None:
                     touch[0]._mark(touch[1])

@@ -59,6 +59,7 @@ class FlatAdam:
         self.lr, self.wd, self.betas, self.eps, self.max_grad_norm = lr, weight_decay, betas, eps, max_grad_norm
         self.step_count = 0
         self._grad_clean = True
+        self.clear_grad = True                    # step() zeroes the gradients it consumes (False: keep them readable)
         self._acc = torch.zeros((1,), dtype=torch.float64, device=dev)
         self._coef = torch.ones((1,), dtype=torch.float32, device=dev)
         self.grad_norm = torch.zeros((1,), dtype=torch.float32, device=dev)
@@ -80,6 +81,21 @@ class FlatAdam:
         runs = []
         for (off, k), t in zip(self._seg, self._touched):
             if not t:
+                continue
+            if runs and runs[-1][1] == off:
+                runs[-1] = (runs[-1][0], off + k)
+            else:
+                runs.append((off, off + k))
+        return runs
+
+    def _reduce_runs(self):
+        """[lo, hi) ranges of the flat gradient buffer that data parallel must all-reduce: everything except the dense
+        embedding tables whose rows are exchanged sample-wise (None = the whole buffer)."""
+        if not any(getattr(p, "_b200_row_exchange", None) is not None for p in self.dense):
+            return None
+        runs = []
+        for (off, k), p in zip(self._seg, self.dense):
+            if getattr(p, "_b200_row_exchange", None) is not None:
                 continue
             if runs and runs[-1][1] == off:
                 runs[-1] = (runs[-1][0], off + k)
@@ -137,7 +153,9 @@ class FlatAdam:
         clip = None
         dp = getattr(self, "dp", None)
         if dp is not None:
-            dp.reduce_dense_grad_(self.grad)   # losses are normalised by the global batch: gradients add up
+            # losses are normalised by the global batch: gradients add up.  Tables whose touched rows were exchanged in
+            # the backward (dist.DataParallel) already hold the global sum: only the other segments are all-reduced.
+            dp.reduce_dense_grad_(self.grad, self._reduce_runs())
         sparse = [(p, self._sparse_lists(p)) for p in self.sparse]
         if self.max_grad_norm is not None:
             self._acc.zero_()
@@ -148,12 +166,12 @@ class FlatAdam:
             K.clip_coef(self._acc, float(self.max_grad_norm), self._coef, self.grad_norm)
             clip = self._coef
         runs = self._runs()
-        self._grad_clean = True          # every run below clears the gradients it consumes; the rest was never written
+        self._grad_clean = bool(self.clear_grad)   # every run below clears the gradients it consumes; the rest was never written
         if self.dev_state is not None and getattr(self, "use_device_state", False):
             hyper = self.dev_state["hyper"]   # written by K.train_step_begin at the start of this step
             for lo, hi in runs:
                 K.adam_dense_dev_(self.flat[lo:hi], self.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], self.betas[0],
-                                  self.betas[1], self.eps, self.wd, hyper, clip, clear_grad=True)
+                                  self.betas[1], self.eps, self.wd, hyper, clip, clear_grad=self.clear_grad)
             for p, lists in sparse:
                 m, v = self.sparse_state[id(p)]
                 for rows, vals, n in lists:
@@ -161,7 +179,7 @@ class FlatAdam:
             return
         for lo, hi in runs:
             K.adam_dense_(self.flat[lo:hi], self.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], lr, self.betas[0],
-                          self.betas[1], self.eps, self.wd, self.step_count, clip, clear_grad=True)
+                          self.betas[1], self.eps, self.wd, self.step_count, clip, clear_grad=self.clear_grad)
         for p, lists in sparse:
             m, v = self.sparse_state[id(p)]
             for rows, vals, n in lists:
@@ -242,15 +260,25 @@ class TwoTowerTrainer:
         host-launch-bound at ~18 us each).  The first `warm_steps` calls of a shape run eagerly, the next one is
         captured; shapes that differ (the ragged last batch) keep running eagerly.  What changes from step to step lives
         on the device: step counter / lr / Adam bias corrections (b200rec_train_step_begin, *_adam_*_dev) and a
-        per-step salt of every dropout seed.  Not used under data parallel (collectives stay eager)."""
+        per-step salt of every dropout seed.  Under data parallel the NCCL collectives are part of the captured graph."""
         self._graph_warm = int(warm_steps)
         self._graphs: Dict[Any, Any] = {}
         self._graph_seen: Dict[Any, int] = {}
         self.optimizer.enable_device_state()
         return self._graph_capturable()
 
+    def release_graphs(self) -> None:
+        """Drop the captured steps (their NCCL nodes must be gone before the process group is destroyed)."""
+        if getattr(self, "_graphs", None):
+            torch.cuda.synchronize()
+            self._graphs.clear()
+            self._graph_seen.clear()
+
     def _graph_capturable(self) -> bool:
-        return getattr(self.model, "dp", None) is None
+        # NCCL collectives issued through torch.distributed are capturable (the process group's internal stream joins the
+        # capture through events); every replica captures and replays the same sequence.  B200REC_DP_GRAPH=0 keeps the
+        # data-parallel step eager.
+        return getattr(self.model, "dp", None) is None or os.environ.get("B200REC_DP_GRAPH", "1") != "0"
 
     def _graph_key(self, uf, pf, nf, uc, ic):
         cat = lambda d: tuple((k, tuple(v.shape), v.dtype) for k, v in (d or {}).items())
@@ -291,7 +319,7 @@ class TwoTowerTrainer:
         if not self.optimizer._grad_clean:       # something accumulated gradients outside a step: the captured step
             self.optimizer.grad.zero_()          # (which starts from a clean buffer) must not add to them
         graph.replay()
-        self.optimizer._grad_clean = True
+        self.optimizer._grad_clean = bool(self.optimizer.clear_grad)
         self.optimizer.step_count += 1
         self.optimizer.dev_state["step_host"] = self.optimizer.step_count   # the graph's first node incremented it
         return loss                      # static tensor: overwritten by the next replay of this shape

@@ -252,6 +252,12 @@ def _gloo_dp_worker(rank, world, port, tmp):
     rows, vals = dp.gather_sparse(torch.tensor([rank + 1, 0]), torch.full((2, 3), float(rank)))
     ok = ok and rows.tolist() == [1, 0, 2, 0] and vals[2].tolist() == [1.0, 1.0, 1.0]
     ok = ok and float(dp.global_loss(torch.tensor(0.5 * (rank + 1)))) == 1.5
+    flat = torch.arange(10, dtype=torch.float32) * (rank + 1)              # only the listed runs are summed over replicas
+    dp.reduce_dense_grad_(flat, [(0, 2), (7, 10)])
+    want = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    want[0:2] = torch.arange(0, 2) * 3.0
+    want[7:10] = torch.arange(7, 10) * 3.0
+    ok = ok and torch.equal(flat, want)
     ok = ok and ShardedFlatIndex.exchange_width(100, 8) == 33 and ShardedFlatIndex.exchange_width(100, 1) == 100
     with open(os.path.join(tmp, f"dp{rank}"), "w") as fh:
         fh.write("1" if ok else "0")

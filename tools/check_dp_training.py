@@ -29,6 +29,7 @@ for sparse, mixed in ((False, False), (True, False), (False, True)):
         tcfg = {"learning_rate": 1e-3, "weight_decay": 0.0 if sparse else 1e-5, "checkpoint_dir": f"/tmp/b200rec_dp_{rank}"}
         dp_model = make(); trainer = TwoTowerTrainer(dp_model, [], [], tcfg, device=str(dev)); DataParallel(dp_model); dp_model.train()
         ref_model = make(); ref_trainer = TwoTowerTrainer(ref_model, [], [], tcfg, device=str(dev)); ref_model.train()
+        trainer.optimizer.clear_grad = ref_trainer.optimizer.clear_grad = False   # the check below reads the gradients
         g = torch.Generator(device=dev).manual_seed(99)
         losses, ref_losses = [], []
         grad_rel = 0.0
@@ -52,7 +53,8 @@ for sparse, mixed in ((False, False), (True, False), (False, True)):
         bn = max((b1 - b2).abs().max().item() for (k1, b1), (_, b2) in zip(dp_model.named_buffers(), ref_model.named_buffers()) if b1.dtype.is_floating_point)
         # losses and first-step gradients agree to rounding (the two runs sum in different orders: chunking, split-K);
         # parameters are only bounded loosely: Adam turns 1e-9 gradient noise on near-zero gradients into lr-sized steps
-        good = rel <= 1e-6 and grad_rel <= 1e-5 and pmax <= 1e-3 and bn <= 1e-5
+        # (lr = 1e-3, 4 steps; weight gradients are summed with fp32 atomics in a run-dependent order)
+        good = rel <= 2e-6 and grad_rel <= 1e-5 and pmax <= 2e-3 and bn <= 1e-5
         ok = ok and good
         if rank == 0:
             print(f"sparse_tables={sparse} mixed_loss={mixed}: losses DP {l.tolist()} vs single {r.tolist()} max rel diff {rel:.2e}; "
@@ -69,10 +71,17 @@ t2 = TwoTowerTrainer(m2, [], [], {"checkpoint_dir": f"/tmp/b200rec_dp_{rank}"}, 
 g = torch.Generator(device=dev).manual_seed(7 + rank)
 uf = torch.randn(B2, FD, device=dev, generator=g); pf = torch.randn(B2, FD, device=dev, generator=g)
 uid = torch.randint(1, NU2 + 1, (B2,), device=dev, generator=g); iid = torch.randint(1, NI2 + 1, (B2,), device=dev, generator=g)
-for _ in range(5): t2.train_step(uf, pf, None, {"user_id": uid}, {"item_id": iid})
-torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
-for _ in range(20): t2.train_step(uf, pf, None, {"user_id": uid}, {"item_id": iid})
-torch.cuda.synchronize(); dist.barrier(); dt = (time.perf_counter() - t0) / 20
-if rank == 0: print(f"DP config-2 step, {world} GPUs x batch {B2} (global in-batch negatives {world*B2}): {dt*1e3:.2f} ms/step, {world*B2/dt:.0f} samples/s", flush=True)
+for graphed in (False, True):
+    if graphed: t2.enable_cuda_graph(warm_steps=1)
+    for _ in range(5): t2.train_step(uf, pf, None, {"user_id": uid}, {"item_id": iid})
+    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+    for _ in range(20): loss = t2.train_step(uf, pf, None, {"user_id": uid}, {"item_id": iid})
+    torch.cuda.synchronize(); dist.barrier(); dt = (time.perf_counter() - t0) / 20
+    if rank == 0: print(f"DP config-2 step ({'CUDA graph' if graphed else 'eager'}), {world} GPUs x batch {B2} (global in-batch negatives {world*B2}): {dt*1e3:.2f} ms/step, {world*B2/dt:.0f} samples/s, loss {float(loss):.4f}", flush=True)
+code = 0 if int(flag.item()) == 1 else 1
+t2.release_graphs(); del t2, m2
+import gc, threading; gc.collect(); torch.cuda.synchronize(); dist.barrier()
+sys.stdout.flush()
+threading.Timer(30.0, lambda: os._exit(code)).start()   # a wedged communicator teardown must not turn a pass into a hang
 dist.destroy_process_group()
-sys.exit(0 if int(flag.item()) == 1 else 1)
+os._exit(code)
