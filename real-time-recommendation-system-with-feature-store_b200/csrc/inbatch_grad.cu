@@ -28,6 +28,12 @@
 
 namespace b200 {
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int IG_EPI_WARPS = 16;                 // epilogue warps: 4 per TMEM lane quarter, 16 logit columns each
 constexpr int IG_THREADS = (4 + IG_EPI_WARPS) * 32;
 constexpr int IG_BM = 128;        // X rows per unit
@@ -54,13 +60,6 @@ struct IgSide {
 struct IgArgs {
   IgSide side[2];
   int units_u;         // units of mode U come first
-  int E;               // embedding width (64 or 128)
-  int KB;              // pad64(E) / 64
-  int nprod_s;         // 1, 3 or 6 piece products for the logits recompute
-  int nprod_g;         // 1 or 3 piece products for the gradient GEMM
-  int nst;             // TMA stages
-  int ng;              // G buffers
-  int nacc;            // OUT accumulators
   int atomic_u, atomic_v;
   float scale_log2;    // inv_t * log2(e)
   float coef;          // inv_t / total_rows (times *coef_dev when given)
@@ -68,14 +67,39 @@ struct IgArgs {
   const float* lse;    // [B] fp32 (natural log)
 };
 
-// piece products, smallest first (they are added in this order): (x piece, y piece)
-__device__ __constant__ int IG_PROD6[6][2] = {{1, 1}, {2, 0}, {0, 2}, {1, 0}, {0, 1}, {0, 0}};
+// Compile-time geometry of one instantiation: E = embedding width, NPS / NPG = piece products of the logits recompute
+// and of the gradient GEMM.  Everything the MMA-issuing warp touches per tile (stage offsets, descriptors, piece
+// products, ring sizes) is an immediate: with run-time ring sizes and product tables that single warp needed ~370
+// instructions (integer divisions, constant-table loads) per tile and paced the whole CTA at ~3200 cycles per tile for
+// 770 cycles of tensor work.
+template <int E, int NPS, int NPG>
+struct IgCfg {
+  static constexpr int KB = E / 64;
+  static constexpr int PS = NPS == 1 ? 1 : (NPS == 3 ? 2 : 3);   // pieces held for the logits GEMM
+  static constexpr int PG = NPG == 1 ? 1 : 2;                    // pieces of G / Y^T
+  static constexpr int X_BYTES = PS * KB * IG_BM * 128;
+  static constexpr int YS_BYTES = PS * KB * IG_BN * 128;          // Y pieces of one stage
+  static constexpr int YT_BYTES = PG * E * 128;                   // Y^T pieces of one stage (one 64-column k-block)
+  static constexpr int STAGE = YS_BYTES + YT_BYTES;
+  static constexpr int G_BYTES = PG * IG_BM * 128;
+  static constexpr int FIXED = 1024 + 256 + X_BYTES;
+  static constexpr int NG = (IG_SMEM_LIMIT - FIXED - 2 * G_BYTES) / STAGE >= 2 ? 2 : 1;
+  static constexpr int NST_RAW = (IG_SMEM_LIMIT - FIXED - NG * G_BYTES) / STAGE;
+  static constexpr int NST = NST_RAW > 4 ? 4 : NST_RAW;
+  static constexpr bool OK = NST >= 2;
+  static constexpr int NACC = (512 - 2 * IG_BN) / E > 4 ? 4 : (512 - 2 * IG_BN) / E;
+  static constexpr int SMEM = FIXED + NST * STAGE + NG * G_BYTES;
+};
 
+template <int E, int NPS, int NPG>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_constant__ CUtensorMap tm_uy,
                     const __grid_constant__ CUtensorMap tm_ut, const __grid_constant__ CUtensorMap tm_vx,
                     const __grid_constant__ CUtensorMap tm_vy, const __grid_constant__ CUtensorMap tm_vt,
                     const IgArgs a) {
+  using C = IgCfg<E, NPS, NPG>;
+  constexpr int KB = C::KB, PS = C::PS, PG = C::PG, NST = C::NST, NG = C::NG, NACC = C::NACC;
+  constexpr int STAGE = C::STAGE, YS_BYTES = C::YS_BYTES, G_BYTES = C::G_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -91,17 +115,10 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
   const CUtensorMap* tmy = mode ? &tm_uy : &tm_vy;   // Y operand, box 64 rows
   const CUtensorMap* tmt = mode ? &tm_ut : &tm_vt;   // Y^T operand, box E rows
 
-  const int ps = a.nprod_s == 1 ? 1 : (a.nprod_s == 3 ? 2 : 3);   // pieces held for the logits GEMM
-  const int pg = a.nprod_g == 1 ? 1 : 2;                          // pieces of G / Y^T
-  const int x_bytes = ps * a.KB * (IG_BM * 128);
-  const int ys_bytes = ps * a.KB * (IG_BN * 128);                  // Y pieces of one stage
-  const int yt_bytes = pg * (a.E * 128);                           // Y^T pieces of one stage (one 64-column k-block)
-  const int stage_bytes = ys_bytes + yt_bytes;
-  const int g_bytes = pg * (IG_BM * 128);
   uint8_t* x_smem = smem;
-  uint8_t* st_smem = x_smem + x_bytes;
-  uint8_t* g_smem = st_smem + a.nst * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(g_smem + a.ng * g_bytes);
+  uint8_t* st_smem = x_smem + C::X_BYTES;
+  uint8_t* g_smem = st_smem + NST * STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(g_smem + NG * G_BYTES);
   uint64_t* full_bar = bars;            // [4]
   uint64_t* empty_bar = bars + 4;       // [4]
   uint64_t* s_full = bars + 8;          // [2]
@@ -137,91 +154,103 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t OUT_COL = 2 * IG_BN;   // TMEM columns: S0 [0,64) | S1 [64,128) | OUT accumulators [128, 128 + nacc*E)
+  constexpr uint32_t OUT_COL = 2 * IG_BN;   // TMEM columns: S0 [0,64) | S1 [64,128) | OUT accumulators [128, 128 + NACC*E)
 
   if (T > 0) {
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer
       if (elect_one()) {
-        mbar_arrive_expect_tx(x_full, x_bytes);
-        for (int p = 0; p < ps; ++p)
-          for (int kb = 0; kb < a.KB; ++kb)
-            tma_load_2d(x_smem + (p * a.KB + kb) * (IG_BM * 128), tmx, x_full, (sd.xp[p] * a.KB + kb) * 64, x_tile * IG_BM);
+        mbar_arrive_expect_tx(x_full, C::X_BYTES);
+#pragma unroll
+        for (int p = 0; p < PS; ++p)
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_2d(x_smem + (p * KB + kb) * (IG_BM * 128), tmx, x_full, (sd.xp[p] * KB + kb) * 64, x_tile * IG_BM);
       }
       __syncwarp();
+      int st = 0;
+      uint32_t eph = 1;
       for (int t = 0; t < T; ++t) {
-        const int st = t % a.nst;
-        mbar_wait(&empty_bar[st], ((t / a.nst) & 1) ^ 1);
+        mbar_wait(&empty_bar[st], eph);
         if (elect_one()) {
-          uint8_t* dst = st_smem + st * stage_bytes;
+          uint8_t* dst = st_smem + st * STAGE;
           const int yrow = (t_begin + t) * IG_BN;
-          mbar_arrive_expect_tx(&full_bar[st], stage_bytes);
-          for (int p = 0; p < ps; ++p)
-            for (int kb = 0; kb < a.KB; ++kb)
-              tma_load_2d(dst + (p * a.KB + kb) * (IG_BN * 128), tmy, &full_bar[st], (sd.yp[p] * a.KB + kb) * 64, yrow);
-          for (int p = 0; p < pg; ++p)
-            tma_load_2d(dst + ys_bytes + p * (a.E * 128), tmt, &full_bar[st], sd.tp[p] * sd.ytw + yrow, 0);
+          mbar_arrive_expect_tx(&full_bar[st], STAGE);
+#pragma unroll
+          for (int p = 0; p < PS; ++p)
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb)
+              tma_load_2d(dst + (p * KB + kb) * (IG_BN * 128), tmy, &full_bar[st], (sd.yp[p] * KB + kb) * 64, yrow);
+#pragma unroll
+          for (int p = 0; p < PG; ++p)
+            tma_load_2d(dst + YS_BYTES + p * (E * 128), tmt, &full_bar[st], sd.tp[p] * sd.ytw + yrow, 0);
         }
         __syncwarp();
+        if (++st == NST) st = 0, eph ^= 1;
       }
     } else if (warp == 1) {
       // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, elected lane)
-      const uint32_t idesc_s = umma_idesc_bf16(IG_BM, IG_BN);
-      const uint32_t idesc_o = umma_idesc_bf16(IG_BM, (uint32_t)a.E);
-      const uint64_t desc_base = umma_desc_k_sw128(0);
-      const uint32_t x_lo = (smem_u32(x_smem) & 0x3FFFFu) >> 4;
-      const uint32_t st_lo = (smem_u32(st_smem) & 0x3FFFFu) >> 4;
-      const uint32_t g_lo = (smem_u32(g_smem) & 0x3FFFFu) >> 4;
-      const int p0 = 6 - a.nprod_s;   // first entry of IG_PROD6 used: 6 -> 0, 3 -> 3, 1 -> 5
+      constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((IG_BN >> 3) << 17) | ((IG_BM >> 4) << 24);
+      constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | ((E >> 3) << 17) | ((IG_BM >> 4) << 24);
+      // piece products, smallest first (they are added in this order): (x piece, y piece)
+      constexpr int PX[6] = {1, 2, 0, 1, 0, 0}, PY[6] = {1, 0, 2, 0, 1, 0};
+      constexpr int P0 = 6 - NPS;   // first product used: 6 -> 0, 3 -> 3, 1 -> 5
+      const uint64_t x_desc = umma_desc_k_sw128(smem_u32(x_smem));
+      const uint64_t st_desc = umma_desc_k_sw128(smem_u32(st_smem));
+      const uint64_t g_desc = umma_desc_k_sw128(smem_u32(g_smem));
       mbar_wait(x_full, 0);
       tc_fence_after();
+      int s_st = 0, o_st = 0, o_acc = 0;       // stage of the next logits tile / of the next gradient tile, accumulator
+      uint32_t s_ph = 0;                        // parity of full_bar[s_st]
       auto issue_s = [&](int t) {
-        const int st = t % a.nst, buf = t & 1;
-        mbar_wait(&full_bar[st], (t / a.nst) & 1);
+        const int buf = t & 1;
+        mbar_wait(&full_bar[s_st], s_ph);
         mbar_wait(&s_empty[buf], ((t >> 1) & 1) ^ 1);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t d_addr = tmem_base + buf * IG_BN;
-          bool first = true;
-          for (int pr = p0; pr < 6; ++pr) {
-            const int xa = IG_PROD6[pr][0], yb = IG_PROD6[pr][1];
-            for (int kb = 0; kb < a.KB; ++kb) {
-              const uint64_t a_desc = desc_base + (x_lo + (((xa * a.KB + kb) * (IG_BM * 128)) >> 4));
-              const uint64_t b_desc = desc_base + (st_lo + ((st * stage_bytes + (yb * a.KB + kb) * (IG_BN * 128)) >> 4));
+          const uint64_t b_base = st_desc + static_cast<uint64_t>((s_st * STAGE) >> 4);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_bf16(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc_s, first ? 0u : 1u);
-                first = false;
-              }
+          for (int pr = P0; pr < 6; ++pr) {
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+              const uint64_t a_desc = x_desc + (((PX[pr] * KB + kb) * (IG_BM * 128)) >> 4);
+              const uint64_t b_desc = b_base + (((PY[pr] * KB + kb) * (IG_BN * 128)) >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc_s, (pr == P0 && kb == 0 && k == 0) ? 0u : 1u);
             }
           }
           umma_commit(&s_full[buf]);
         }
         __syncwarp();
+        if (++s_st == NST) s_st = 0, s_ph ^= 1;
       };
       auto issue_o = [&](int t) {
-        const int st = t % a.nst, gb = t % a.ng, acc = t % a.nacc;
-        mbar_wait(&g_full[gb], (t / a.ng) & 1);
+        const int gb = t & (NG - 1);
+        mbar_wait(&g_full[gb], (NG == 2 ? (t >> 1) : t) & 1);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t d_addr = tmem_base + OUT_COL + acc * a.E;
-          bool first = t < a.nacc;
+          const uint32_t d_addr = tmem_base + OUT_COL + o_acc * E;
+          const uint64_t a_base = g_desc + static_cast<uint64_t>((gb * G_BYTES) >> 4);
+          const uint64_t b_base = st_desc + static_cast<uint64_t>((o_st * STAGE + YS_BYTES) >> 4);
+          const uint32_t keep = t >= NACC ? 1u : 0u;
           // products (G piece, Y^T piece): m.h, h.m, h.h  (or h.h alone)
-          for (int pr = (a.nprod_g == 3 ? 0 : 2); pr < 3; ++pr) {
-            const int ga = pr == 0 ? 1 : 0, yb = pr == 1 ? 1 : 0;
-            const uint64_t a_desc = desc_base + (g_lo + ((gb * g_bytes + ga * (IG_BM * 128)) >> 4));
-            const uint64_t b_desc = desc_base + (st_lo + ((st * stage_bytes + ys_bytes + yb * (a.E * 128)) >> 4));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_bf16(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc_o, first ? 0u : 1u);
-              first = false;
-            }
+          for (int pr = (NPG == 3 ? 0 : 2); pr < 3; ++pr) {
+            const uint64_t a_desc = a_base + (((pr == 0 ? 1 : 0) * (IG_BM * 128)) >> 4);
+            const uint64_t b_desc = b_base + (((pr == 1 ? 1 : 0) * (E * 128)) >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc_o, (pr == (NPG == 3 ? 0 : 2) && k == 0) ? keep : 1u);
           }
           umma_commit(&g_empty[gb]);
-          umma_commit(&empty_bar[st]);
+          umma_commit(&empty_bar[o_st]);
           if (t == T - 1) umma_commit(out_full);
         }
         __syncwarp();
+        if (++o_st == NST) o_st = 0;
+        if (++o_acc == NACC) o_acc = 0;
       };
       issue_s(0);
       for (int t = 0; t < T; ++t) {
@@ -240,16 +269,29 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
       float coef = a.coef;
       if (a.coef_dev != nullptr) coef *= __ldg(a.coef_dev);
       const float nl_row = (!sd.lse_by_col && row_ok) ? -__ldg(a.lse + row_g) * LOG2E : 0.f;
-      const long long hot = row_g + sd.dshift;   // global column of this row's positive (may fall outside [0, ycols))
+      // this row's positive sits at global column row_g + dshift (possibly outside [0, ycols)); all index math is int32
+      // (rows, ycols < 2^30).  Rows beyond sd.rows need no masking: row r of G only feeds row r of OUT, which is not
+      // stored; columns beyond ycols are masked in the (warp-uniform) tail tile only.
+      const int hot = (int)row_g + sd.dshift;
+      const bool lse_vec = sd.lse_by_col && ((reinterpret_cast<uintptr_t>(a.lse) & 15) == 0);
       for (int t = 0; t < T; ++t) {
-        const int buf = t & 1, gb = t % a.ng;
-        const long long c0 = (long long)(t_begin + t) * IG_BN + part * 16;
-        float nl_col[16];
+        const int buf = t & 1, gb = t & (NG - 1);
+        const int c0 = (t_begin + t) * IG_BN + part * 16;
+        const bool tail = c0 + 16 > sd.ycols;                      // warp-uniform
+        float nl[16];
         if (sd.lse_by_col) {
+          if (lse_vec && !tail) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const long long c = c0 + i;
-            nl_col[i] = -__ldg(a.lse + (c < sd.ycols ? c : sd.ycols - 1)) * LOG2E;
+            for (int j = 0; j < 4; ++j) {
+              const float4 l4 = __ldg(reinterpret_cast<const float4*>(a.lse + c0) + j);
+              nl[4 * j] = -l4.x * LOG2E, nl[4 * j + 1] = -l4.y * LOG2E, nl[4 * j + 2] = -l4.z * LOG2E, nl[4 * j + 3] = -l4.w * LOG2E;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c = c0 + i;
+              nl[i] = -__ldg(a.lse + (c < sd.ycols ? c : sd.ycols - 1)) * LOG2E;
+            }
           }
         }
         mbar_wait(&s_full[buf], (t >> 1) & 1);
@@ -260,33 +302,56 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[buf]);
+        // G = coef * (2^(S * scale - lse * log2e) - onehot): one FFMA, one MUFU.EX2 and one FMUL per element
         float gv[16];
+        if (sd.lse_by_col) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const long long c = c0 + i;
-          const float nl = sd.lse_by_col ? nl_col[i] : nl_row;
-          const float p = exp2f(fmaf(__uint_as_float(v[i]), a.scale_log2, nl));
-          const float gg = coef * (p - (c == hot ? 1.f : 0.f));
-          gv[i] = (c < sd.ycols && row_ok) ? gg : 0.f;
+          for (int i = 0; i < 16; ++i) gv[i] = coef * ex2_approx(fmaf(__uint_as_float(v[i]), a.scale_log2, nl[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) gv[i] = coef * ex2_approx(fmaf(__uint_as_float(v[i]), a.scale_log2, nl_row));
         }
-        // G(t) -> shared memory, K-major SW128: row r at r*128 B, 16-byte chunk j stored at position j ^ (r & 7)
-        mbar_wait(&g_empty[gb], ((t / a.ng) & 1) ^ 1);
-        uint8_t* gbase = g_smem + gb * g_bytes + row_l * 128;
+        const int d = hot - c0;                                    // position of the positive inside this thread's 16 columns
+        if (__any_sync(0xffffffffu, static_cast<unsigned>(d) < 16u)) {
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          uint32_t hw[4], mw[4];
+          for (int i = 0; i < 16; ++i) gv[i] -= (i == d) ? coef : 0.f;
+        }
+        if (tail) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float f0 = gv[ch * 8 + 2 * j], f1 = gv[ch * 8 + 2 * j + 1];
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
-            const float2 hf = __bfloat1622float2(h2);
-            const __nv_bfloat162 m2 = __floats2bfloat162_rn(f0 - hf.x, f1 - hf.y);
-            hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
-            mw[j] = *reinterpret_cast<const uint32_t*>(&m2);
+          for (int i = 0; i < 16; ++i) gv[i] = (c0 + i < sd.ycols) ? gv[i] : 0.f;
+        }
+        // G(t) -> shared memory, K-major SW128: row r at r*128 B, 16-byte chunk j stored at position j ^ (r & 7).
+        mbar_wait(&g_empty[gb], (((NG == 2 ? (t >> 1) : t) & 1) ^ 1));
+        uint8_t* gbase = g_smem + gb * G_BYTES + row_l * 128;
+        if constexpr (PG == 2) {
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            uint32_t hw[4], mw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {   // x = h + m: h = rn_bf16(x), m = rn_bf16(x - h) (the subtraction is exact)
+              const float f0 = gv[ch * 8 + 2 * j], f1 = gv[ch * 8 + 2 * j + 1];
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+              hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
+              const __nv_bfloat162 m2 = __floats2bfloat162_rn(f0 - __uint_as_float(hw[j] << 16),
+                                                              f1 - __uint_as_float(hw[j] & 0xFFFF0000u));
+              mw[j] = *reinterpret_cast<const uint32_t*>(&m2);
+            }
+            const int pos = ((part * 2 + ch) ^ (row_l & 7)) * 16;
+            *reinterpret_cast<uint4*>(gbase + pos) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(gbase + IG_BM * 128 + pos) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
           }
-          const int pos = ((part * 2 + ch) ^ (row_l & 7)) * 16;
-          *reinterpret_cast<uint4*>(gbase + pos) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          if (pg == 2) *reinterpret_cast<uint4*>(gbase + IG_BM * 128 + pos) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+        } else {
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            uint32_t hw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(gv[ch * 8 + 2 * j], gv[ch * 8 + 2 * j + 1]);
+              hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            const int pos = ((part * 2 + ch) ^ (row_l & 7)) * 16;
+            *reinterpret_cast<uint4*>(gbase + pos) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          }
         }
         fence_proxy_async_smem();   // generic-proxy stores above must be visible to the tensor core's async-proxy reads
         __syncwarp();
@@ -295,8 +360,8 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
       // gradient rows: sum the NACC accumulators with round-to-nearest adds, store (or add when the tile was split)
       mbar_wait(out_full, 0);
       tc_fence_after();
-      const int ncol = a.E / 4;   // columns of OUT per thread (16 or 32)
-      const int used = T < a.nacc ? T : a.nacc;
+      constexpr int ncol = E / 4;   // columns of OUT per thread (16 or 32)
+      const int used = T < NACC ? T : NACC;
       const bool atomic = mode ? a.atomic_v != 0 : a.atomic_u != 0;
       float* orow = sd.out + row_g * sd.ld_out + part * ncol;
 #pragma unroll 1
@@ -307,7 +372,7 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
         tmem_ld_wait();
         for (int ac = 1; ac < used; ++ac) {
           uint32_t w[16];
-          tmem_ld_32x16(taddr + ac * a.E, w);
+          tmem_ld_32x16(taddr + ac * E, w);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(w[j]));
@@ -334,28 +399,32 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
   }
 }
 
+// ring sizes / shared memory of the instantiation that serves (E, nprod_s, nprod_g); false when none fits
+template <int E, int NPS, int NPG>
+static bool ig_cfg_get(int& smem) {
+  smem = IgCfg<E, NPS, NPG>::SMEM;
+  return IgCfg<E, NPS, NPG>::OK;
+}
+
+static bool ig_cfg(int E, int nps, int npg, int& smem) {
+  if (E == 64) {
+    if (nps == 1 && npg == 1) return ig_cfg_get<64, 1, 1>(smem);
+    if (nps == 3 && npg == 3) return ig_cfg_get<64, 3, 3>(smem);
+    if (nps == 6 && npg == 3) return ig_cfg_get<64, 6, 3>(smem);
+  } else if (E == 128) {
+    if (nps == 1 && npg == 1) return ig_cfg_get<128, 1, 1>(smem);
+    if (nps == 3 && npg == 3) return ig_cfg_get<128, 3, 3>(smem);
+    if (nps == 6 && npg == 3) return ig_cfg_get<128, 6, 3>(smem);
+  }
+  return false;
+}
+
 static int ig_plan(IgArgs& a, int64_t B, int64_t NI, int E, int nprod_s, int nprod_g, int& smem_bytes) {
   if (E != 64 && E != 128) return fail("inbatch_grad: fused path needs E = 64 or 128 (got %d)", E);
-  if (nprod_s != 1 && nprod_s != 3 && nprod_s != 6) return fail("inbatch_grad: nprod_s must be 1, 3 or 6");
-  if (nprod_g != 1 && nprod_g != 3) return fail("inbatch_grad: nprod_g must be 1 or 3");
-  a.E = E;
-  a.KB = E / 64;
-  a.nprod_s = nprod_s;
-  a.nprod_g = nprod_g;
-  const int ps = nprod_s == 1 ? 1 : (nprod_s == 3 ? 2 : 3), pg = nprod_g == 1 ? 1 : 2;
-  const int x_bytes = ps * a.KB * (IG_BM * 128), stage = ps * a.KB * (IG_BN * 128) + pg * (E * 128), g_bytes = pg * (IG_BM * 128);
-  const int fixed = 1024 + 256 + x_bytes;
-  a.ng = 2;
-  a.nst = (IG_SMEM_LIMIT - fixed - a.ng * g_bytes) / stage;
-  if (a.nst < 2) {
-    a.ng = 1;
-    a.nst = (IG_SMEM_LIMIT - fixed - a.ng * g_bytes) / stage;
-  }
-  if (a.nst < 2) return fail("inbatch_grad: E = %d with %d piece products does not fit the resident tile", E, nprod_s);
-  if (a.nst > 4) a.nst = 4;
-  a.nacc = (512 - 2 * IG_BN) / E;
-  if (a.nacc > 4) a.nacc = 4;
-  smem_bytes = fixed + a.nst * stage + a.ng * g_bytes;
+  if (!((nprod_s == 1 && nprod_g == 1) || (nprod_s == 3 && nprod_g == 3) || (nprod_s == 6 && nprod_g == 3)))
+    return fail("inbatch_grad: piece products (logits, gradient) must be (1,1), (3,3) or (6,3)");
+  if (!ig_cfg(E, nprod_s, nprod_g, smem_bytes))
+    return fail("inbatch_grad: E = %d with %d piece products does not fit the resident tile", E, nprod_s);
   // units of equal length: L = tiles of the shorter column range, capped (accumulator chains, tail balance)
   const int64_t tu = (NI + IG_BN - 1) / IG_BN, tv = (B + IG_BN - 1) / IG_BN;
   int64_t L = tu < tv ? tu : tv;
@@ -371,6 +440,24 @@ static int ig_plan(IgArgs& a, int64_t B, int64_t NI, int E, int nprod_s, int npr
   a.atomic_u = su.splits > 1;
   a.atomic_v = sv.splits > 1;
   return 0;
+}
+
+template <int E, int NPS, int NPG>
+static int ig_launch(int units, int smem, cudaStream_t st, const CUtensorMap& ux, const CUtensorMap& uy, const CUtensorMap& ut,
+                     const CUtensorMap& vx, const CUtensorMap& vy, const CUtensorMap& vt, const IgArgs& a) {
+  if constexpr (IgCfg<E, NPS, NPG>::OK) {
+    auto kern = inbatch_grad_kernel<E, NPS, NPG>;
+    static bool attr = false;
+    if (!attr) {
+      B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM_LIMIT));
+      attr = true;
+    }
+    kern<<<units, IG_THREADS, smem, st>>>(ux, uy, ut, vx, vy, vt, a);
+    B200_LAUNCH_OK("inbatch_grad_kernel");
+    return 0;
+  } else {
+    return fail("inbatch_grad: configuration not instantiated");
+  }
 }
 
 }  // namespace b200
@@ -399,6 +486,7 @@ extern "C" int b200rec_inbatch_grad(const void* u_op, int64_t ld_u, const int32_
   IgArgs a;
   int smem = 0;
   if (ig_plan(a, B, NI, E, nprod_s, nprod_g, smem)) return 1;
+  const int KB = E / 64;
   const int ps = nprod_s == 1 ? 1 : (nprod_s == 3 ? 2 : 3), pg = nprod_g == 1 ? 1 : 2;
   const int64_t padB = (B + 63) / 64 * 64, padNI = (NI + 63) / 64 * 64;
   IgSide& su = a.side[0];
@@ -414,7 +502,7 @@ extern "C" int b200rec_inbatch_grad(const void* u_op, int64_t ld_u, const int32_
     sv.tp[p] = p < pg ? ut_pieces_host[p] : 0;
     if (p < pg) max_vt = max_vt > vt_pieces_host[p] ? max_vt : vt_pieces_host[p], max_ut = max_ut > ut_pieces_host[p] ? max_ut : ut_pieces_host[p];
   }
-  if ((max_u + 1) * a.KB * 64 > ld_u || (max_v + 1) * a.KB * 64 > ld_v) return fail("inbatch_grad: piece block outside the operand row");
+  if ((max_u + 1) * KB * 64 > ld_u || (max_v + 1) * KB * 64 > ld_v) return fail("inbatch_grad: piece block outside the operand row");
   if ((max_ut + 1) * padB > ld_ut || (max_vt + 1) * padNI > ld_vt) return fail("inbatch_grad: piece block outside the transposed operand row");
   su.ytw = (int)padNI, sv.ytw = (int)padB;
   su.dshift = (int)diag0, sv.dshift = -(int)diag0;
@@ -434,13 +522,14 @@ extern "C" int b200rec_inbatch_grad(const void* u_op, int64_t ld_u, const int32_
   if (make_tmap_bf16_2d(&vt, vt_op, (uint64_t)E, (uint64_t)ld_vt, (uint64_t)ld_vt, (uint32_t)E)) return 1;
   if (a.atomic_u) B200_CUDA_OK(cudaMemset2DAsync(dU, sizeof(float) * (size_t)ld_du, 0, sizeof(float) * (size_t)E, (size_t)B, st));
   if (a.atomic_v) B200_CUDA_OK(cudaMemset2DAsync(dV, sizeof(float) * (size_t)ld_dv, 0, sizeof(float) * (size_t)E, (size_t)NI, st));
-  static int smem_set = 0;
-  if (smem_set < smem) {
-    B200_CUDA_OK(cudaFuncSetAttribute(inbatch_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM_LIMIT));
-    smem_set = IG_SMEM_LIMIT;
-  }
   const int units = a.units_u + sv.x_tiles * sv.splits;
-  inbatch_grad_kernel<<<units, IG_THREADS, smem, st>>>(ux, uy, ut, vx, vy, vt, a);
-  B200_LAUNCH_OK("inbatch_grad_kernel");
-  return 0;
+#define IG_CASE(EE, S, G) if (E == EE && nprod_s == S && nprod_g == G) return ig_launch<EE, S, G>(units, smem, st, ux, uy, ut, vx, vy, vt, a)
+  IG_CASE(64, 1, 1);
+  IG_CASE(64, 3, 3);
+  IG_CASE(64, 6, 3);
+  IG_CASE(128, 1, 1);
+  IG_CASE(128, 3, 3);
+  IG_CASE(128, 6, 3);
+#undef IG_CASE
+  return fail("inbatch_grad: unsupported configuration");
 }

@@ -10,6 +10,12 @@
 
 namespace b200 {
 
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct LseEpi {
   static constexpr bool kDbg = false;
   static constexpr int SCRATCH_BYTES = 64;
@@ -47,15 +53,42 @@ struct LseEpi {
       tmem_ld_32x32(taddr + c, v);
       tmem_ld_wait();
       const int lim = nvalid - c;
-      float cm = -INFINITY;
+      float mn, acc;
+      if (lim >= 32 && sc > 0.f) {
+        // full group (warp-uniform): max of the raw logits with 3-input maxima (scaling by sc > 0 is monotone), then one
+        // FFMA + MUFU.EX2 + FADD per logit on four independent partial sums
+        float c0 = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+        float c1 = fmax3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < lim) cm = fmaxf(cm, __uint_as_float(v[i]) * sc);
-      const float mn = fmaxf(m[a], cm);
-      float acc = 0.f;
+        for (int i = 6; i < 30; i += 6) {
+          c0 = fmax3(c0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+          c1 = fmax3(c1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+          c0 = fmaxf(c0, __uint_as_float(v[i + 4]));
+          c1 = fmaxf(c1, __uint_as_float(v[i + 5]));
+        }
+        c0 = fmax3(c0, __uint_as_float(v[30]), __uint_as_float(v[31]));
+        mn = fmaxf(m[a], fmaxf(c0, c1) * sc);
+        const float nmn = -mn;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < lim) acc += exp2f(fmaf(__uint_as_float(v[i]), sc, -mn));
+        for (int i = 0; i < 32; i += 4) {
+          a0 += ex2_fast(fmaf(__uint_as_float(v[i]), sc, nmn));
+          a1 += ex2_fast(fmaf(__uint_as_float(v[i + 1]), sc, nmn));
+          a2 += ex2_fast(fmaf(__uint_as_float(v[i + 2]), sc, nmn));
+          a3 += ex2_fast(fmaf(__uint_as_float(v[i + 3]), sc, nmn));
+        }
+        acc = (a0 + a1) + (a2 + a3);
+      } else {
+        float cm = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < lim) cm = fmaxf(cm, __uint_as_float(v[i]) * sc);
+        mn = fmaxf(m[a], cm);
+        acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < lim) acc += exp2f(fmaf(__uint_as_float(v[i]), sc, -mn));
+      }
       s[a] = s[a] * exp2f(m[a] - mn) + acc;
       m[a] = mn;
     }
