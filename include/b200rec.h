@@ -287,7 +287,8 @@ int b200rec_sample_negatives(const int64_t* user_of_row, int64_t B, const int64_
  * dU[b,:] = sum_j G[b,j] V[j,:],  dV[j,:] = sum_b G[b,j] U[b,:],  G = coef * (*coef_dev) * (exp(<u_b,v_j>*inv_t - lse[b])
  * - [j == diag0 + b]) — the gradient of mean-CE(U V^T / T, arange) that autograd derives for reference
  * src/models/two_tower.py:470-477.  u_op / v_op: split-bf16 row operands as b200rec_split_bf16 writes them
- * ([B | NI, blocks * pad64(E)]); ut_op / vt_op: operands of the TRANSPOSES ([E, blocks * pad64(B | NI)]).
+ * ([B | NI, blocks * pad64(E)]); ut_op / vt_op / ld_ut / ld_vt / ut_pieces_host / vt_pieces_host are IGNORED (may be
+ * NULL / 0): the gradient GEMMs read the row operands as MN-major tiles, no transposed copies are needed.
  * *_pieces_host[p]: block index of piece p (0 = h, 1 = m, 2 = l) inside an operand row.  nprod_s = 1 | 3 | 6 piece
  * products recompute the logits, nprod_g = 1 | 3 form the two gradient GEMMs.  E must be 64 or 128
  * (b200rec_inbatch_grad_supported tells; callers fall back to the chunked GEMM path otherwise).  dU / dV are written

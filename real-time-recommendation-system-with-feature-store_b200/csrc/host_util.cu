@@ -27,6 +27,14 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
                       uint32_t box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled not available from the driver");
+  // cuTensorMapEncodeTiled is a DRIVER call: on a thread that has made no runtime call yet (the autograd engine's
+  // worker thread running a backward whose first library call builds tensor maps) no context is current and it fails
+  // with CUDA_ERROR_INVALID_CONTEXT.  cudaFree(nullptr) binds the device's primary context to the calling thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail("TMA base pointer must be 16-byte aligned");
   if ((ld * 2) % 16 != 0) return fail("TMA row pitch must be a multiple of 16 bytes (ld=%llu)", (unsigned long long)ld);
   if (box_rows == 0 || box_rows > 256) return fail("TMA box rows out of range: %u", box_rows);

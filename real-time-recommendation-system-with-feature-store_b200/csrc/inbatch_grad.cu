@@ -51,8 +51,6 @@ struct IgSide {
   int lse_by_col;
   int xp[3];           // 64-column block index of pieces h, m, l inside X's operand rows
   int yp[3];           // same for Y's operand rows
-  int tp[2];           // block index of pieces h, m inside Y^T's operand rows (block width = ytw columns)
-  int ytw;             // pad64(ycols): columns per piece block of the transposed operand
   float* out;
   long long ld_out;
 };
@@ -79,14 +77,15 @@ struct IgCfg {
   static constexpr int PG = NPG == 1 ? 1 : 2;                    // pieces of G / Y^T
   static constexpr int X_BYTES = PS * KB * IG_BM * 128;
   static constexpr int YS_BYTES = PS * KB * IG_BN * 128;          // Y pieces of one stage
-  static constexpr int YT_BYTES = PG * E * 128;                   // Y^T pieces of one stage (one 64-column k-block)
-  static constexpr int STAGE = YS_BYTES + YT_BYTES;
+  static constexpr int STAGE = YS_BYTES;   // the gradient GEMM reads the same Y pieces as an MN-major operand (no Y^T copy)
   static constexpr int G_BYTES = PG * IG_BM * 128;
   static constexpr int FIXED = 1024 + 256 + X_BYTES;
   static constexpr int NG = (IG_SMEM_LIMIT - FIXED - 2 * G_BYTES) / STAGE >= 2 ? 2 : 1;
   static constexpr int NST_RAW = (IG_SMEM_LIMIT - FIXED - NG * G_BYTES) / STAGE;
   static constexpr int NST = NST_RAW > 4 ? 4 : NST_RAW;
-  static constexpr bool OK = NST >= 2;
+  static constexpr bool OK = NST >= 2 && PS >= PG;
+  static constexpr int LOOKAHEAD = NST >= 3 ? 2 : 1;   // logits tiles issued ahead of the gradient GEMM (< NST: a stage is
+                                                       // only refilled after the gradient GEMM of its tile)
   static constexpr int NACC = (512 - 2 * IG_BN) / E > 4 ? 4 : (512 - 2 * IG_BN) / E;
   static constexpr int SMEM = FIXED + NST * STAGE + NG * G_BYTES;
 };
@@ -94,12 +93,10 @@ struct IgCfg {
 template <int E, int NPS, int NPG>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_constant__ CUtensorMap tm_uy,
-                    const __grid_constant__ CUtensorMap tm_ut, const __grid_constant__ CUtensorMap tm_vx,
-                    const __grid_constant__ CUtensorMap tm_vy, const __grid_constant__ CUtensorMap tm_vt,
-                    const IgArgs a) {
+                    const __grid_constant__ CUtensorMap tm_vx, const __grid_constant__ CUtensorMap tm_vy, const IgArgs a) {
   using C = IgCfg<E, NPS, NPG>;
   constexpr int KB = C::KB, PS = C::PS, PG = C::PG, NST = C::NST, NG = C::NG, NACC = C::NACC;
-  constexpr int STAGE = C::STAGE, YS_BYTES = C::YS_BYTES, G_BYTES = C::G_BYTES;
+  constexpr int STAGE = C::STAGE, G_BYTES = C::G_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -113,7 +110,6 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
   if (T > sd.tiles_per_unit) T = sd.tiles_per_unit;
   const CUtensorMap* tmx = mode ? &tm_vx : &tm_ux;   // X operand, box 128 rows
   const CUtensorMap* tmy = mode ? &tm_uy : &tm_vy;   // Y operand, box 64 rows
-  const CUtensorMap* tmt = mode ? &tm_ut : &tm_vt;   // Y^T operand, box E rows
 
   uint8_t* x_smem = smem;
   uint8_t* st_smem = x_smem + C::X_BYTES;
@@ -132,7 +128,6 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(tmx);
     tma_prefetch_desc(tmy);
-    tma_prefetch_desc(tmt);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < 4; ++s) {
@@ -181,9 +176,6 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb)
               tma_load_2d(dst + (p * KB + kb) * (IG_BN * 128), tmy, &full_bar[st], (sd.yp[p] * KB + kb) * 64, yrow);
-#pragma unroll
-          for (int p = 0; p < PG; ++p)
-            tma_load_2d(dst + YS_BYTES + p * (E * 128), tmt, &full_bar[st], sd.tp[p] * sd.ytw + yrow, 0);
         }
         __syncwarp();
         if (++st == NST) st = 0, eph ^= 1;
@@ -191,12 +183,16 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
     } else if (warp == 1) {
       // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, elected lane)
       constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((IG_BN >> 3) << 17) | ((IG_BM >> 4) << 24);
-      constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | ((E >> 3) << 17) | ((IG_BM >> 4) << 24);
+      // gradient GEMM: OUT[128, E] += G[128, 64] . Y[64, E]; B = the Y tile as loaded for the logits GEMM ([64 rows][128 B
+      // of E], SW128), read as an MN-major operand: N = E contiguous, K = the tile's rows 128 B apart (8-row groups 1024 B
+      // = SBO), 64-wide E blocks one piece block apart (LBO)
+      constexpr uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((E >> 3) << 17) | ((IG_BM >> 4) << 24);
       // piece products, smallest first (they are added in this order): (x piece, y piece)
       constexpr int PX[6] = {1, 2, 0, 1, 0, 0}, PY[6] = {1, 0, 2, 0, 1, 0};
       constexpr int P0 = 6 - NPS;   // first product used: 6 -> 0, 3 -> 3, 1 -> 5
       const uint64_t x_desc = umma_desc_k_sw128(smem_u32(x_smem));
       const uint64_t st_desc = umma_desc_k_sw128(smem_u32(st_smem));
+      const uint64_t yt_desc = umma_desc_mn_sw128(smem_u32(st_smem), IG_BN * 128, 1024);
       const uint64_t g_desc = umma_desc_k_sw128(smem_u32(g_smem));
       mbar_wait(x_full, 0);
       tc_fence_after();
@@ -233,16 +229,16 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
         if (elect_one()) {
           const uint32_t d_addr = tmem_base + OUT_COL + o_acc * E;
           const uint64_t a_base = g_desc + static_cast<uint64_t>((gb * G_BYTES) >> 4);
-          const uint64_t b_base = st_desc + static_cast<uint64_t>((o_st * STAGE + YS_BYTES) >> 4);
+          const uint64_t b_base = yt_desc + static_cast<uint64_t>((o_st * STAGE) >> 4);
           const uint32_t keep = t >= NACC ? 1u : 0u;
-          // products (G piece, Y^T piece): m.h, h.m, h.h  (or h.h alone)
+          // products (G piece, Y piece): m.h, h.m, h.h  (or h.h alone); one MMA contracts 16 tile rows = 2048 B
 #pragma unroll
           for (int pr = (NPG == 3 ? 0 : 2); pr < 3; ++pr) {
             const uint64_t a_desc = a_base + (((pr == 0 ? 1 : 0) * (IG_BM * 128)) >> 4);
-            const uint64_t b_desc = b_base + (((pr == 1 ? 1 : 0) * (E * 128)) >> 4);
+            const uint64_t b_desc = b_base + (((pr == 1 ? 1 : 0) * KB * (IG_BN * 128)) >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(d_addr, a_desc + 2 * k, b_desc + 2 * k, idesc_o, (pr == (NPG == 3 ? 0 : 2) && k == 0) ? keep : 1u);
+              umma_bf16(d_addr, a_desc + 2 * k, b_desc + 128 * k, idesc_o, (pr == (NPG == 3 ? 0 : 2) && k == 0) ? keep : 1u);
           }
           umma_commit(&g_empty[gb]);
           umma_commit(&empty_bar[o_st]);
@@ -252,9 +248,12 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
         if (++o_st == NST) o_st = 0;
         if (++o_acc == NACC) o_acc = 0;
       };
-      issue_s(0);
+      // logits tiles run LOOKAHEAD ahead of the gradient GEMM: S(t + 2) is issued as soon as the epilogue has read S(t)
+      // out of its TMEM buffer, so the epilogue of tile t + 1 never waits for the tensor core or for this warp
+      constexpr int LA = C::LOOKAHEAD;
+      for (int t = 0; t < LA && t < T; ++t) issue_s(t);
       for (int t = 0; t < T; ++t) {
-        if (t + 1 < T) issue_s(t + 1);   // the tensor core recomputes the next logits tile while the epilogue builds G(t)
+        if (t + LA < T) issue_s(t + LA);
         issue_o(t);
       }
     } else if (warp >= 4) {
@@ -443,8 +442,8 @@ static int ig_plan(IgArgs& a, int64_t B, int64_t NI, int E, int nprod_s, int npr
 }
 
 template <int E, int NPS, int NPG>
-static int ig_launch(int units, int smem, cudaStream_t st, const CUtensorMap& ux, const CUtensorMap& uy, const CUtensorMap& ut,
-                     const CUtensorMap& vx, const CUtensorMap& vy, const CUtensorMap& vt, const IgArgs& a) {
+static int ig_launch(int units, int smem, cudaStream_t st, const CUtensorMap& ux, const CUtensorMap& uy,
+                     const CUtensorMap& vx, const CUtensorMap& vy, const IgArgs& a) {
   if constexpr (IgCfg<E, NPS, NPG>::OK) {
     auto kern = inbatch_grad_kernel<E, NPS, NPG>;
     static bool attr = false;
@@ -452,7 +451,7 @@ static int ig_launch(int units, int smem, cudaStream_t st, const CUtensorMap& ux
       B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM_LIMIT));
       attr = true;
     }
-    kern<<<units, IG_THREADS, smem, st>>>(ux, uy, ut, vx, vy, vt, a);
+    kern<<<units, IG_THREADS, smem, st>>>(ux, uy, vx, vy, a);
     B200_LAUNCH_OK("inbatch_grad_kernel");
     return 0;
   } else {
@@ -477,8 +476,10 @@ extern "C" int b200rec_inbatch_grad(const void* u_op, int64_t ld_u, const int32_
                                     const int32_t* vt_pieces_host, int64_t B, int64_t NI, int E, int nprod_s, int nprod_g,
                                     float inv_t, const float* lse, int64_t diag0, float coef, const float* coef_dev,
                                     float* dU, int64_t ld_du, float* dV, int64_t ld_dv, void* stream) {
-  if (!u_op || !v_op || !ut_op || !vt_op || !lse || !dU || !dV) return fail("inbatch_grad: null pointer");
-  if (!u_pieces_host || !v_pieces_host || !ut_pieces_host || !vt_pieces_host) return fail("inbatch_grad: null piece table");
+  // ut_op / vt_op (transposed operands) are no longer read: the gradient GEMM takes the row operands as MN-major tiles.
+  (void)ut_op, (void)ld_ut, (void)ut_pieces_host, (void)vt_op, (void)ld_vt, (void)vt_pieces_host;
+  if (!u_op || !v_op || !lse || !dU || !dV) return fail("inbatch_grad: null pointer");
+  if (!u_pieces_host || !v_pieces_host) return fail("inbatch_grad: null piece table");
   if (B <= 0 || NI <= 0 || B > INT32_MAX / 2 || NI > INT32_MAX / 2) return fail("inbatch_grad: bad sizes");
   if (diag0 < 0 || diag0 + B > NI) return fail("inbatch_grad: positives [diag0, diag0 + B) must lie inside the item rows");
   if ((ld_du & 3) || (ld_dv & 3) || (reinterpret_cast<uintptr_t>(dU) & 15) || (reinterpret_cast<uintptr_t>(dV) & 15))
@@ -488,23 +489,16 @@ extern "C" int b200rec_inbatch_grad(const void* u_op, int64_t ld_u, const int32_
   if (ig_plan(a, B, NI, E, nprod_s, nprod_g, smem)) return 1;
   const int KB = E / 64;
   const int ps = nprod_s == 1 ? 1 : (nprod_s == 3 ? 2 : 3), pg = nprod_g == 1 ? 1 : 2;
-  const int64_t padB = (B + 63) / 64 * 64, padNI = (NI + 63) / 64 * 64;
   IgSide& su = a.side[0];
   IgSide& sv = a.side[1];
-  int max_u = 0, max_v = 0, max_ut = 0, max_vt = 0;
-  for (int p = 0; p < 3; ++p) {
+  int max_u = 0, max_v = 0;
+  for (int p = 0; p < 3; ++p) {   // pieces h, m, l of the row operands (the gradient GEMM uses h, m of the same blocks)
     su.xp[p] = sv.yp[p] = p < ps ? u_pieces_host[p] : 0;
     su.yp[p] = sv.xp[p] = p < ps ? v_pieces_host[p] : 0;
     if (p < ps) max_u = max_u > u_pieces_host[p] ? max_u : u_pieces_host[p], max_v = max_v > v_pieces_host[p] ? max_v : v_pieces_host[p];
   }
-  for (int p = 0; p < 2; ++p) {
-    su.tp[p] = p < pg ? vt_pieces_host[p] : 0;   // mode U contracts with V^T
-    sv.tp[p] = p < pg ? ut_pieces_host[p] : 0;
-    if (p < pg) max_vt = max_vt > vt_pieces_host[p] ? max_vt : vt_pieces_host[p], max_ut = max_ut > ut_pieces_host[p] ? max_ut : ut_pieces_host[p];
-  }
+  if (pg > ps) return fail("inbatch_grad: the gradient GEMM needs the m piece of the row operands");
   if ((max_u + 1) * KB * 64 > ld_u || (max_v + 1) * KB * 64 > ld_v) return fail("inbatch_grad: piece block outside the operand row");
-  if ((max_ut + 1) * padB > ld_ut || (max_vt + 1) * padNI > ld_vt) return fail("inbatch_grad: piece block outside the transposed operand row");
-  su.ytw = (int)padNI, sv.ytw = (int)padB;
   su.dshift = (int)diag0, sv.dshift = -(int)diag0;
   su.lse_by_col = 0, sv.lse_by_col = 1;
   su.out = dU, su.ld_out = ld_du, sv.out = dV, sv.ld_out = ld_dv;
@@ -513,17 +507,15 @@ extern "C" int b200rec_inbatch_grad(const void* u_op, int64_t ld_u, const int32_
   a.coef_dev = coef_dev;
   a.lse = lse;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  CUtensorMap ux, uy, ut, vx, vy, vt;
+  CUtensorMap ux, uy, vx, vy;
   if (make_tmap_bf16_2d(&ux, u_op, (uint64_t)B, (uint64_t)ld_u, (uint64_t)ld_u, IG_BM)) return 1;
   if (make_tmap_bf16_2d(&uy, u_op, (uint64_t)B, (uint64_t)ld_u, (uint64_t)ld_u, IG_BN)) return 1;
-  if (make_tmap_bf16_2d(&ut, ut_op, (uint64_t)E, (uint64_t)ld_ut, (uint64_t)ld_ut, (uint32_t)E)) return 1;
   if (make_tmap_bf16_2d(&vx, v_op, (uint64_t)NI, (uint64_t)ld_v, (uint64_t)ld_v, IG_BM)) return 1;
   if (make_tmap_bf16_2d(&vy, v_op, (uint64_t)NI, (uint64_t)ld_v, (uint64_t)ld_v, IG_BN)) return 1;
-  if (make_tmap_bf16_2d(&vt, vt_op, (uint64_t)E, (uint64_t)ld_vt, (uint64_t)ld_vt, (uint32_t)E)) return 1;
   if (a.atomic_u) B200_CUDA_OK(cudaMemset2DAsync(dU, sizeof(float) * (size_t)ld_du, 0, sizeof(float) * (size_t)E, (size_t)B, st));
   if (a.atomic_v) B200_CUDA_OK(cudaMemset2DAsync(dV, sizeof(float) * (size_t)ld_dv, 0, sizeof(float) * (size_t)E, (size_t)NI, st));
   const int units = a.units_u + sv.x_tiles * sv.splits;
-#define IG_CASE(EE, S, G) if (E == EE && nprod_s == S && nprod_g == G) return ig_launch<EE, S, G>(units, smem, st, ux, uy, ut, vx, vy, vt, a)
+#define IG_CASE(EE, S, G) if (E == EE && nprod_s == S && nprod_g == G) return ig_launch<EE, S, G>(units, smem, st, ux, uy, vx, vy, a)
   IG_CASE(64, 1, 1);
   IG_CASE(64, 3, 3);
   IG_CASE(64, 6, 3);

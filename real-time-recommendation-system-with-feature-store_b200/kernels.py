@@ -396,18 +396,18 @@ def inbatch_grad_supported(B: int, NI: int, E: int, nprod_s: int, nprod_g: int) 
     return bool(N.lib().b200rec_inbatch_grad_supported(B, NI, E, nprod_s, nprod_g))
 
 
-def inbatch_grad(u_op, u_blocks, v_op, v_blocks, ut_op, ut_blocks, vt_op, vt_blocks, B: int, NI: int, E: int,
-                 nprod_s: int, nprod_g: int, inv_t: float, lse, diag0: int, coef: float, coef_dev, dU, dV) -> None:
+def inbatch_grad(u_op, u_blocks, v_op, v_blocks, B: int, NI: int, E: int, nprod_s: int, nprod_g: int, inv_t: float, lse,
+                 diag0: int, coef: float, coef_dev, dU, dV) -> None:
     """Fused in-batch loss backward (csrc/inbatch_grad.cu): logits recomputed tile-wise in TMEM, G = softmax - onehot
-    formed in registers, both gradient GEMMs fed from shared memory.  Writes dU [B,E] and dV [NI,E] completely."""
+    formed in registers, both gradient GEMMs fed from shared memory (the row operands double as the MN-major operand of
+    the gradient GEMMs: no transposed copies).  Writes dU [B,E] and dV [NI,E] completely."""
     def tab(blocks):
         b = list(blocks) + [0] * (3 - len(blocks))
         return (_C.c_int32 * 3)(*b)
     N.check(N.lib().b200rec_inbatch_grad(N.ptr(u_op), u_op.stride(0), tab(u_blocks), N.ptr(v_op), v_op.stride(0), tab(v_blocks),
-                                         N.ptr(ut_op), ut_op.stride(0), tab(ut_blocks), N.ptr(vt_op), vt_op.stride(0),
-                                         tab(vt_blocks), B, NI, E, nprod_s, nprod_g, float(inv_t), N.ptr(lse), int(diag0),
-                                         float(coef), N.ptr(coef_dev), N.ptr(dU), dU.stride(0), N.ptr(dV), dV.stride(0),
-                                         N.stream()), "inbatch_grad")
+                                         None, 0, None, None, 0, None, B, NI, E, nprod_s, nprod_g, float(inv_t), N.ptr(lse),
+                                         int(diag0), float(coef), N.ptr(coef_dev), N.ptr(dU), dU.stride(0), N.ptr(dV),
+                                         dV.stride(0), N.stream()), "inbatch_grad")
 
 
 def lse_rows(S, scale: float, diag0: int, want_pos: bool):

@@ -507,12 +507,8 @@ class InBatchCEFn(Function):
         if os.environ.get("B200REC_INBATCH_BWD") != "chunked" and K.inbatch_grad_supported(B, NI, E, nps, npg):
             du = torch.empty_like(u)
             di = torch.empty_like(i)
-            tt = 1 if terms == 1 else 3
-            ut = K.split_bf16(u, tt, 0, transpose=True)               # [E, tt*pad64(B)]  pieces h (, m)
-            it = K.split_bf16(i, tt, 0, transpose=True)               # [E, tt*pad64(NI)]
-            K.inbatch_grad(uo, K.PIECE_BLOCKS[(terms, 0)], io, K.PIECE_BLOCKS[(terms, 1)], ut, K.PIECE_BLOCKS[(tt, 0)],
-                           it, K.PIECE_BLOCKS[(tt, 0)], B, NI, E, nps, npg, inv_t, lse, diag_offset, inv_t / total_rows,
-                           gdev, du, di)
+            K.inbatch_grad(uo, K.PIECE_BLOCKS[(terms, 0)], io, K.PIECE_BLOCKS[(terms, 1)], B, NI, E, nps, npg, inv_t, lse,
+                           diag_offset, inv_t / total_rows, gdev, du, di)
             return du, di, None, None, None, None
         du = torch.empty_like(u)
         di = torch.zeros_like(i)
