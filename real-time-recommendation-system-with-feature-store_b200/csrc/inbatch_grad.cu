@@ -34,6 +34,24 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 lanes x K bf16, two per 32-bit column) comes from tensor memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 8 consecutive 32-bit columns: thread t of the warp writes TMEM lane (base_lane + t)
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 constexpr int IG_EPI_WARPS = 16;                 // epilogue warps: 4 per TMEM lane quarter, 16 logit columns each
 constexpr int IG_THREADS = (4 + IG_EPI_WARPS) * 32;
 constexpr int IG_BM = 128;        // X rows per unit
@@ -78,16 +96,19 @@ struct IgCfg {
   static constexpr int X_BYTES = PS * KB * IG_BM * 128;
   static constexpr int YS_BYTES = PS * KB * IG_BN * 128;          // Y pieces of one stage
   static constexpr int STAGE = YS_BYTES;   // the gradient GEMM reads the same Y pieces as an MN-major operand (no Y^T copy)
-  static constexpr int G_BYTES = PG * IG_BM * 128;
   static constexpr int FIXED = 1024 + 256 + X_BYTES;
-  static constexpr int NG = (IG_SMEM_LIMIT - FIXED - 2 * G_BYTES) / STAGE >= 2 ? 2 : 1;
-  static constexpr int NST_RAW = (IG_SMEM_LIMIT - FIXED - NG * G_BYTES) / STAGE;
+  static constexpr int NG = 2;                  // G buffers (tensor memory: PG pieces x 32 columns each)
+  static constexpr int G_COLS = PG * (IG_BN / 2);
+  static constexpr int NST_RAW = (IG_SMEM_LIMIT - FIXED) / STAGE;
   static constexpr int NST = NST_RAW > 4 ? 4 : NST_RAW;
   static constexpr bool OK = NST >= 2 && PS >= PG;
   static constexpr int LOOKAHEAD = NST >= 3 ? 2 : 1;   // logits tiles issued ahead of the gradient GEMM (< NST: a stage is
                                                        // only refilled after the gradient GEMM of its tile)
-  static constexpr int NACC = (512 - 2 * IG_BN) / E > 4 ? 4 : (512 - 2 * IG_BN) / E;
-  static constexpr int SMEM = FIXED + NST * STAGE + NG * G_BYTES;
+  // TMEM columns: S0 [0,64) | S1 [64,128) | G buffers [128, 128 + NG*G_COLS) | OUT accumulators [256, 256 + NACC*E)
+  static constexpr int G_COL0 = 2 * IG_BN;
+  static constexpr int OUT_COL0 = 256;
+  static constexpr int NACC = (512 - OUT_COL0) / E > 4 ? 4 : (512 - OUT_COL0) / E;
+  static constexpr int SMEM = FIXED + NST * STAGE;
 };
 
 template <int E, int NPS, int NPG>
@@ -96,7 +117,7 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
                     const __grid_constant__ CUtensorMap tm_vx, const __grid_constant__ CUtensorMap tm_vy, const IgArgs a) {
   using C = IgCfg<E, NPS, NPG>;
   constexpr int KB = C::KB, PS = C::PS, PG = C::PG, NST = C::NST, NG = C::NG, NACC = C::NACC;
-  constexpr int STAGE = C::STAGE, G_BYTES = C::G_BYTES;
+  constexpr int STAGE = C::STAGE, G_COLS = C::G_COLS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -113,8 +134,7 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
 
   uint8_t* x_smem = smem;
   uint8_t* st_smem = x_smem + C::X_BYTES;
-  uint8_t* g_smem = st_smem + NST * STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(g_smem + NG * G_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(st_smem + NST * STAGE);
   uint64_t* full_bar = bars;            // [4]
   uint64_t* empty_bar = bars + 4;       // [4]
   uint64_t* s_full = bars + 8;          // [2]
@@ -149,7 +169,7 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t OUT_COL = 2 * IG_BN;   // TMEM columns: S0 [0,64) | S1 [64,128) | OUT accumulators [128, 128 + NACC*E)
+  constexpr uint32_t OUT_COL = C::OUT_COL0, G_COL = C::G_COL0;
 
   if (T > 0) {
     if (warp == 0) {
@@ -193,7 +213,6 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
       const uint64_t x_desc = umma_desc_k_sw128(smem_u32(x_smem));
       const uint64_t st_desc = umma_desc_k_sw128(smem_u32(st_smem));
       const uint64_t yt_desc = umma_desc_mn_sw128(smem_u32(st_smem), IG_BN * 128, 1024);
-      const uint64_t g_desc = umma_desc_k_sw128(smem_u32(g_smem));
       mbar_wait(x_full, 0);
       tc_fence_after();
       int s_st = 0, o_st = 0, o_acc = 0;       // stage of the next logits tile / of the next gradient tile, accumulator
@@ -228,17 +247,17 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
         tc_fence_after();
         if (elect_one()) {
           const uint32_t d_addr = tmem_base + OUT_COL + o_acc * E;
-          const uint64_t a_base = g_desc + static_cast<uint64_t>((gb * G_BYTES) >> 4);
+          const uint32_t a_base = tmem_base + G_COL + gb * G_COLS;   // G(t) pieces h | m, 32 columns each, in TMEM
           const uint64_t b_base = yt_desc + static_cast<uint64_t>((o_st * STAGE) >> 4);
           const uint32_t keep = t >= NACC ? 1u : 0u;
           // products (G piece, Y piece): m.h, h.m, h.h  (or h.h alone); one MMA contracts 16 tile rows = 2048 B
 #pragma unroll
           for (int pr = (NPG == 3 ? 0 : 2); pr < 3; ++pr) {
-            const uint64_t a_desc = a_base + (((pr == 0 ? 1 : 0) * (IG_BM * 128)) >> 4);
+            const uint32_t a_addr = a_base + (pr == 0 ? 1 : 0) * (IG_BN / 2);
             const uint64_t b_desc = b_base + (((pr == 1 ? 1 : 0) * KB * (IG_BN * 128)) >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d_addr, a_desc + 2 * k, b_desc + 128 * k, idesc_o, (pr == (NPG == 3 ? 0 : 2) && k == 0) ? keep : 1u);
+            for (int k = 0; k < 4; ++k)   // 16 contraction indices = 8 TMEM columns of A, 16 tile rows of B
+              umma_bf16_ts(d_addr, a_addr + 8 * k, b_desc + 128 * k, idesc_o, (pr == (NPG == 3 ? 0 : 2) && k == 0) ? keep : 1u);
           }
           umma_commit(&g_empty[gb]);
           umma_commit(&empty_bar[o_st]);
@@ -319,40 +338,27 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
 #pragma unroll
           for (int i = 0; i < 16; ++i) gv[i] = (c0 + i < sd.ycols) ? gv[i] : 0.f;
         }
-        // G(t) -> shared memory, K-major SW128: row r at r*128 B, 16-byte chunk j stored at position j ^ (r & 7).
-        mbar_wait(&g_empty[gb], (((NG == 2 ? (t >> 1) : t) & 1) ^ 1));
-        uint8_t* gbase = g_smem + gb * G_BYTES + row_l * 128;
-        if constexpr (PG == 2) {
+        // G(t) -> tensor memory as the A operand of the gradient GEMM: lane = row, two bf16 per 32-bit column, piece h in
+        // columns [0,32) of the buffer, piece m in [32,64); this thread owns 8 columns (its 16 logit columns) of each
+        mbar_wait(&g_empty[gb], (((t >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t gaddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + G_COL + gb * G_COLS + part * 8;
+        uint32_t hw[8], mw[8];
 #pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
-            uint32_t hw[4], mw[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {   // x = h + m: h = rn_bf16(x), m = rn_bf16(x - h) (the subtraction is exact)
-              const float f0 = gv[ch * 8 + 2 * j], f1 = gv[ch * 8 + 2 * j + 1];
-              const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
-              hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
-              const __nv_bfloat162 m2 = __floats2bfloat162_rn(f0 - __uint_as_float(hw[j] << 16),
-                                                              f1 - __uint_as_float(hw[j] & 0xFFFF0000u));
-              mw[j] = *reinterpret_cast<const uint32_t*>(&m2);
-            }
-            const int pos = ((part * 2 + ch) ^ (row_l & 7)) * 16;
-            *reinterpret_cast<uint4*>(gbase + pos) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(gbase + IG_BM * 128 + pos) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-          }
-        } else {
-#pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
-            uint32_t hw[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat162 h2 = __floats2bfloat162_rn(gv[ch * 8 + 2 * j], gv[ch * 8 + 2 * j + 1]);
-              hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
-            }
-            const int pos = ((part * 2 + ch) ^ (row_l & 7)) * 16;
-            *reinterpret_cast<uint4*>(gbase + pos) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        for (int j = 0; j < 8; ++j) {   // x = h + m: h = rn_bf16(x), m = rn_bf16(x - h) (the subtraction is exact)
+          const float f0 = gv[2 * j], f1 = gv[2 * j + 1];
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+          hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
+          if constexpr (PG == 2) {
+            const __nv_bfloat162 m2 = __floats2bfloat162_rn(f0 - __uint_as_float(hw[j] << 16),
+                                                            f1 - __uint_as_float(hw[j] & 0xFFFF0000u));
+            mw[j] = *reinterpret_cast<const uint32_t*>(&m2);
           }
         }
-        fence_proxy_async_smem();   // generic-proxy stores above must be visible to the tensor core's async-proxy reads
+        tmem_st_32x8(gaddr, hw);
+        if constexpr (PG == 2) tmem_st_32x8(gaddr + IG_BN / 2, mw);
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&g_full[gb]);
       }
