@@ -96,7 +96,8 @@ struct IgCfg {
   static constexpr int X_BYTES = PS * KB * IG_BM * 128;
   static constexpr int YS_BYTES = PS * KB * IG_BN * 128;          // Y pieces of one stage
   static constexpr int STAGE = YS_BYTES;   // the gradient GEMM reads the same Y pieces as an MN-major operand (no Y^T copy)
-  static constexpr int FIXED = 1024 + 256 + X_BYTES;
+  static constexpr int NL_BYTES = IG_MAX_UNIT_TILES * IG_BN * 4;   // -lse * log2e of the unit's columns (mode V)
+  static constexpr int FIXED = 1024 + 256 + NL_BYTES + X_BYTES;
   static constexpr int NG = 2;                  // G buffers (tensor memory: PG pieces x 32 columns each)
   static constexpr int G_COLS = PG * (IG_BN / 2);
   static constexpr int NST_RAW = (IG_SMEM_LIMIT - FIXED) / STAGE;
@@ -144,6 +145,7 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
   uint64_t* x_full = bars + 16;
   uint64_t* out_full = bars + 17;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  float* s_nl = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(tmx);
@@ -156,8 +158,8 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1);
-      mbar_init(&s_empty[b], IG_EPI_WARPS);
-      mbar_init(&g_full[b], IG_EPI_WARPS);
+      mbar_init(&s_empty[b], IG_EPI_WARPS / 2);   // the epilogue warps work in two groups, one per tile parity
+      mbar_init(&g_full[b], IG_EPI_WARPS / 2);
       mbar_init(&g_empty[b], 1);
     }
     mbar_init(x_full, 1);
@@ -165,6 +167,12 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (sd.lse_by_col) {   // mode V: the log-sum-exp belongs to the COLUMN (a user): stage this unit's slice once, prescaled
+    for (int i = threadIdx.x; i < T * IG_BN; i += IG_THREADS) {
+      const int c = t_begin * IG_BN + i;
+      s_nl[i] = c < sd.ycols ? -__ldg(a.lse + c) * 1.4426950408889634f : 0.f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -277,9 +285,14 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
       }
     } else if (warp >= 4) {
       // ---------------------------------------------------------------- epilogue: logits -> G pieces -> gradient rows
+      // Two groups of 8 warps: group g turns the logits tiles t = g, g + 2, ... into G (S buffer g, G buffer g), so two
+      // tiles are in flight and the groups' phases (TMEM load, MUFU, pack, TMEM store) interleave on every scheduler.
+      // Within a group: warp = TMEM lane quarter x 32-column half of the 64-column tile.
       const int ew = warp - 4;
       const int quarter = warp & 3;          // TMEM lanes 32*quarter .. +31 are accessible to this warp
-      const int part = ew >> 2;              // 16-column quarter of the logits tile
+      const int grp = ew >> 3;
+      const int half = (ew >> 2) & 1;
+      const int part = ew >> 2;              // output stage: E/4 columns of the gradient rows per warp
       const int row_l = quarter * 32 + lane;
       const long long row_g = (long long)x_tile * IG_BM + row_l;
       const bool row_ok = row_g < sd.rows;
@@ -291,76 +304,74 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
       // (rows, ycols < 2^30).  Rows beyond sd.rows need no masking: row r of G only feeds row r of OUT, which is not
       // stored; columns beyond ycols are masked in the (warp-uniform) tail tile only.
       const int hot = (int)row_g + sd.dshift;
-      const bool lse_vec = sd.lse_by_col && ((reinterpret_cast<uintptr_t>(a.lse) & 15) == 0);
-      for (int t = 0; t < T; ++t) {
-        const int buf = t & 1, gb = t & (NG - 1);
-        const int c0 = (t_begin + t) * IG_BN + part * 16;
-        const bool tail = c0 + 16 > sd.ycols;                      // warp-uniform
-        float nl[16];
-        if (sd.lse_by_col) {
-          if (lse_vec && !tail) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 l4 = __ldg(reinterpret_cast<const float4*>(a.lse + c0) + j);
-              nl[4 * j] = -l4.x * LOG2E, nl[4 * j + 1] = -l4.y * LOG2E, nl[4 * j + 2] = -l4.z * LOG2E, nl[4 * j + 3] = -l4.w * LOG2E;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int c = c0 + i;
-              nl[i] = -__ldg(a.lse + (c < sd.ycols ? c : sd.ycols - 1)) * LOG2E;
-            }
-          }
-        }
-        mbar_wait(&s_full[buf], (t >> 1) & 1);
+      const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+      for (int t = grp; t < T; t += 2) {
+        const int buf = grp;                                       // == t & 1
+        const uint32_t par = (t >> 1) & 1;
+        const int cb = (t_begin + t) * IG_BN + half * 32;          // first global column of this warp's 32
+        mbar_wait(&s_full[buf], par);
         tc_fence_after();
-        uint32_t v[16];
-        tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * IG_BN + part * 16, v);
+        uint32_t v[2][16];
+        tmem_ld_32x16(lane_base + buf * IG_BN + half * 32, v[0]);
+        tmem_ld_32x16(lane_base + buf * IG_BN + half * 32 + 16, v[1]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[buf]);
-        // G = coef * (2^(S * scale - lse * log2e) - onehot): one FFMA, one MUFU.EX2 and one FMUL per element
-        float gv[16];
-        if (sd.lse_by_col) {
+        const uint32_t gaddr = lane_base + G_COL + buf * G_COLS + half * 16;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) gv[i] = coef * ex2_approx(fmaf(__uint_as_float(v[i]), a.scale_log2, nl[i]));
-        } else {
+        for (int hh = 0; hh < 2; ++hh) {
+          const int c0 = cb + hh * 16;
+          // G = coef * (2^(S * scale - lse * log2e) - onehot): one FFMA, one MUFU.EX2 and one FMUL per element
+          float gv[16];
+          if (sd.lse_by_col) {
+            const float4* nl4 = reinterpret_cast<const float4*>(s_nl + (c0 - t_begin * IG_BN));
 #pragma unroll
-          for (int i = 0; i < 16; ++i) gv[i] = coef * ex2_approx(fmaf(__uint_as_float(v[i]), a.scale_log2, nl_row));
-        }
-        const int d = hot - c0;                                    // position of the positive inside this thread's 16 columns
-        if (__any_sync(0xffffffffu, static_cast<unsigned>(d) < 16u)) {
+            for (int j = 0; j < 4; ++j) {
+              const float4 n4 = nl4[j];
+              gv[4 * j] = coef * ex2_approx(fmaf(__uint_as_float(v[hh][4 * j]), a.scale_log2, n4.x));
+              gv[4 * j + 1] = coef * ex2_approx(fmaf(__uint_as_float(v[hh][4 * j + 1]), a.scale_log2, n4.y));
+              gv[4 * j + 2] = coef * ex2_approx(fmaf(__uint_as_float(v[hh][4 * j + 2]), a.scale_log2, n4.z));
+              gv[4 * j + 3] = coef * ex2_approx(fmaf(__uint_as_float(v[hh][4 * j + 3]), a.scale_log2, n4.w));
+            }
+          } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) gv[i] -= (i == d) ? coef : 0.f;
-        }
-        if (tail) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) gv[i] = (c0 + i < sd.ycols) ? gv[i] : 0.f;
-        }
-        // G(t) -> tensor memory as the A operand of the gradient GEMM: lane = row, two bf16 per 32-bit column, piece h in
-        // columns [0,32) of the buffer, piece m in [32,64); this thread owns 8 columns (its 16 logit columns) of each
-        mbar_wait(&g_empty[gb], (((t >> 1) & 1) ^ 1));
-        tc_fence_after();
-        const uint32_t gaddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + G_COL + gb * G_COLS + part * 8;
-        uint32_t hw[8], mw[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {   // x = h + m: h = rn_bf16(x), m = rn_bf16(x - h) (the subtraction is exact)
-          const float f0 = gv[2 * j], f1 = gv[2 * j + 1];
-          const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
-          hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
-          if constexpr (PG == 2) {
-            const __nv_bfloat162 m2 = __floats2bfloat162_rn(f0 - __uint_as_float(hw[j] << 16),
-                                                            f1 - __uint_as_float(hw[j] & 0xFFFF0000u));
-            mw[j] = *reinterpret_cast<const uint32_t*>(&m2);
+            for (int i = 0; i < 16; ++i) gv[i] = coef * ex2_approx(fmaf(__uint_as_float(v[hh][i]), a.scale_log2, nl_row));
           }
+          const int d = hot - c0;                                  // position of the positive inside these 16 columns
+          if (__any_sync(0xffffffffu, static_cast<unsigned>(d) < 16u)) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) gv[i] -= (i == d) ? coef : 0.f;
+          }
+          if (c0 + 16 > sd.ycols) {                                // warp-uniform: tail tile
+#pragma unroll
+            for (int i = 0; i < 16; ++i) gv[i] = (c0 + i < sd.ycols) ? gv[i] : 0.f;
+          }
+          // G(t) -> tensor memory as the A operand of the gradient GEMM: lane = row, two bf16 per 32-bit column, piece h
+          // in columns [0,32) of the buffer, piece m in [32,64); 16 logit columns = 8 TMEM columns of each piece
+          uint32_t hw[8], mw[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {   // x = h + m: h = rn_bf16(x), m = rn_bf16(x - h) (the subtraction is exact)
+            const float f0 = gv[2 * j], f1 = gv[2 * j + 1];
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+            hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            if constexpr (PG == 2) {
+              const __nv_bfloat162 m2 = __floats2bfloat162_rn(f0 - __uint_as_float(hw[j] << 16),
+                                                              f1 - __uint_as_float(hw[j] & 0xFFFF0000u));
+              mw[j] = *reinterpret_cast<const uint32_t*>(&m2);
+            }
+          }
+          if (hh == 0) {   // the gradient GEMM of tile t - 2 must have consumed this G buffer
+            mbar_wait(&g_empty[buf], par ^ 1);
+            tc_fence_after();
+          }
+          tmem_st_32x8(gaddr + hh * 8, hw);
+          if constexpr (PG == 2) tmem_st_32x8(gaddr + IG_BN / 2 + hh * 8, mw);
         }
-        tmem_st_32x8(gaddr, hw);
-        if constexpr (PG == 2) tmem_st_32x8(gaddr + IG_BN / 2, mw);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&g_full[gb]);
+        if (lane == 0) mbar_arrive(&g_full[buf]);
       }
       // gradient rows: sum the NACC accumulators with round-to-nearest adds, store (or add when the tile was split)
       mbar_wait(out_full, 0);
