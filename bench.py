@@ -564,23 +564,45 @@ def run_ml1m_block(ctx: Ctx, steps: int, warmup: int, cpu_baseline: bool):
 # ------------------------------------------------------------------------------------------------ config 1: epoch + eval
 def synth_ratings(path: str, users_dat: str, movies_dat: str, n: int = 1_000_209, seed: int = SEED) -> None:
     """ratings.dat is not shipped with the reference (.MISSING_LARGE_BLOBS): synthesise `UserID::MovieID::Rating::
-    Timestamp` rows over the real user / movie ids: Zipf-popular movies, ratings 1-5 skewed to
-    3-5, timestamps 2000-04-25 .. 2003-02-28, fixed seed.  Every user gets >= 20 interactions as in ML-1M."""
+    Timestamp` rows over the real user / movie ids, fixed seed.  The towers of the ML-1M
+    configuration see FEATURES only (gender / age / occupation, genres / year), so the synthetic preferences are a
+    fixed random bilinear form of exactly those fields: affinity(u, m) = [gender, age, occupation one-hot](u) . W .
+    genres(m).  Each user draws a log-normal number (>= 20, as in ML-1M) of distinct movies with probability
+    proportional to popularity x exp(1.5 affinity) (Gumbel top-k) and rates them 1-5 around 3.1 + 0.9 affinity;
+    timestamps 2000-04-25 .. 2003-02-28.  A model can therefore learn something, and its scores do not collapse into
+    ties (with preference-free random ratings every user's top-100 was decided by 1e-8 score differences)."""
     rng = np.random.default_rng(seed)
-    uids = np.array([int(l.split("::")[0]) for l in open(users_dat, encoding="latin-1") if l.strip()])
-    mids = np.array([int(l.split("::")[0]) for l in open(movies_dat, encoding="latin-1") if l.strip()])
+    urows = [l.strip().split("::") for l in open(users_dat, encoding="latin-1") if l.strip()]
+    mrows = [l.strip().split("::") for l in open(movies_dat, encoding="latin-1") if l.strip()]
+    uids = np.array([int(r[0]) for r in urows])
+    mids = np.array([int(r[0]) for r in mrows])
+    genres = sorted({g for r in mrows for g in r[2].split("|")})
+    gmat = np.zeros((len(mrows), len(genres)), dtype=np.float32)
+    for i, r in enumerate(mrows):
+        for g in r[2].split("|"):
+            gmat[i, genres.index(g)] = 1.0
+    gmat /= np.sqrt(gmat.sum(1, keepdims=True))
+    ufe = np.zeros((len(urows), 2 + 21), dtype=np.float32)
+    for i, r in enumerate(urows):
+        ufe[i, 0] = 1.0 if r[1] == "M" else -1.0
+        ufe[i, 1] = (float(r[2]) - 30.0) / 15.0
+        ufe[i, 2 + int(r[3])] = 1.0
+    aff = (ufe @ rng.standard_normal((ufe.shape[1], gmat.shape[1])).astype(np.float32)) @ gmat.T
+    aff = (aff - aff.mean()) / aff.std()
     pop = 1.0 / np.arange(1, len(mids) + 1) ** 0.9
-    pop /= pop.sum()
+    logp = np.log(pop[rng.permutation(len(mids))])[None, :] + 1.5 * aff
     per_user = np.maximum(20, rng.lognormal(4.6, 0.9, len(uids)).astype(np.int64))
     per_user = np.minimum(per_user, len(mids) // 2)
     per_user = (per_user * (n / per_user.sum())).astype(np.int64).clip(20, len(mids) // 2)
-    perm = rng.permutation(len(mids))
+    keys = logp + rng.gumbel(size=logp.shape)
+    order = np.argsort(-keys, axis=1)
     rows = []
-    for u, c in zip(uids, per_user):
-        m = perm[rng.choice(len(mids), size=int(c), replace=False, p=pop)]
-        r = rng.choice([1, 2, 3, 4, 5], size=int(c), p=[0.06, 0.11, 0.26, 0.35, 0.22])
-        t = rng.integers(956703932, 1046454590, size=int(c))
-        rows.append(np.stack([np.full(int(c), u), mids[m], r, t], axis=1))
+    for i, (u, c) in enumerate(zip(uids, per_user)):
+        c = int(c)
+        m = order[i, :c]
+        r = np.clip(np.rint(3.1 + 0.9 * aff[i, m] + 0.7 * rng.standard_normal(c)), 1, 5).astype(np.int64)
+        t = rng.integers(956703932, 1046454590, size=c)
+        rows.append(np.stack([np.full(c, u), mids[m], r, t], axis=1))
     allr = np.concatenate(rows)
     with open(path, "w") as fh:
         fh.write("\n".join("::".join(map(str, row)) for row in allr.tolist()))
