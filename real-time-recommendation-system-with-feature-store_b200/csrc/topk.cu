@@ -1269,8 +1269,11 @@ static int launch_topk(const TopkPlan& p, const void* catalogue, int64_t N, int6
   ea.k = k;
   ea.cap = p.cap;
   // hand a list over every ~k/4 candidates: each merge selects over k + list keys, so the threshold scales with k
-  // (k = 1000: 7.6 ms per 1024-query batch at 32, 5.3 ms at 256)
-  ea.flush = kn.flush >= 0 ? kn.flush : (k / 4 > 32 ? (k / 4) / 32 * 32 : 32);
+  // (k = 1000: 7.6 ms per 1024-query batch at 32, 5.3 ms at 256).  Few queries and a large k (the serving loop's
+  // top-1000 for <= 256 users): every unit feeds the same few queries, the merges serialise on those queries' locks and
+  // a fresher threshold saves little, so lists are only handed over when full and the final select does the merging
+  // (50 M x 64, k = 1000: Q = 1 4.44 -> 1.55 ms, Q = 128 5.07 -> 3.37 ms; at Q >= 512 the k/4 rule wins: 6.6 vs 8.2 ms).
+  ea.flush = kn.flush >= 0 ? kn.flush : ((k > 128 && Q <= 256) ? p.cap : (k / 4 > 32 ? (k / 4) / 32 * 32 : 32));
   ea.debug = kn.debug;
   ea.hsleep = kn.hsleep;
   void (*kern)(const CUtensorMap, const CUtensorMap, const StreamGeom, const TopkArgs);
