@@ -60,8 +60,8 @@ def _bwd_terms(terms: int) -> int:
     """Split-bf16 terms of the GRADIENT GEMMs (dgrad, wgrad, the two in-batch gradient products) when the forward runs
     fp32-grade (6 terms).  3 terms ([h m h] x [m h h]: products accurate to ~2^-17, fp32 accumulation) halve their
     FLOPs and operand traffic; the golden parity tests (per-step losses, embeddings, gradients and parameters against the
-    reference at 1e-5) hold with them, and the logits recompute that feeds exp() keeps 6.  B200REC_BWD_TERMS=6 restores
-    fp32-grade gradient products."""
+    reference at 1e-5) hold with them; the fused in-batch backward recomputes its logits with the same 3 products.
+    B200REC_BWD_TERMS=6 restores 6-product dgrad / wgrad GEMMs and a 6-product logits recompute."""
     if terms == 6:
         t = int(os.environ.get("B200REC_BWD_TERMS", "3"))
         return t if t in (3, 6) else 3

@@ -188,6 +188,25 @@ def test_fused_inbatch_backward_with_gathered_negatives(B, G, E, rank):
     assert (res["fused"][0] - res["chunked"][0]).abs().max() <= 1e-4 * ur.grad.abs().max()
 
 
+@pytest.mark.parametrize("B,E", [(2048, 64), (1500, 128)])
+def test_fused_inbatch_backward_six_product_recompute(B, E, monkeypatch):
+    """B200REC_BWD_TERMS=6: the logits recompute of the fused gradient kernel uses the 6 fp32-grade piece products
+    (inbatch_grad_kernel<E, 6, 3>; E = 128 fits since the gradient GEMM reads the row operands as MN-major tiles and G
+    lives in tensor memory).  The gradient GEMMs keep 3 products (~2^-17 each): gradients within 5e-5 of fp64 torch."""
+    from b200rec import kernels as K, ops
+    monkeypatch.setenv("B200REC_BWD_TERMS", "6")
+    assert K.inbatch_grad_supported(B, B, E, 6, 3)
+    torch.manual_seed(B)
+    u = torch.nn.functional.normalize(torch.randn(B, E), dim=1)
+    v = torch.nn.functional.normalize(torch.randn(B, E) + 0.5 * u, dim=1)
+    uc, vc = u.clone().to(DEV).requires_grad_(), v.clone().to(DEV).requires_grad_()
+    ops.InBatchCEFn.apply(uc, vc, 20.0, 6, 0, B).backward()
+    ur, vr = u.clone().double().requires_grad_(), v.clone().double().requires_grad_()
+    torch.nn.functional.cross_entropy(ur @ vr.T * 20.0, torch.arange(B)).backward()
+    assert (uc.grad.cpu().double() - ur.grad).abs().max() <= 5e-5 * ur.grad.abs().max()
+    assert (vc.grad.cpu().double() - vr.grad).abs().max() <= 5e-5 * vr.grad.abs().max()
+
+
 def test_bf16_mode_within_budget():
     from b200rec.training_utils import create_two_tower_model_for_training
     torch.manual_seed(3)

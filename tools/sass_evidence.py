@@ -1,5 +1,5 @@
 """Per-kernel counts of the Blackwell-native SASS instructions in libb200rec.so (no GPU needed):
-UTCHMMA (tcgen05.mma, .2CTA = cta_group::2), UTMALDG (TMA tensor loads), LDTM (tcgen05.ld), UTCBAR (tcgen05.commit),
+UTCHMMA (tcgen05.mma, .2CTA = cta_group::2), UTMALDG (TMA tensor loads), LDTM / STTM (tcgen05.ld / .st), UTCBAR (tcgen05.commit),
 SYNCS (mbarrier), plus registers per thread.   python tools/sass_evidence.py > profiles/r02_sass_evidence.txt"""
 import collections, os, re, subprocess, sys
 lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
@@ -9,7 +9,7 @@ res = subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text
 regs = {}
 for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+)", res):
     regs[m.group(1)] = int(m.group(2))
-pats = ["UTCHMMA.2CTA", "UTCHMMA", "UTMALDG", "UTMAPF", "LDTM", "UTCBAR", "UTCATOMSWS", "SYNCS", "ELECT", "REDUX", "ATOMG", "RED"]
+pats = ["UTCHMMA.2CTA", "UTCHMMA", "UTMALDG", "STTM", "LDTM", "UTCBAR", "UTCATOMSWS", "SYNCS", "ELECT", "REDUX", "ATOMG", "RED"]
 cur, counts = None, collections.OrderedDict()
 for line in sass.splitlines():
     m = re.match(r"\s*Function : (\S+)", line)
