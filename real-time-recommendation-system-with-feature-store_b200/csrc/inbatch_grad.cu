@@ -120,7 +120,7 @@ inbatch_grad_kernel(const __grid_constant__ CUtensorMap tm_ux, const __grid_cons
   constexpr int KB = C::KB, PS = C::PS, PG = C::PG, NST = C::NST, NG = C::NG, NACC = C::NACC;
   constexpr int STAGE = C::STAGE, G_COLS = C::G_COLS;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS / STS)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mode = (int)blockIdx.x >= a.units_u ? 1 : 0;
   const IgSide& sd = a.side[mode];

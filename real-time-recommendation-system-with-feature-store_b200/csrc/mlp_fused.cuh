@@ -225,7 +225,7 @@ __device__ __forceinline__ float mf_bwd1(const MfBlock& k, const MfStats& s, con
 template <int MODE, bool RELU, bool DROP>
 __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(const MfArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS / STS)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int np = a.np, NT = a.NT;
   const int a_piece = 128 * 128, b_piece = NT * 128;

@@ -116,7 +116,7 @@ stream_scores_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   static_assert(2 * NQ * BN <= 512, "two accumulator buffers must fit the 512 TMEM columns");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS / STS)
   uint8_t* q_smem = smem;
   uint8_t* ring = smem + NQ * g.KB * ST_QTILE_BYTES;
   uint8_t* tail = ring + g.stages * STAGE_BYTES;

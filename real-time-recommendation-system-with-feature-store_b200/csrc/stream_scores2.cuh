@@ -192,7 +192,7 @@ stream_scores2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   // that read (t, 0) and the epilogue of (t, 0) starts half a tile earlier.  NQ2 = 1: one 256-column accumulator.
   constexpr int NSUB = NQ2;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS / STS)
   uint8_t* q_smem = smem;
   uint8_t* ring = smem + NQ2 * g.KB * ST_QTILE_BYTES;
   const int ks = g.ks;                       // 64-column atoms per ring stage
