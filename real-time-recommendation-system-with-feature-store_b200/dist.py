@@ -305,11 +305,16 @@ class DataParallel:
             dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
 
     def gather_sparse(self, rows: torch.Tensor, vals: torch.Tensor):
-        """(rows [n], vals [n,e]) of this replica -> concatenation over replicas (padding rows stay 0)."""
-        ar = torch.empty((self.world * rows.shape[0],), dtype=rows.dtype, device=rows.device)
-        av = torch.empty((self.world * vals.shape[0], vals.shape[1]), dtype=vals.dtype, device=vals.device)
-        dist.all_gather_into_tensor(ar, rows.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(av, vals.contiguous(), group=self.group)
+        """(rows [n] int64, vals [n,e] fp32) of this replica -> concatenation over replicas (padding rows stay 0).
+        ONE collective: the ids travel as two extra fp32 columns (bit pattern) of the value rows."""
+        n, e = vals.shape
+        packed = torch.empty((n, e + 2), dtype=torch.float32, device=vals.device)
+        packed[:, :e] = vals
+        packed[:, e:] = rows.contiguous().view(torch.float32).view(n, 2)
+        everyone = torch.empty((self.world * n, e + 2), dtype=torch.float32, device=vals.device)
+        dist.all_gather_into_tensor(everyone, packed, group=self.group)
+        ar = everyone[:, e:].contiguous().view(torch.int64).view(-1)
+        av = everyone[:, :e].contiguous()
         return ar, av
 
     def gather_counts(self, n: int):
