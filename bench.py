@@ -417,14 +417,16 @@ def run_table_train_block(ctx: Ctx, steps: int, warmup: int, cpu_baseline: bool,
     ctx.barrier()
     e2e_ms = ctx.max_over_ranks((time.perf_counter() - t0) / steps * 1e3)[0]
     # algorithmic work of ONE replica's step: towers 6 * sum(in*out) FLOP per sample and pass,
-    # in-batch loss 6 * B_local * B_global * E; bytes = optimiser traffic (28 B per densely updated parameter; row-sparse
+    # in-batch loss 6 * B_local * B_global * E; bytes = optimiser traffic (24-28 B per densely updated parameter; row-sparse
     # tables touch 28 B per element of a touched row) + embedding gather / scatter + activations
     dims = [FD + edim] + list(hidden) + [E]
     macs = sum(a * b for a, b in zip(dims[:-1], dims[1:]))
     flops = 2 * 6 * B * macs + 6.0 * B * (B * world) * E
     mlp_params = 2 * sum(a * b + b for a, b in zip(dims[:-1], dims[1:]))
     table_params = (NU + 1 + NI + 1) * edim
-    dense_bytes = 28.0 * (mlp_params + (0 if sparse_tables else table_params))
+    # dense tables: p, m, v read + written = 24 B per parameter (the gradient is read, and reset, on touched rows only:
+    # b200rec_adam_table); MLP parameters 28 B (g read as well)
+    dense_bytes = 28.0 * mlp_params + (0.0 if sparse_tables else 24.0 * table_params + 2 * 8.0 * B * edim * world)
     sparse_bytes = (28.0 * 2 * B * edim * world) if sparse_tables else 0.0
     act_bytes = 4.0 * B * sum(dims) * 2 * 3
     bytes_ = dense_bytes + sparse_bytes + act_bytes + 2 * B * (8 + 2 * 4 * edim)

@@ -264,6 +264,22 @@ int b200rec_train_step_begin(int64_t* step_dev, const float* lr_dev, float beta1
 int b200rec_adam_dense_dev(float* p, float* g, float* m, float* v, int64_t n, float beta1, float beta2, float eps,
                            float weight_decay, const float* hyper_dev, const float* clip_coef_dev, int clear_grad,
                            void* stream);
+
+/* ---- dense embedding tables under dense Adam (reference trainers/two_tower.py:60-64: Adam + weight decay over ALL
+ * parameters moves every row each step, but a step's gradient is non-zero only on the rows the batch touched).
+ * b200rec_scatter_add_rows_flagged = b200rec_scatter_add_rows that also sets row_flags[row] = 1; b200rec_table_sumsq adds
+ * the squared gradient of the flagged rows to *out; b200rec_adam_table applies the Adam + weight-decay update to every
+ * row, reading (and, with clear_grad, zeroing) the gradient of flagged rows only and clearing their flags: 24 B per
+ * parameter instead of 32.  hyper_dev != NULL: {lr, 1 - beta1^t, sqrt(1 - beta2^t)} come from device memory
+ * (b200rec_train_step_begin) and lr / bias_c1 / bias_c2_sqrt are ignored.  width <= 128. */
+int b200rec_scatter_add_rows_flagged(const int64_t* idx, int64_t B, const float* dY, int64_t ld_dy, int width,
+                                     int64_t padding_idx, int64_t table_rows, float* dense, int64_t ld, int32_t* row_flags,
+                                     void* stream);
+int b200rec_table_sumsq(const float* g, int64_t ld, int64_t rows, int width, const int32_t* row_flags, double* out,
+                        void* stream);
+int b200rec_adam_table(float* p, float* g, float* m, float* v, int64_t ld, int64_t rows, int width, int32_t* row_flags,
+                       float lr, float beta1, float beta2, float eps, float weight_decay, float bias_c1, float bias_c2_sqrt,
+                       const float* hyper_dev, const float* clip_coef_dev, int clear_grad, void* stream);
 int b200rec_sparse_adam_dev(float* table, float* exp_avg, float* exp_avg_sq, int64_t ld, int width, const int64_t* rows,
                             const float* grad_rows, const int32_t* n_rows, int64_t max_rows, float beta1, float beta2,
                             float eps, const float* hyper_dev, const float* clip_coef_dev, void* stream);

@@ -257,7 +257,8 @@ namespace b200 {
 // path stays for row-sparse tables, whose optimizer needs each distinct row exactly once.
 __global__ void __launch_bounds__(256)
 scatter_add_rows_kernel(const int64_t* __restrict__ idx, int64_t B, const float* __restrict__ dY, int64_t ld_dy, int width,
-                        int64_t padding_idx, int64_t table_rows, float* __restrict__ dense, int64_t ld) {
+                        int64_t padding_idx, int64_t table_rows, float* __restrict__ dense, int64_t ld,
+                        int32_t* __restrict__ row_flags) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += warps) {
@@ -266,6 +267,7 @@ scatter_add_rows_kernel(const int64_t* __restrict__ idx, int64_t B, const float*
     const float* src = dY + b * ld_dy;
     float* dst = dense + r * ld;
     for (int c = lane; c < width; c += 32) atomicAdd(dst + c, __ldg(src + c));
+    if (row_flags != nullptr && lane == 0) row_flags[r] = 1;   // this row's gradient is (possibly) non-zero this step
   }
 }
 }  // namespace b200
@@ -278,7 +280,21 @@ extern "C" int b200rec_scatter_add_rows(const int64_t* idx, int64_t B, const flo
   const int64_t blocks = (B + 7) / 8;
   const int grid = (int)(blocks < (int64_t)num_sms() * 16 ? blocks : (int64_t)num_sms() * 16);
   scatter_add_rows_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(idx, B, dY, ld_dy, width, padding_idx,
-                                                                                    table_rows, dense, ld);
+                                                                                    table_rows, dense, ld, nullptr);
+  B200_LAUNCH_OK("scatter_add_rows_kernel");
+  return 0;
+}
+
+extern "C" int b200rec_scatter_add_rows_flagged(const int64_t* idx, int64_t B, const float* dY, int64_t ld_dy, int width,
+                                                int64_t padding_idx, int64_t table_rows, float* dense, int64_t ld,
+                                                int32_t* row_flags, void* stream) {
+  using namespace b200;
+  if (!idx || !dY || !dense || !row_flags) return fail("scatter_add_rows_flagged: null pointer");
+  if (B <= 0 || width <= 0 || table_rows <= 0) return fail("scatter_add_rows_flagged: empty input");
+  const int64_t blocks = (B + 7) / 8;
+  const int grid = (int)(blocks < (int64_t)num_sms() * 16 ? blocks : (int64_t)num_sms() * 16);
+  scatter_add_rows_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(idx, B, dY, ld_dy, width, padding_idx,
+                                                                                    table_rows, dense, ld, row_flags);
   B200_LAUNCH_OK("scatter_add_rows_kernel");
   return 0;
 }

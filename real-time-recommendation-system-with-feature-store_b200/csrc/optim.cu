@@ -110,6 +110,102 @@ sparse_adam_kernel(float* __restrict__ table, float* __restrict__ m, float* __re
   }
 }
 
+
+// ---- dense embedding tables under the reference's dense Adam ------------------------------------------------------
+// Adam with L2-coupled weight decay moves EVERY row each step (gi = wd * p), but the gradient of a step is non-zero
+// only on the rows the batch touched (a few thousand of 10^6): the scatter kernel raises a per-row flag, and these
+// kernels read (and reset) the gradient of flagged rows only — 24 B per parameter instead of 32 (28 + the reset), and
+// the gradient-norm pass touches the flags and the flagged rows instead of the whole 282 MB buffer.
+// One warp per row (lane = column mod 32), ROWS_PER_ITER rows in flight per warp.
+constexpr int TBL_ROWS_PER_ITER = 4;
+constexpr int TBL_MAX_EPL = 4;   // columns per lane: tables up to 128 wide
+
+__global__ void __launch_bounds__(256)
+table_sumsq_kernel(const float* __restrict__ g, int64_t ld, int64_t rows, int width, const int32_t* __restrict__ flags,
+                   double* __restrict__ out) {
+  __shared__ double red[8];
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  double s = 0.0;
+  // lanes scan 32 flags at a time; flagged rows are then summed by the whole warp
+  for (int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; r0 < rows; r0 += warps * 32) {
+    const int64_t r = r0 + lane;
+    unsigned hit = __ballot_sync(FULL_MASK, r < rows && __ldg(flags + r) != 0);
+    while (hit) {
+      const int j = __ffs(hit) - 1;
+      hit &= hit - 1;
+      const float* row = g + (r0 + j) * ld;
+      for (int c = lane; c < width; c += 32) {
+        const float v = __ldg(row + c);
+        s += (double)v * v;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL_MASK, s, o);
+  if (lane == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    if (t != 0.0) atomicAdd(out, t);
+  }
+}
+
+template <int EPL>
+__global__ void __launch_bounds__(256)
+adam_table_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t ld,
+                  int64_t rows, int width, int32_t* __restrict__ flags, float lr, float beta1, float beta2, float eps,
+                  float wd, float bias_c1, float bias_c2_sqrt, const float* __restrict__ clip_coef,
+                  const float* __restrict__ hyper_dev, int clear_grad) {
+  const float cc = clip_coef ? __ldg(clip_coef) : 1.f;
+  if (hyper_dev) {
+    lr = __ldg(hyper_dev);
+    bias_c1 = __ldg(hyper_dev + 1);
+    bias_c2_sqrt = __ldg(hyper_dev + 2);
+  }
+  const float step_size = lr / bias_c1;
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  constexpr int R = TBL_ROWS_PER_ITER;
+  for (int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R; r0 < rows; r0 += warps * R) {
+    float P[R][EPL], M[R][EPL], V[R][EPL], G[R][EPL];
+    int f[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) f[j] = (r0 + j < rows) ? flags[r0 + j] : 0;   // warp-uniform
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int64_t o = (r0 + j) * ld;
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) {
+        const int c = lane + 32 * k;
+        const bool ok = r0 + j < rows && c < width;
+        P[j][k] = ok ? p[o + c] : 0.f;
+        M[j][k] = ok ? m[o + c] : 0.f;
+        V[j][k] = ok ? v[o + c] : 0.f;
+        G[j][k] = (ok && f[j] != 0) ? g[o + c] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int64_t o = (r0 + j) * ld;
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) {
+        const int c = lane + 32 * k;
+        if (r0 + j < rows && c < width) {
+          adam_one(P[j][k], G[j][k], M[j][k], V[j][k], cc, wd, beta1, beta2, eps, step_size, bias_c2_sqrt);
+          p[o + c] = P[j][k];
+          m[o + c] = M[j][k];
+          v[o + c] = V[j][k];
+          if (clear_grad && f[j] != 0) g[o + c] = 0.f;
+        }
+      }
+      if (clear_grad && f[j] != 0 && lane == 0) flags[r0 + j] = 0;   // this warp is the only reader of the row's flag
+    }
+  }
+}
+
 static int flat_grid(int64_t total) {
   int64_t g = (total + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 16;
@@ -156,6 +252,40 @@ extern "C" int b200rec_adam_dense_dev(float* p, float* g, float* m, float* v, in
   adam_dense_kernel<<<flat_grid(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, n, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f, clip_coef_dev, hyper_dev, clear_grad);
   B200_LAUNCH_OK("adam_dense_kernel");
+  return 0;
+}
+
+
+extern "C" int b200rec_table_sumsq(const float* g, int64_t ld, int64_t rows, int width, const int32_t* row_flags,
+                                   double* out, void* stream) {
+  if (!g || !row_flags || !out) return fail("table_sumsq: null pointer");
+  if (rows <= 0 || width <= 0 || ld < width) return fail("table_sumsq: bad shape");
+  const int64_t blocks = (rows + 255) / 256;
+  const int grid = (int)(blocks < (int64_t)num_sms() * 8 ? blocks : (int64_t)num_sms() * 8);
+  table_sumsq_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, ld, rows, width, row_flags, out);
+  B200_LAUNCH_OK("table_sumsq_kernel");
+  return 0;
+}
+
+extern "C" int b200rec_adam_table(float* p, float* g, float* m, float* v, int64_t ld, int64_t rows, int width,
+                                  int32_t* row_flags, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                  float bias_c1, float bias_c2_sqrt, const float* hyper_dev, const float* clip_coef_dev,
+                                  int clear_grad, void* stream) {
+  if (!p || !g || !m || !v || !row_flags) return fail("adam_table: null pointer");
+  if (rows <= 0 || width <= 0 || ld < width) return fail("adam_table: bad shape");
+  if (width > 32 * TBL_MAX_EPL) return fail("adam_table: rows wider than %d columns use b200rec_adam_dense", 32 * TBL_MAX_EPL);
+  const int64_t blocks = (rows + 8 * TBL_ROWS_PER_ITER - 1) / (8 * TBL_ROWS_PER_ITER);
+  const int grid = (int)(blocks < (int64_t)num_sms() * 16 ? blocks : (int64_t)num_sms() * 16);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int epl = (width + 31) / 32;
+#define ADAM_TABLE(E) adam_table_kernel<E><<<grid, 256, 0, st>>>(p, g, m, v, ld, rows, width, row_flags, lr, beta1, beta2, eps, \
+                                                                 weight_decay, bias_c1, bias_c2_sqrt, clip_coef_dev, hyper_dev, clear_grad)
+  if (epl == 1) ADAM_TABLE(1);
+  else if (epl == 2) ADAM_TABLE(2);
+  else if (epl == 3) ADAM_TABLE(3);
+  else ADAM_TABLE(4);
+#undef ADAM_TABLE
+  B200_LAUNCH_OK("adam_table_kernel");
   return 0;
 }
 

@@ -2,6 +2,7 @@
 asynchronously on torch's current CUDA stream; torch is used only to own device memory."""
 from __future__ import annotations
 
+import math
 from typing import Optional, Tuple
 
 import torch
@@ -217,8 +218,15 @@ def embedding_sparse_grad(idx: torch.Tensor, dY: torch.Tensor, width: int, table
     return rows, grads, n
 
 
-def scatter_add_rows(idx: torch.Tensor, dY: torch.Tensor, width: int, dense: torch.Tensor, padding_idx: int = 0) -> None:
-    """dense[idx[b], :width] += dY[b, :width] with fp32 atomics (padding row and out-of-range ids skipped)."""
+def scatter_add_rows(idx: torch.Tensor, dY: torch.Tensor, width: int, dense: torch.Tensor, padding_idx: int = 0,
+                     row_flags: Optional[torch.Tensor] = None) -> None:
+    """dense[idx[b], :width] += dY[b, :width] with fp32 atomics (padding row and out-of-range ids skipped);
+    row_flags (int32 [rows]): also raise the flag of every row that received a gradient."""
+    if row_flags is not None:
+        N.check(N.lib().b200rec_scatter_add_rows_flagged(N.ptr(idx), idx.shape[0], N.ptr(dY), dY.stride(0), width,
+                                                         padding_idx, dense.shape[0], N.ptr(dense), dense.stride(0),
+                                                         N.ptr(row_flags), N.stream()), "scatter_add_rows_flagged")
+        return
     N.check(N.lib().b200rec_scatter_add_rows(N.ptr(idx), idx.shape[0], N.ptr(dY), dY.stride(0), width, padding_idx,
                                              dense.shape[0], N.ptr(dense), dense.stride(0), N.stream()), "scatter_add_rows")
 
@@ -462,6 +470,22 @@ def rowdot_bwd(g, U, I, scale: float):
 # ------------------------------------------------------------------------------------------------ optimiser
 def sumsq_(x_flat, acc64) -> None:
     N.check(N.lib().b200rec_sumsq(N.ptr(x_flat), x_flat.numel(), N.ptr(acc64), N.stream()), "sumsq")
+
+
+def table_sumsq_(grad2d, row_flags, acc64) -> None:
+    """acc64 += sum of squares of the flagged rows of a dense table gradient [rows, e]."""
+    N.check(N.lib().b200rec_table_sumsq(N.ptr(grad2d), grad2d.stride(0), grad2d.shape[0], grad2d.shape[1], N.ptr(row_flags),
+                                        N.ptr(acc64), N.stream()), "table_sumsq")
+
+
+def adam_table_(p2d, g2d, m2d, v2d, row_flags, lr, beta1, beta2, eps, wd, step: int, clip=None, hyper_dev=None,
+                clear_grad: bool = True) -> None:
+    """Adam + L2-coupled weight decay over every row of a dense table, reading the gradient of flagged rows only."""
+    bc1 = 1.0 - beta1 ** step if hyper_dev is None else 1.0
+    bc2s = math.sqrt(1.0 - beta2 ** step) if hyper_dev is None else 1.0
+    N.check(N.lib().b200rec_adam_table(N.ptr(p2d), N.ptr(g2d), N.ptr(m2d), N.ptr(v2d), p2d.stride(0), p2d.shape[0],
+                                       p2d.shape[1], N.ptr(row_flags), float(lr), beta1, beta2, eps, wd, bc1, bc2s,
+                                       N.ptr(hyper_dev), N.ptr(clip), int(clear_grad), N.stream()), "adam_table")
 
 
 def clip_coef(acc64, max_norm: float, coef, norm_out=None) -> None:

@@ -371,12 +371,13 @@ class GatherConcatFn(Function):
                     # data parallel: every replica adds the sample rows of ALL replicas (instead of all-reducing the
                     # whole dense table gradient afterwards)
                     ids_all, rows_all = ex.gather_sparse(idx64[f], dout[:, offs[f]:offs[f] + widths[f]].contiguous())
-                    K.scatter_add_rows(ids_all, rows_all, widths[f], table.grad, 0)
+                    K.scatter_add_rows(ids_all, rows_all, widths[f], table.grad, 0, getattr(table, "_b200_row_flags", None))
                 else:
-                    K.scatter_add_rows(idx64[f], dout[:, offs[f]:], widths[f], table.grad, 0)
+                    K.scatter_add_rows(idx64[f], dout[:, offs[f]:], widths[f], table.grad, 0,
+                                       getattr(table, "_b200_row_flags", None))
                 touch = getattr(table, "_b200_touch", None)
                 if touch is not None:
-                    touch[0]._mark(touch[1])
+                    touch[0]._mark(touch[1], flagged=getattr(table, "_b200_row_flags", None) is not None)
                 grads.append(None)
                 continue
             rows, vals, n = K.embedding_sparse_grad(idx64[f], dout[:, offs[f]:], widths[f], table.shape[0], 0)

@@ -52,9 +52,24 @@ class FlatAdam:
         # autograd hook marks dense parameters, GatherConcatFn marks tables it scatters into in place.
         self._touched = [False] * len(self.dense)
         self._touch_sticky = False
+        # Dense embedding tables (two_tower.py marks them _b200_table): Adam + weight decay moves every row each step, but
+        # the step's gradient is non-zero only on the rows the batch touched.  The scatter kernel raises a per-row flag
+        # (ops.GatherConcatFn.backward) and b200rec_adam_table / b200rec_table_sumsq read the gradient of flagged rows
+        # only (24 B instead of 32 per parameter).  Any other way a table gets its gradient falls back to the flat kernels.
+        self._table = [bool(getattr(p, "_b200_table", False)) and p.dim() == 2 and p.shape[1] <= 128
+                       and os.environ.get("B200REC_TABLE_ADAM", "1") != "0" for p in self.dense]
+        self._flag_ok = [True] * len(self.dense)
         for i, p in enumerate(self.dense):
             p._b200_touch = (self, i)
-            p.register_post_accumulate_grad_hook(lambda t, _i=i: self._mark(_i))
+            # fires after every backward that reaches p, also when the kernels wrote straight into p.grad and handed
+            # autograd no tensor: it only records "reached by backward" (flagged=None)
+            p.register_post_accumulate_grad_hook(lambda t, _i=i: self._mark(_i, None))
+            if self._table[i]:
+                p._b200_row_flags = torch.zeros((p.shape[0],), dtype=torch.int32, device=dev)
+                # a DEFINED gradient tensor arriving through autograd (any op other than the flagging scatter) was
+                # accumulated densely: this step's update of the table must read the whole gradient
+                # (autograd also calls tensor hooks with None when a backward returned no tensor for p)
+                p.register_hook(lambda g, _i=i: self._mark(_i, False) if g is not None else None)
         self.sparse_state = {id(p): (torch.zeros_like(p.data), torch.zeros_like(p.data)) for p in self.sparse}
         self.lr, self.wd, self.betas, self.eps, self.max_grad_norm = lr, weight_decay, betas, eps, max_grad_norm
         self.step_count = 0
@@ -67,8 +82,35 @@ class FlatAdam:
         # CUDA-graph training (TwoTowerTrainer.enable_cuda_graph): step counter, lr and Adam's bias corrections on the device
         self.dev_state = None
 
-    def _mark(self, i: int) -> None:
+    def _mark(self, i: int, flagged: Optional[bool] = False) -> None:
+        """Parameter i received a gradient this step.  flagged=True: through the row-flagging scatter kernel;
+        False: some other writer (the table's update falls back to the flat kernels); None: no statement."""
         self._touched[i] = True
+        if flagged is False:
+            self._flag_ok[i] = False
+
+    def _plan(self):
+        """(flat [lo, hi) element ranges, table segment indices) of the parameters that received a gradient this step:
+        tables whose gradient came through the flagging scatter are updated row-wise, everything else by the flat
+        kernels (adjacent segments merged into one launch)."""
+        everything = self._touch_sticky or all(self._touched)
+        flat, tables = [], []
+        for i, (off, k) in enumerate(self._seg):
+            if not (everything or self._touched[i]):
+                continue
+            if self._table[i] and self._touched[i] and self._flag_ok[i] and not self._touch_sticky:
+                tables.append(i)
+            elif flat and flat[-1][1] == off:
+                flat[-1] = (flat[-1][0], off + k)
+            else:
+                flat.append((off, off + k))
+        return flat, tables
+
+    def _table_views(self, i: int):
+        off, k = self._seg[i]
+        shape = self.dense[i].shape
+        return (self.flat[off:off + k].view(shape), self.grad[off:off + k].view(shape), self.m[off:off + k].view(shape),
+                self.v[off:off + k].view(shape), self.dense[i]._b200_row_flags)
 
     def touch_all(self) -> None:
         """Gradients are written straight into .grad by the caller (no autograd): update every parameter."""
@@ -110,6 +152,7 @@ class FlatAdam:
             self.grad.zero_()
         self._grad_clean = False
         self._touched = [False] * len(self.dense)
+        self._flag_ok = [True] * len(self.dense)
         for p in self.sparse:
             p._b200_sparse_grad = None
 
@@ -157,18 +200,30 @@ class FlatAdam:
             # the backward (dist.DataParallel) already hold the global sum: only the other segments are all-reduced.
             dp.reduce_dense_grad_(self.grad, self._reduce_runs())
         sparse = [(p, self._sparse_lists(p)) for p in self.sparse]
+        runs, tables = self._plan()
         if self.max_grad_norm is not None:
             self._acc.zero_()
-            K.sumsq_(self.grad, self._acc)
+            if tables:
+                # untouched parameters hold zero gradients: the norm is taken over what received one
+                for lo, hi in runs:
+                    K.sumsq_(self.grad[lo:hi], self._acc)
+                for i in tables:
+                    _, g2, _, _, flags = self._table_views(i)
+                    K.table_sumsq_(g2, flags, self._acc)
+            else:
+                K.sumsq_(self.grad, self._acc)
             for _, lists in sparse:
                 for _, vals, _ in lists:
                     K.sumsq_(vals.reshape(-1), self._acc)   # rows beyond n are zero-filled by the coalescing kernel
             K.clip_coef(self._acc, float(self.max_grad_norm), self._coef, self.grad_norm)
             clip = self._coef
-        runs = self._runs()
         self._grad_clean = bool(self.clear_grad)   # every run below clears the gradients it consumes; the rest was never written
         if self.dev_state is not None and getattr(self, "use_device_state", False):
             hyper = self.dev_state["hyper"]   # written by K.train_step_begin at the start of this step
+            for i in tables:
+                p2, g2, m2, v2, flags = self._table_views(i)
+                K.adam_table_(p2, g2, m2, v2, flags, 0.0, self.betas[0], self.betas[1], self.eps, self.wd, 1, clip, hyper,
+                              clear_grad=self.clear_grad)
             for lo, hi in runs:
                 K.adam_dense_dev_(self.flat[lo:hi], self.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], self.betas[0],
                                   self.betas[1], self.eps, self.wd, hyper, clip, clear_grad=self.clear_grad)
@@ -177,6 +232,10 @@ class FlatAdam:
                 for rows, vals, n in lists:
                     K.sparse_adam_dev_(p.data, m, v, rows, vals, n, self.betas[0], self.betas[1], self.eps, hyper, clip)
             return
+        for i in tables:
+            p2, g2, m2, v2, flags = self._table_views(i)
+            K.adam_table_(p2, g2, m2, v2, flags, lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_count, clip,
+                          None, clear_grad=self.clear_grad)
         for lo, hi in runs:
             K.adam_dense_(self.flat[lo:hi], self.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], lr, self.betas[0],
                           self.betas[1], self.eps, self.wd, self.step_count, clip, clear_grad=self.clear_grad)

@@ -61,6 +61,7 @@ class _TowerBase(nn.Module):
             if embedding_dims and feat_name in embedding_dims:
                 embed_dim = int(embedding_dims[feat_name])  # B200 extension: 16-byte aligned rows (64 / 128 wide)
             self.embeddings[feat_name] = nn.Embedding(cardinality + 1, embed_dim, padding_idx=0)
+            self.embeddings[feat_name].weight._b200_table = True   # FlatAdam: row-flagged dense update (trainer.py)
             total_embedding_dim += embed_dim
         self._total_embedding_dim = total_embedding_dim
         return None
