@@ -316,6 +316,17 @@ int b200rec_inbatch_grad(const void* u_op, int64_t ld_u, const int32_t* u_pieces
                          int nprod_s, int nprod_g, float inv_t, const float* lse, int64_t diag0, float coef,
                          const float* coef_dev, float* dU, int64_t ld_du, float* dV, int64_t ld_dv, void* stream);
 
+/* ---- one-shot all-reduce of a small fp64 vector over NVLink peer memory (csrc/peer_reduce.cu): the synced BatchNorm
+ * statistics and the loss share of exact data-parallel training (reference: none, the reference is single-process;
+ * this keeps N replicas equal to its one process on the global batch, trainers/two_tower.py:98-151).
+ * peer_buffers_host[r]: device address of rank r's symmetric buffer (b200rec_peer_allreduce_bytes(max_n) bytes, zeroed,
+ * mapped on this device, e.g. by torch.distributed._symmetric_memory); data[0..n) is replaced by the sum over ranks taken
+ * in rank order (bit-identical on every rank).  Every rank issues the same calls in the same order on one stream.
+ * *status_dev is set to 1 when a peer did not answer within seconds (the kernel then returns instead of hanging). */
+size_t b200rec_peer_allreduce_bytes(int max_n);
+int b200rec_peer_allreduce_f64(double* data, int n, int rank, int world, const uint64_t* peer_buffers_host, int max_n,
+                               int* status_dev, void* stream);
+
 /* ---- on-device ranking metrics (csrc/eval_metrics.cu; replaces the per-user Python of Evaluator.evaluate,
  * reference src/evaluation/metrics.py:240-319 with helpers :74-231) ----
  * pred int64 [Q, K] (ld_pred): ranked item ROWS per user as the top-K kernel emits them (-1 = empty slot);

@@ -9,6 +9,8 @@ the exchange on CPU with the oracle standing in for the CUDA kernels.
 """
 from __future__ import annotations
 
+import os
+
 import inspect
 from typing import Callable, Optional, Tuple
 
@@ -53,6 +55,40 @@ class _PeerExchange:
 
     def barrier(self, channel: int) -> None:
         self.hdl.barrier(channel=channel)
+
+
+class _PeerAllReduce:
+    """One-shot fp64 all-reduce of small vectors through symmetric NVLink memory (csrc/peer_reduce.cu): one 1-block
+    kernel per call instead of an NCCL all-reduce (25-60 us each inside the captured training step)."""
+
+    MAX_N = 2048
+
+    def __init__(self, group, device):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        from . import _native as N
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("peer all-reduce serves one NVLink box (<= 8 ranks)")
+        nbytes = int(N.lib().b200rec_peer_allreduce_bytes(self.MAX_N))
+        self.buf = symm.empty((nbytes + 255) // 256 * 256, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.ptrs = (ctypes.c_uint64 * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
+        self.status = torch.zeros((1,), dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        self.hdl.barrier(channel=0)          # every buffer is zeroed before anybody stores into it
+        torch.cuda.synchronize(device)
+
+    def __call__(self, t: torch.Tensor) -> None:
+        from . import _native as N
+        N.check(N.lib().b200rec_peer_allreduce_f64(N.ptr(t), t.numel(), self.rank, self.world, self.ptrs, self.MAX_N,
+                                                   N.ptr(self.status), N.stream()), "peer_allreduce_f64")
+
+    def check(self) -> None:
+        """Raises when a call timed out waiting for a peer (synchronises: call it outside the hot step)."""
+        if int(self.status.item()) != 0:
+            raise RuntimeError("b200rec peer all-reduce: a replica did not answer (diverged call sequence or dead peer)")
 
 
 class ShardedFlatIndex:
@@ -264,6 +300,21 @@ class _AllGatherRows(torch.autograd.Function):
         return gx, None
 
 
+class _TowerDP:
+    """The data-parallel context one tower sees: everything of the parent DataParallel, but its own peer all-reduce
+    buffers.  The call sequence of a peer all-reduce context must be identical on every replica; with one context per
+    tower the two towers can run on different streams (their kernels interleave differently on every GPU)."""
+
+    def __init__(self, parent: "DataParallel", peer_ar):
+        self._parent, self._peer_ar = parent, peer_ar
+
+    def __getattr__(self, name):
+        return getattr(self._parent, name)
+
+    def reduce_sums(self, t: torch.Tensor) -> None:
+        DataParallel._reduce_small(self._peer_ar, self._parent.group, t)
+
+
 class DataParallel:
     """Exact data-parallel training of the two-tower model (one process per GPU, equal local batches): the result is
     what ONE process computes on the concatenated global batch (reference trainers/two_tower.py:98-151):
@@ -289,9 +340,45 @@ class DataParallel:
             for emb in getattr(tower, "embeddings", {}).values():
                 if not getattr(emb.weight, "_b200_sparse", False):
                     emb.weight._b200_row_exchange = self
+        self._setup_peer_allreduce(model)
+
+    def _setup_peer_allreduce(self, model) -> None:
+        """NVLink peer-memory all-reduce for the small fp64 exchanges (BatchNorm sums, loss): every rank takes the same
+        branch (agreed with one MIN all-reduce); anything that fails selects the NCCL path."""
+        self._peer_ar = None
+        self.streams_safe = False
+        if os.environ.get("B200REC_PEER_ALLREDUCE", "1") == "0" or dist.get_backend(self.group) != "nccl":
+            return
+        dev = next(model.parameters()).device
+        ctx, ok = [], 1
+        try:
+            ctx = [_PeerAllReduce(self.group, dev) for _ in range(3)]   # loss / user tower / item tower
+        except Exception as exc:  # noqa: BLE001
+            import logging
+            logging.getLogger("b200rec").warning("peer-memory all-reduce unavailable (%s): using NCCL", exc)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) != 1:
+            return
+        self._peer_ar = ctx[0]
+        model.user_tower.dp = _TowerDP(self, ctx[1])
+        model.item_tower.dp = _TowerDP(self, ctx[2])
+        # no collective of a tower goes through the (single, ordered) NCCL communicator any more except the touched-row
+        # exchange, which torch orders by host call: the towers may run on two streams as they do on one GPU
+        self.streams_safe = os.environ.get("B200REC_DP_OVERLAP", "1") != "0"
+
+    @staticmethod
+    def _reduce_small(pr, group, t: torch.Tensor) -> None:
+        if (pr is not None and t.dtype == torch.float64 and t.is_cuda and t.is_contiguous()
+                and 0 < t.numel() <= pr.MAX_N):
+            pr(t)
+            return
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
     def reduce_sums(self, t: torch.Tensor) -> None:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        """In-place sum over the replicas of a small statistics vector (fp64 BatchNorm sums): bit-identical everywhere."""
+        self._reduce_small(getattr(self, "_peer_ar", None), self.group, t)
 
     def all_gather_rows(self, x: torch.Tensor) -> torch.Tensor:
         return _AllGatherRows.apply(x, self.group)
@@ -326,6 +413,10 @@ class DataParallel:
         return [int(x) for x in t.tolist()]
 
     def global_loss(self, local_share: torch.Tensor) -> torch.Tensor:
+        if getattr(self, "_peer_ar", None) is not None and local_share.is_cuda:
+            out = local_share.detach().to(torch.float64).reshape(1)
+            self.reduce_sums(out)
+            return out.to(local_share.dtype).reshape(local_share.shape)
         out = local_share.detach().clone()
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
         return out

@@ -259,10 +259,11 @@ class TowerMLPFn(Function):
                 if (dgamma is None) != (dbeta is None):               # the kernel writes both or none
                     dgamma = dgamma if dgamma is not None else torch.zeros_like(params[base + 2])
                     dbeta = dbeta if dbeta is not None else torch.zeros_like(params[base + 3])
-            if side is not None and dp is None:
+            if side is not None and (dp is None or getattr(dp, "streams_safe", False)):
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
-                    K.mlp_wgrad(dy, own, own_b, None, x if l == 0 else None, lower, npb, dw, db, dgamma, dbeta)
+                    K.mlp_wgrad(dy, own, own_b, (local[l] if l < L else None) if dp is not None else None,
+                                x if l == 0 else None, lower, npb, dw, db, dgamma, dbeta)
             else:
                 K.mlp_wgrad(dy, own, own_b, local[l] if l < L else None, x if l == 0 else None, lower, npb, dw, db, dgamma,
                             dbeta)
@@ -278,7 +279,7 @@ class TowerMLPFn(Function):
                 keep.append(dx)
                 if l == 0:
                     dx0 = dx
-        if side is not None and dp is None:
+        if side is not None and (dp is None or getattr(dp, "streams_safe", False)):
             main.wait_stream(side)
         return (dx0, None, *grads)
 

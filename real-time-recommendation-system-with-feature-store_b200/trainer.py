@@ -405,9 +405,11 @@ class TwoTowerTrainer:
         self.optimizer.zero_grad()
         # The two towers are independent until the loss: the user tower runs on a side stream next to the item tower
         # (autograd replays each tower's backward on the stream of its forward, so the backward overlaps the same way;
-        # every launch of a tower fills less than one wave of the 148 SMs).  Not under data parallel: the BatchNorm
-        # all-reduces of both towers would be issued on one communicator from two streams.
-        overlap = dp is None and os.environ.get("B200REC_OVERLAP", "1") != "0"
+        # every launch of a tower fills less than one wave of the 148 SMs).  Under data parallel only when each tower
+        # has its own peer all-reduce context (dist._TowerDP): BatchNorm all-reduces of both towers issued on ONE NCCL
+        # communicator from two streams would not be ordered.
+        overlap = ((dp is None or getattr(dp, "streams_safe", False))
+                   and os.environ.get("B200REC_OVERLAP", "1") != "0")
         main = torch.cuda.current_stream()
         if overlap:
             side = self._side_stream()
