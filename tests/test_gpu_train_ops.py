@@ -288,6 +288,42 @@ def test_adam_table_kernel_matches_adam_dense(rows, e):
     assert outs[0][3] == pytest.approx(float((grad.double() ** 2).sum()), rel=1e-12)
 
 
+def test_peer_allreduce_single_rank_and_graph_replay():
+    """csrc/peer_reduce.cu with world = 1 (the buffer is its own peer): data is unchanged, the sequence number in the
+    buffer advances once per call — also when the calls are replayed from a CUDA graph, which is how the data-parallel
+    training step runs them.  (World >= 2 needs one GPU per rank: tests/test_gpu_model.py DP test, tools/check_dp_training.py.)"""
+    import ctypes
+    from b200rec import _native as N
+    max_n = 512
+    nbytes = int(N.lib().b200rec_peer_allreduce_bytes(max_n))
+    assert nbytes == 256 + 2 * 8 * max_n * 8
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device=DEV)
+    ptrs = (ctypes.c_uint64 * 1)(buf.data_ptr())
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    x = torch.arange(300, dtype=torch.float64, device=DEV) * 0.25
+    ref = x.clone()
+
+    def call():
+        N.check(N.lib().b200rec_peer_allreduce_f64(N.ptr(x), x.numel(), 0, 1, ptrs, max_n, N.ptr(status), N.stream()), "peer")
+
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    assert torch.equal(x, ref) and int(buf[:8].view(torch.int64).item()) == 3 and int(status.item()) == 0
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            call()
+            call()
+    for _ in range(4):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(x, ref) and int(buf[:8].view(torch.int64).item()) == 3 + 2 * 4 and int(status.item()) == 0
+    assert N.lib().b200rec_peer_allreduce_f64(N.ptr(x), max_n + 1, 0, 1, ptrs, max_n, N.ptr(status), N.stream()) != 0
+
+
 def test_bf16_mode_within_budget():
     from b200rec.training_utils import create_two_tower_model_for_training
     torch.manual_seed(3)
