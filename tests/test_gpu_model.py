@@ -195,6 +195,71 @@ def test_content_embedding_branch():
     assert torch.allclose(e.norm(dim=1), torch.ones(4, device=DEV), atol=1e-5)
 
 
+def test_content_projection_branch_matches_reference(golden_dir):
+    """ItemTower(use_content_embedding=True): content_projection (reference two_tower.py:184-191) appended to the concat
+    (:264-266); golden from the imported reference (tests/golden/make_golden_round2.py): train-mode forward, gradients
+    of sum(emb * w) w.r.t. every parameter, eval-mode forward."""
+    from b200rec.two_tower import ItemTower
+    g = np.load(os.path.join(golden_dir, "content_branch.npz"))
+    it = ItemTower(input_dim=12, embedding_dim=32, hidden_layers=[64, 48], dropout_rate=0.0, activation="relu",
+                   categorical_features={"genre": 20}, use_content_embedding=True, content_embedding_dim=64)
+    it.load_state_dict({k[3:]: torch.from_numpy(np.asarray(g[k])) for k in g.files if k.startswith("sd.")})
+    it = it.to(DEV)
+    num, cat, content, w = (torch.from_numpy(g[k]).to(DEV) for k in ("numerical", "genre", "content", "w"))
+    it.train()
+    emb = it(num, {"genre": cat}, content)
+    (emb * w).sum().backward()
+    torch.cuda.synchronize()
+    assert _rel(emb.detach().cpu(), g["emb_train"]) <= 1e-5
+    checked = 0
+    for k, prm in it.named_parameters():
+        ref = g[f"grad.{k}"]
+        assert prm.grad is not None, k
+        assert _rel(prm.grad.cpu().numpy(), ref) <= 2e-4, f"grad {k}: {_rel(prm.grad.cpu().numpy(), ref):.3e}"
+        checked += 1
+    assert checked == len([k for k in g.files if k.startswith("grad.")])
+    it.eval()
+    with torch.no_grad():
+        assert _rel(it(num, {"genre": cat}, content).cpu(), g["emb_eval"]) <= 1e-5
+
+
+def test_loss_trajectory_matches_the_reference_trainer(golden_dir):
+    """>= 100 steps from the same init.  The golden holds the per-step losses of the reference's
+    OWN TwoTowerTrainer.train_epoch (trainers/two_tower.py:84-156: 0.7 explicit + 0.3 in-batch, clip 1.0, Adam 1e-3 /
+    wd 1e-5, dropout 0) over 120 seeded batches (5.47 -> 1.53); the same batches go through b200rec's trainer step.
+    Tolerances state what is measured: the first steps agree to fp32 rounding; later the two runs are two fp32
+    evaluations of a chaotic map (the gradient GEMMs here use 3 split-bf16 products, ~2^-17 per product, and Adam
+    divides by sqrt(v) of near-zero gradients), so the per-step loss drifts apart slowly."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    from trajectory_batches import make_batches
+    from b200rec.trainer import TwoTowerTrainer
+    from b200rec.training_utils import create_two_tower_model_for_training
+    g = np.load(os.path.join(golden_dir, "trajectory_120.npz"))
+    steps, B, R = int(g["steps"]), int(g["B"]), int(g["R"])
+    ud, idim = int(g["user_dim"]), int(g["item_dim"])
+    cfg = {"embedding_dim": 64, "hidden_layers": [128, 64], "dropout_rate": 0.0, "temperature": 0.05}
+    model = create_two_tower_model_for_training(ud, idim, cfg)
+    model.load_state_dict({k[3:]: torch.from_numpy(np.asarray(g[k])) for k in g.files if k.startswith("sd.")})
+    tr = TwoTowerTrainer(model, [], [], {"learning_rate": 1e-3, "weight_decay": 1e-5,
+                                         "checkpoint_dir": "/tmp/b200rec_traj_ckpt"}, device=DEV)
+    model.train()
+    got = []
+    for b in make_batches(int(g["seed"]), steps, B, R, ud, idim):
+        got.append(tr.train_step(b["user_features"].to(DEV), b["pos_item_features"].to(DEV),
+                                 b["neg_item_features"].to(DEV)))
+    got = torch.stack(got).double().cpu().numpy()
+    ref = g["losses"]
+    rel = np.abs(got - ref) / np.abs(ref)
+    print("trajectory rel diff: first 10 max %.2e, all max %.2e, last %.2e" % (rel[:10].max(), rel.max(), rel[-1]))
+    assert rel[:10].max() <= 1e-5, rel[:10]
+    assert rel.max() <= TRAJECTORY_TOL, (rel.max(), int(rel.argmax()))
+    assert abs(got.mean() - float(g["epoch_mean"])) <= TRAJECTORY_TOL * float(g["epoch_mean"])
+
+
+TRAJECTORY_TOL = 2e-3
+
+
 def test_eval_determinism_and_save_load_roundtrip(tmp_path):
     m = _model()
     m.eval()
