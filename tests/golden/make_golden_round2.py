@@ -83,7 +83,9 @@ def trajectory(steps=120, seed=77, B=256, R=4, user_dim=3, item_dim=20):
     model.contrastive_loss, model.in_batch_negative_loss = c, i
     mean = tr.train_epoch(1)
     out = dict(init)
-    out.update({"losses": np.asarray(losses, dtype=np.float64), "epoch_mean": np.float64(mean), "seed": np.int64(seed),
+    out.update({"batch_checksum": np.asarray([float(b["user_features"].double().sum() + b["pos_item_features"].double().sum()
+                                                    + b["neg_item_features"].double().sum()) for b in batches]),
+                "losses": np.asarray(losses, dtype=np.float64), "epoch_mean": np.float64(mean), "seed": np.int64(seed),
                 "B": np.int64(B), "R": np.int64(R), "steps": np.int64(steps), "user_dim": np.int64(user_dim),
                 "item_dim": np.int64(item_dim)})
     out.update({f"final.{k}": v.detach().numpy().copy() for k, v in model.state_dict().items()})

@@ -298,3 +298,25 @@ def test_blocked_baseline_search_equals_the_checker_on_tie_free_data():
     small = flat_ip.IndexFlatIP(24)
     small.add(cat[:20])
     assert np.array_equal(I[:, :20], small.search(qry, 30)[1][:, :20])
+
+
+def test_round2_goldens_are_consistent(golden_dir):
+    """content_branch.npz / trajectory_120.npz (tests/golden/make_golden_round2.py, imported reference): the trajectory's
+    batches regenerate bit for bit from the stored seed on this machine (torch CPU generator), the reference's loss
+    falls from ~ln-scale to < 2 over the 120 steps, the content-branch embeddings are unit rows."""
+    import os
+    import sys
+    import numpy as np
+    sys.path.insert(0, golden_dir)
+    from trajectory_batches import make_batches
+    g = np.load(os.path.join(golden_dir, "trajectory_120.npz"))
+    batches = make_batches(int(g["seed"]), int(g["steps"]), int(g["B"]), int(g["R"]), int(g["user_dim"]), int(g["item_dim"]))
+    sums = [float(b["user_features"].double().sum() + b["pos_item_features"].double().sum()
+                  + b["neg_item_features"].double().sum()) for b in batches]
+    assert np.array_equal(np.asarray(sums), g["batch_checksum"])
+    assert g["losses"].shape == (120,) and g["losses"][0] > 5.0 and g["losses"][-1] < 2.0
+    assert abs(g["losses"].mean() - float(g["epoch_mean"])) < 1e-6
+    c = np.load(os.path.join(golden_dir, "content_branch.npz"))
+    for k in ("emb_train", "emb_eval"):
+        assert np.allclose(np.linalg.norm(c[k], axis=1), 1.0, atol=1e-5)
+    assert any(k.startswith("grad.content_projection") for k in c.files)
