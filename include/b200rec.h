@@ -275,6 +275,14 @@ int b200rec_adam_dense_dev(float* p, float* g, float* m, float* v, int64_t n, fl
 int b200rec_scatter_add_rows_flagged(const int64_t* idx, int64_t B, const float* dY, int64_t ld_dy, int width,
                                      int64_t padding_idx, int64_t table_rows, float* dense, int64_t ld, int32_t* row_flags,
                                      void* stream);
+/* Row-sparse tables without a sort: acc [B, width] must be zero, slot [table_rows] int32 all zero (it is zero again on
+ * return).  rows_out[b] = idx[b] for the first sample of every distinct valid row (its leader) and -1 otherwise; the
+ * gradient rows of all samples of a row are summed into acc[leader].  Feed (rows_out, acc, n = B) to
+ * b200rec_sparse_adam(_dev), which skips rows < 0, and acc to b200rec_sumsq.  Replaces b200rec_embedding_sparse_grad
+ * (sort + segment sum) on the training path; that one stays for deterministic runs. */
+int b200rec_sparse_claim_accumulate(const int64_t* idx, int64_t B, const float* dY, int64_t ld_dy, int width,
+                                    int64_t padding_idx, int64_t table_rows, int32_t* slot, int64_t* rows_out, float* acc,
+                                    void* stream);
 int b200rec_table_sumsq(const float* g, int64_t ld, int64_t rows, int width, const int32_t* row_flags, double* out,
                         void* stream);
 int b200rec_adam_table(float* p, float* g, float* m, float* v, int64_t ld, int64_t rows, int width, int32_t* row_flags,

@@ -51,6 +51,7 @@ SIGNATURES = {
     "b200rec_scatter_add_rows": (_I, [_P, _I64, _P, _I64, _I, _I64, _I64, _P, _I64, _P]),
     "b200rec_peer_allreduce_bytes": (_SZ, [_I]),
     "b200rec_peer_allreduce_f64": (_I, [_P, _I, _I, _I, _P, _I, _P, _P]),
+    "b200rec_sparse_claim_accumulate": (_I, [_P, _I64, _P, _I64, _I, _I64, _I64, _P, _P, _P, _P]),
     "b200rec_scatter_add_rows_flagged": (_I, [_P, _I64, _P, _I64, _I, _I64, _I64, _P, _I64, _P, _P]),
     "b200rec_table_sumsq": (_I, [_P, _I64, _I64, _I, _P, _P, _P]),
     "b200rec_adam_table": (_I, [_P, _P, _P, _P, _I64, _I64, _I, _P, _F, _F, _F, _F, _F, _F, _F, _P, _P, _I, _P]),

@@ -270,6 +270,43 @@ scatter_add_rows_kernel(const int64_t* __restrict__ idx, int64_t B, const float*
     if (row_flags != nullptr && lane == 0) row_flags[r] = 1;   // this row's gradient is (possibly) non-zero this step
   }
 }
+
+// Row-sparse tables (config 4: 50 M rows): the optimiser needs every DISTINCT touched row once, with the gradients of its
+// duplicates summed.  Sort + segment sum did that in ~10 launches and ~140 us per table (cub radix sort of 8192 keys,
+// scan, a 32-block segment sum); here the first sample that claims a row (atomicCAS on a per-row slot) becomes its
+// leader, every sample adds its gradient row to the LEADER's row of a compact [B, width] buffer, and rows_out[b] is the
+// row id for leaders and -1 for everybody else (the sparse Adam skips -1).  One launch + a release launch that frees
+// the slots again; duplicates are summed with fp32 atomics (order-dependent in the last bit, as in the dense scatter).
+__global__ void __launch_bounds__(256)
+sparse_claim_accumulate_kernel(const int64_t* __restrict__ idx, int64_t B, const float* __restrict__ dY, int64_t ld_dy,
+                               int width, int64_t padding_idx, int64_t table_rows, int32_t* __restrict__ slot,
+                               int64_t* __restrict__ rows_out, float* __restrict__ acc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += warps) {
+    const int64_t r = __ldg(idx + b);
+    if (r == padding_idx || r < 0 || r >= table_rows) {
+      if (lane == 0) rows_out[b] = -1;
+      continue;
+    }
+    int old = 0;
+    if (lane == 0) old = atomicCAS(slot + r, 0, (int)b + 1);   // 0 = free, b + 1 = claimed by sample b
+    old = __shfl_sync(0xffffffffu, old, 0);
+    const int64_t leader = old == 0 ? b : (int64_t)old - 1;
+    if (lane == 0) rows_out[b] = old == 0 ? r : -1;
+    const float* src = dY + b * ld_dy;
+    float* dst = acc + leader * width;
+    for (int c = lane; c < width; c += 32) atomicAdd(dst + c, __ldg(src + c));
+  }
+}
+
+__global__ void sparse_release_kernel(const int64_t* __restrict__ rows, int64_t n, int32_t* __restrict__ slot) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int64_t r = rows[i];
+    if (r >= 0) slot[r] = 0;
+  }
+}
 }  // namespace b200
 
 extern "C" int b200rec_scatter_add_rows(const int64_t* idx, int64_t B, const float* dY, int64_t ld_dy, int width,
@@ -296,6 +333,23 @@ extern "C" int b200rec_scatter_add_rows_flagged(const int64_t* idx, int64_t B, c
   scatter_add_rows_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(idx, B, dY, ld_dy, width, padding_idx,
                                                                                     table_rows, dense, ld, row_flags);
   B200_LAUNCH_OK("scatter_add_rows_kernel");
+  return 0;
+}
+
+
+extern "C" int b200rec_sparse_claim_accumulate(const int64_t* idx, int64_t B, const float* dY, int64_t ld_dy, int width,
+                                               int64_t padding_idx, int64_t table_rows, int32_t* slot, int64_t* rows_out,
+                                               float* acc, void* stream) {
+  using namespace b200;
+  if (!idx || !dY || !slot || !rows_out || !acc) return fail("sparse_claim_accumulate: null pointer");
+  if (B <= 0 || B >= INT32_MAX || width <= 0 || table_rows <= 0) return fail("sparse_claim_accumulate: bad sizes");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t blocks = (B + 7) / 8;
+  const int grid = (int)(blocks < (int64_t)num_sms() * 16 ? blocks : (int64_t)num_sms() * 16);
+  sparse_claim_accumulate_kernel<<<grid, 256, 0, st>>>(idx, B, dY, ld_dy, width, padding_idx, table_rows, slot, rows_out, acc);
+  B200_LAUNCH_OK("sparse_claim_accumulate_kernel");
+  sparse_release_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(rows_out, B, slot);
+  B200_LAUNCH_OK("sparse_release_kernel");
   return 0;
 }
 

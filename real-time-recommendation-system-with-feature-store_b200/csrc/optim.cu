@@ -98,6 +98,7 @@ sparse_adam_kernel(float* __restrict__ table, float* __restrict__ m, float* __re
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < n; u += warps) {
     const int64_t r = __ldg(rows + u);
+    if (r < 0) continue;   // b200rec_sparse_claim_accumulate: a duplicate whose gradient went to its row's leader
     for (int c = lane; c < width; c += 32) {
       const int64_t o = r * ld + c;
       const float gi = __ldg(grad_rows + u * width + c) * cc;

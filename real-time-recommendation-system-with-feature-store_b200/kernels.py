@@ -218,6 +218,20 @@ def embedding_sparse_grad(idx: torch.Tensor, dY: torch.Tensor, width: int, table
     return rows, grads, n
 
 
+def sparse_claim_accumulate(idx: torch.Tensor, dY: torch.Tensor, width: int, table_rows: int, slot: torch.Tensor,
+                            padding_idx: int = 0):
+    """Sort-free coalescing for row-sparse tables: returns (rows int64 [B] with -1 for duplicates / invalid ids,
+    grads [B, width] with every distinct row's summed gradient in its leader's row, n int32[1] = B)."""
+    B = idx.shape[0]
+    rows = torch.empty((B,), dtype=torch.int64, device=idx.device)
+    acc = torch.zeros((B, width), dtype=torch.float32, device=idx.device)
+    n = torch.full((1,), B, dtype=torch.int32, device=idx.device)
+    N.check(N.lib().b200rec_sparse_claim_accumulate(N.ptr(idx), B, N.ptr(dY), dY.stride(0), width, padding_idx, table_rows,
+                                                    N.ptr(slot), N.ptr(rows), N.ptr(acc), N.stream()),
+            "sparse_claim_accumulate")
+    return rows, acc, n
+
+
 def scatter_add_rows(idx: torch.Tensor, dY: torch.Tensor, width: int, dense: torch.Tensor, padding_idx: int = 0,
                      row_flags: Optional[torch.Tensor] = None) -> None:
     """dense[idx[b], :width] += dY[b, :width] with fp32 atomics (padding row and out-of-range ids skipped);

@@ -317,6 +317,14 @@ class NormalizeFn(Function):
         return K.normalize_bwd(de, e, norms)
 
 
+def sparse_slot_map(table: torch.Tensor) -> torch.Tensor:
+    """int32 [rows] claim map of a row-sparse table (all zero between launches; 4 B per row next to the row's 4*e B)."""
+    slot = getattr(table, "_b200_slot", None)
+    if slot is None or slot.device != table.device or slot.shape[0] != table.shape[0]:
+        slot = table._b200_slot = torch.zeros((table.shape[0],), dtype=torch.int32, device=table.device)
+    return slot
+
+
 class GatherConcatFn(Function):
     """cat([numerical, emb_f(idx_f) ...], -1) in one kernel (two_tower.py:113-126); backward = coalesced sparse row
     gradients per table, delivered as the dense gradient nn.Embedding(sparse=False) produces (padding row 0 gets none),
@@ -379,6 +387,15 @@ class GatherConcatFn(Function):
                 touch = getattr(table, "_b200_touch", None)
                 if touch is not None:
                     touch[0]._mark(touch[1], flagged=getattr(table, "_b200_row_flags", None) is not None)
+                grads.append(None)
+                continue
+            if getattr(table, "_b200_sparse", False) and os.environ.get("B200REC_EMB_BWD", "atomic") != "sorted":
+                # row-sparse table: claim a leader per distinct row and add every sample's gradient to it (one launch
+                # instead of sort + scan + segment sum); duplicates and invalid ids come back as row -1
+                rows, vals, n = K.sparse_claim_accumulate(idx64[f], dout[:, offs[f]:], widths[f], table.shape[0],
+                                                          sparse_slot_map(table), 0)
+                prev = getattr(table, "_b200_sparse_grad", None)
+                table._b200_sparse_grad = (prev or []) + [(rows, vals, n)]
                 grads.append(None)
                 continue
             rows, vals, n = K.embedding_sparse_grad(idx64[f], dout[:, offs[f]:], widths[f], table.shape[0], 0)

@@ -164,6 +164,9 @@ class FlatAdam:
             rows = torch.cat([r for r, _, _ in lists]) if len(lists) > 1 else lists[0][0]
             vals = torch.cat([v for _, v, _ in lists]) if len(lists) > 1 else lists[0][1]
             rows, vals = dp.gather_sparse(rows, vals)
+            if os.environ.get("B200REC_EMB_BWD", "atomic") != "sorted":
+                from .ops import sparse_slot_map
+                return [K.sparse_claim_accumulate(rows, vals, vals.shape[1], p.shape[0], sparse_slot_map(p), 0)]
             return [K.embedding_sparse_grad(rows, vals, vals.shape[1], p.shape[0], 0)]
         if len(lists) <= 1:
             return lists

@@ -324,6 +324,40 @@ def test_peer_allreduce_single_rank_and_graph_replay():
     assert N.lib().b200rec_peer_allreduce_f64(N.ptr(x), max_n + 1, 0, 1, ptrs, max_n, N.ptr(status), N.stream()) != 0
 
 
+def test_sparse_claim_accumulate_equals_sort_and_segment_sum():
+    """Row-sparse table gradients without a sort (b200rec_sparse_claim_accumulate): every distinct valid row appears
+    once in rows_out (-1 for duplicates, the padding id and out-of-range ids), its summed gradient sits in the same
+    position of the compact buffer, the claim map is all zero again; scattered into a dense table the result equals
+    the sort + segment-sum path (b200rec_embedding_sparse_grad) up to the order of the fp32 additions."""
+    from b200rec import kernels as K
+    g = torch.Generator().manual_seed(9)
+    rows_t, B, e = 300, 4096, 40
+    ids = torch.randint(0, rows_t, (B,), generator=g)
+    ids[::97] = 0            # padding id
+    ids[5::211] = rows_t + 3  # out of range
+    ids[7::223] = -2
+    dY = torch.randn(B, e + 8, generator=g)          # a column block of a wider gradient
+    slot = torch.zeros(rows_t, dtype=torch.int32, device=DEV)
+    rows, acc, n = K.sparse_claim_accumulate(ids.to(DEV), dY.to(DEV)[:, 4:], e, rows_t, slot, 0)
+    torch.cuda.synchronize()
+    assert int(n.item()) == B and int(slot.abs().sum().item()) == 0
+    r = rows.cpu()
+    valid = (ids > 0) & (ids < rows_t)
+    lead = r >= 0
+    assert torch.equal(torch.sort(r[lead]).values, torch.unique(ids[valid]))      # every distinct valid row exactly once
+    assert torch.equal(r[lead], ids[lead]) and not lead[~valid].any()
+    assert float(acc.cpu()[~lead].abs().max()) == 0.0
+    ref = torch.zeros(rows_t, e, dtype=torch.float64)
+    ref.index_add_(0, ids[valid], dY[valid][:, 4:4 + e].double())
+    dense = torch.zeros(rows_t, e, device=DEV)
+    K.scatter_rows(rows.clamp(min=0), acc * lead.to(DEV)[:, None], n, dense, accumulate=True)
+    assert torch.allclose(dense.cpu().double(), ref, atol=1e-5, rtol=1e-5)
+    rows2, vals2, n2 = K.embedding_sparse_grad(ids.clamp(min=-1).to(DEV), dY.to(DEV)[:, 4:], e, rows_t, 0)
+    dense2 = torch.zeros(rows_t, e, device=DEV)
+    K.scatter_rows(rows2, vals2, n2, dense2)
+    assert torch.allclose(dense.cpu(), dense2.cpu(), atol=1e-5, rtol=1e-5)
+
+
 def test_bf16_mode_within_budget():
     from b200rec.training_utils import create_two_tower_model_for_training
     torch.manual_seed(3)
