@@ -77,18 +77,24 @@ class TowerOracle:
     # ---- forward (two_tower.py:112-132) -------------------------------------------------------
     def forward(self, numerical: np.ndarray, categorical: Optional[Dict[str, np.ndarray]] = None,
                 training: bool = True, dropout_masks: Optional[List[np.ndarray]] = None,
-                update_running: bool = False) -> np.ndarray:
+                update_running: bool = False, content: Optional[np.ndarray] = None) -> np.ndarray:
         x = np.asarray(numerical, dtype=self.dtype)
         fields = []
+        embs = []
         if categorical:
-            embs = []
             for name, idx in categorical.items():  # caller's dict order (two_tower.py:116)
                 key = f"embeddings.{name}.weight"
                 if key in self.p:
                     embs.append(self.p[key][np.asarray(idx)])
                     fields.append((name, np.asarray(idx), self.p[key].shape[1]))
-            if embs:
-                x = np.concatenate([x] + embs, axis=-1)
+        if content is not None and "content_projection.0.weight" in self.p:
+            # ItemTower content branch (two_tower.py:184-191 Linear -> ReLU -> Dropout -> Linear, appended after the
+            # categorical embeddings :264-266); forward only, dropout 0 / eval
+            c = np.asarray(content, dtype=self.dtype)
+            h = np.maximum(c @ self.p["content_projection.0.weight"].T + self.p["content_projection.0.bias"], 0)
+            embs.append(h @ self.p["content_projection.3.weight"].T + self.p["content_projection.3.bias"])
+        if embs:
+            x = np.concatenate([x] + embs, axis=-1)
         layers = []
         for l in range(self.L):
             W, b = self.p[f"mlp.{4*l}.weight"], self.p[f"mlp.{4*l}.bias"]

@@ -320,3 +320,18 @@ def test_round2_goldens_are_consistent(golden_dir):
     for k in ("emb_train", "emb_eval"):
         assert np.allclose(np.linalg.norm(c[k], axis=1), 1.0, atol=1e-5)
     assert any(k.startswith("grad.content_projection") for k in c.files)
+
+
+def test_oracle_content_projection_branch_matches_reference(golden_dir):
+    """oracle.TowerOracle with the ItemTower content branch (two_tower.py:184-191,264-266) against the golden generated
+    from the imported reference: train-mode (batch statistics) and eval-mode embeddings."""
+    import os
+    import numpy as np
+    from oracle.two_tower import TowerOracle
+    g = np.load(os.path.join(golden_dir, "content_branch.npz"))
+    t = TowerOracle({k[3:]: g[k] for k in g.files if k.startswith("sd.")}, 2, "relu")
+    # the golden's eval forward ran after the training forward had updated the running statistics
+    for training, key in ((True, "emb_train"), (False, "emb_eval")):
+        e = t.forward(g["numerical"], {"genre": g["genre"]}, training=training, content=g["content"],
+                      update_running=training)
+        assert np.abs(e - g[key]).max() <= 2e-6, key
