@@ -309,6 +309,8 @@ class _TowerDP:
         self._parent, self._peer_ar = parent, peer_ar
 
     def __getattr__(self, name):
+        if name.startswith("_"):   # copy / pickle probe dunder and private names before __init__ has run
+            raise AttributeError(name)
         return getattr(self._parent, name)
 
     def reduce_sums(self, t: torch.Tensor) -> None:
