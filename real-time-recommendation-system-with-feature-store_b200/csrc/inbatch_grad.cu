@@ -1,9 +1,10 @@
 // Fused backward of the in-batch negative loss (K3, reference src/models/two_tower.py:453-479: S = U.V^T / T,
 // CE(S, arange) — what torch autograd turns into softmax(S) - onehot followed by two GEMMs).  Flash-style: the logits
 // tile is RECOMPUTED on the tensor cores (tcgen05, accumulator in TMEM), turned into G = coef * (exp(S/T - lse) - onehot)
-// in registers, written to shared memory as a split-bf16 MMA operand and immediately contracted with the other side's
-// embeddings into the gradient accumulator (also TMEM).  Neither S, nor the probabilities, nor G ever reach HBM: the
-// kernel reads 2 x (B + NI) x E operands and writes the two [rows, E] gradients.
+// in registers, written back to TENSOR MEMORY as split-bf16 pieces (tcgen05.st) and contracted from there — as the TMEM
+// A operand of a tcgen05.mma — with the other side's embeddings into the gradient accumulator (also TMEM).  Neither S,
+// nor the probabilities, nor G ever reach HBM or shared memory: the kernel reads 2 x (B + NI) x E operand pieces and
+// writes the two [rows, E] gradients.
 //
 //   out[r, :] = sum_c G[r, c] * Y[c, :]      rows r from X (a 128-row tile resident in shared memory), columns c from Y
 //   mode U: X = U, Y = V, lse indexed by row,    one-hot at c == r + diag0          ->  dU
@@ -12,16 +13,17 @@
 // tile's columns are split over several units — data parallel: 8192 local users x 65536 gathered items — the partial
 // gradients are combined with fp32 atomics into a pre-zeroed output).
 //
-// Per CTA: warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warp 2 TMEM allocator, warps 4-19 epilogue
-// (thread = TMEM lane x 16-column quarter of the 64-column logits tile; with 8 epilogue warps of 32 columns each the
-// exp / split / store work per tile, not the tensor core, set the pace: 2 warps per scheduler could not hide its latency).  Pipeline per Y tile t:
-//   TMA: Y operand pieces (for S) + Y^T pieces (for the gradient GEMM) -> stage t % NST            full / empty
-//   MMA: S(t+1) = X . Y(t+1)^T  (split-bf16 products h.h + m.h + h.m [+ l.h + h.l + m.m])           s_full / s_empty
-//   epi: S(t) -> G(t) pieces (h, m) in shared memory, SW128 K-major                                 g_full / g_empty
-//   MMA: OUT[t % NACC] += G(t) . Y^T(t)   (NACC accumulators: tcgen05 adds with truncation, short chains stay exact)
+// Per CTA: warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warp 2 TMEM allocator, warps 4-19 epilogue in two
+// groups of 8 (group = tile parity; warp = TMEM lane quarter x 32-column half of the logits tile).  Pipeline per Y tile t:
+//   TMA: Y operand pieces -> stage t % NST (the SAME tile feeds both GEMMs)                          full / empty
+//   MMA: S(t+2) = X . Y(t+2)^T  (split-bf16 products h.h + m.h + h.m [+ l.h + h.l + m.m]), B K-major  s_full / s_empty
+//   epi: S(t) -> G(t) pieces (h, m) -> TMEM columns of G buffer t % 2 (tcgen05.st)                   g_full / g_empty
+//   MMA: OUT[t % NACC] += G(t) . Y(t)   A = G from TMEM (TS form), B = the Y tile read MN-major (N = E contiguous,
+//        K = tile rows); NACC accumulators: tcgen05 adds with truncation, short chains stay exact
+// Everything the MMA-issuing warp computes per tile is a compile-time constant of IgCfg<E, NPS, NPG>.
 // fp32-grade numerics as everywhere in this library: operands are exact sums of bf16 pieces, products of pieces are
 // exact in the tensor core, only the dropped piece products (<= 2^-17 relative for 3 products) and fp32 accumulation
-// remain.
+// remain.  History and ncu evidence: profiles/r02_inbatch_grad_history.md.
 #include "host_util.h"
 #include "tc_common.cuh"
 #include "../../include/b200rec.h"
