@@ -19,6 +19,11 @@ published IndexFlatIP algorithm:
 It is pinned instead against the reference's own exact twin (np.dot + argsort) in
 ``tests/test_oracle.py`` on tie-free data.
 
+Three restatements of the same search live here: ``IndexFlatIP.search`` (the readable CHECKER the parity tests
+compare the CUDA path with), ``search_reservoir`` (the CPU BASELINE bench.py times: MKL sgemm tiles + faiss'
+reservoir result handler in C, ``oracle/csrc/flat_select.c``) and ``search_blocked`` (the same with torch.topk per
+block, the fallback when no C compiler is around); the tests pin the latter two to the checker.
+
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
 leg may import this module.
 """
@@ -161,6 +166,65 @@ def search_blocked(xb, q, k: int, threads: int = 0, db_block: int = 1 << 17, q_b
             run_s, run_i = top_s, torch.gather(cat_i, 1, pos)
         D[q0:q0 + q_block], I[q0:q0 + q_block] = run_s, run_i
     return D.numpy(), I.numpy()
+
+
+_SELECT_LIB = None
+
+
+def _select_lib():
+    """oracle/_build/libflatselect.so (oracle/csrc/flat_select.c: faiss-cpu's reservoir result handler restated in C),
+    built on first use when missing or stale."""
+    global _SELECT_LIB
+    if _SELECT_LIB is None:
+        import ctypes
+        from . import build_c
+        lib = ctypes.CDLL(build_c.build())
+        p, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+        lib.flat_select_add_block.argtypes = [p, i64, i64, i64, i64, i32, p, p, p, p, i32]
+        lib.flat_select_add_block.restype = None
+        lib.flat_select_finish.argtypes = [i64, i32, p, p, p, p, p, i32]
+        lib.flat_select_finish.restype = None
+        _SELECT_LIB = lib
+    return _SELECT_LIB
+
+
+def search_reservoir(xb, q, k: int, threads: int = 0, db_block: int = 4096, q_block: int = 1024):
+    """Exact flat IP search the way faiss-cpu 1.7.4 runs IndexFlatIP for nq >= 20 and k >= 100
+    (`exhaustive_inner_product_blas` + `ReservoirResultHandler`): sgemm over a (query block x database block) tile that
+    stays cache resident (torch-CPU / MKL, all host threads), the tile handed to a per-query reservoir of capacity 2k
+    that only admits scores above the query's running threshold (oracle/csrc/flat_select.c, OpenMP over the queries).
+    About one compare per score next to the 2·D FLOP of the sgemm, so the search runs at the sgemm rate — this is the
+    CPU BASELINE bench.py times (`cpu_baseline`, `--impl reference`).  Order (score desc, row asc) like the checker
+    IndexFlatIP.search above.  xb / q: float32 numpy or torch CPU tensors.  Returns (D, I) numpy."""
+    import torch
+    lib = _select_lib()
+    if threads > 0:
+        torch.set_num_threads(threads)
+    nt = threads if threads > 0 else torch.get_num_threads()
+    xb = torch.as_tensor(xb)
+    q = torch.as_tensor(q)
+    assert xb.dtype == torch.float32 and q.dtype == torch.float32 and xb.is_contiguous() and q.is_contiguous()
+    nq, n = q.shape[0], xb.shape[0]
+    D = np.empty((nq, k), dtype=np.float32)
+    I = np.empty((nq, k), dtype=np.int64)
+    tile = torch.empty((min(q_block, max(nq, 1)), db_block), dtype=torch.float32)
+    for q0 in range(0, nq, q_block):
+        qs = q[q0:q0 + q_block]
+        m = qs.shape[0]
+        res_s = np.empty((m, 2 * k), dtype=np.float32)
+        res_i = np.empty((m, 2 * k), dtype=np.int64)
+        res_n = np.zeros((m,), dtype=np.int32)
+        thr = np.full((m,), -FLT_MAX, dtype=np.float32)
+        for b0 in range(0, n, db_block):
+            blk = xb[b0:b0 + db_block]
+            w = blk.shape[0]
+            s = tile[:m, :w]
+            torch.matmul(qs, blk.T, out=s)
+            lib.flat_select_add_block(s.data_ptr(), s.stride(0), m, w, b0, k, res_s.ctypes.data, res_i.ctypes.data,
+                                      res_n.ctypes.data, thr.ctypes.data, nt)
+        lib.flat_select_finish(m, k, res_s.ctypes.data, res_i.ctypes.data, res_n.ctypes.data,
+                               D[q0:q0 + m].ctypes.data, I[q0:q0 + m].ctypes.data, nt)
+    return D, I
 
 
 class FaissIndexOracle:

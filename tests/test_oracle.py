@@ -283,7 +283,7 @@ def test_metrics_oracle_matches_the_reference_evaluator():
 
 
 def test_blocked_baseline_search_equals_the_checker_on_tie_free_data():
-    """oracle.flat_ip.search_blocked (threaded sgemm + topk, what bench.py times as the CPU baseline) returns the same
+    """oracle.flat_ip.search_blocked (threaded sgemm + topk, the CPU baseline's fallback without a C compiler) returns the same
     ids and scores as the deterministic checker IndexFlatIP.search when no two scores are equal."""
     rng = np.random.default_rng(8)
     cat = rng.standard_normal((5000, 24)).astype(np.float32)
@@ -298,6 +298,43 @@ def test_blocked_baseline_search_equals_the_checker_on_tie_free_data():
     small = flat_ip.IndexFlatIP(24)
     small.add(cat[:20])
     assert np.array_equal(I[:, :20], small.search(qry, 30)[1][:, :20])
+
+
+def test_reservoir_baseline_search_equals_the_checker_including_ties():
+    """oracle.flat_ip.search_reservoir (blocked sgemm + the C reservoir result handler of oracle/csrc/flat_select.c: what
+    bench.py times as the CPU baseline) returns exactly the checker's lists, also when scores tie (duplicated rows: the
+    order is score desc, row asc, and only a strictly greater score displaces the k-th), for ragged block shapes, for
+    k larger than the catalogue and when reservoirs overflow many times (rows sorted by increasing score)."""
+    rng = np.random.default_rng(9)
+    cat = rng.standard_normal((6000, 24)).astype(np.float32)
+    cat[1000:1500] = cat[:500]            # exact score ties between rows r and r + 1000
+    cat[5990:] = cat[10:20]
+    qry = rng.standard_normal((70, 24)).astype(np.float32)
+    ix = flat_ip.IndexFlatIP(24)
+    ix.add(cat)
+    for k in (1, 30, 100):
+        rD, rI = ix.search(qry, k)
+        for db_block, q_block, threads in ((700, 32, 3), (4096, 1024, 0), (64, 7, 2)):
+            D, I = flat_ip.search_reservoir(cat, qry, k, threads, db_block=db_block, q_block=q_block)
+            assert np.array_equal(I, rI), (k, db_block)
+            assert np.allclose(D, rD, atol=1e-5)
+    D, I = flat_ip.search_reservoir(cat[:20], qry, 30)        # k > ntotal: -1 / -FLT_MAX padding
+    assert (I[:, 20:] == -1).all() and (D[:, 20:] == -flat_ip.FLT_MAX).all()
+    small = flat_ip.IndexFlatIP(24)
+    small.add(cat[:20])
+    assert np.array_equal(I[:, :20], small.search(qry, 30)[1][:, :20])
+    # worst case for the reservoir: every row beats the threshold (rows ordered by increasing score for every query)
+    base = np.abs(rng.standard_normal((1, 8))).astype(np.float32)
+    ramp = (np.arange(1, 3001, dtype=np.float32)[:, None] * base)
+    qpos = np.abs(rng.standard_normal((5, 8))).astype(np.float32)
+    ix2 = flat_ip.IndexFlatIP(8)
+    ix2.add(ramp)
+    rD, rI = ix2.search(qpos, 10)
+    D, I = flat_ip.search_reservoir(ramp, qpos, 10, 2, db_block=256)
+    assert np.array_equal(I, rI) and np.allclose(D, rD, rtol=1e-6)
+    # and it agrees with the torch.topk variant on tie-free data
+    cat3 = rng.standard_normal((5000, 24)).astype(np.float32)
+    assert np.array_equal(flat_ip.search_reservoir(cat3, qry, 30)[1], flat_ip.search_blocked(cat3, qry, 30)[1])
 
 
 def test_round2_goldens_are_consistent(golden_dir):
