@@ -300,6 +300,28 @@ def test_blocked_baseline_search_equals_the_checker_on_tie_free_data():
     assert np.array_equal(I[:, :20], small.search(qry, 30)[1][:, :20])
 
 
+def test_flat_ip_oracle_agrees_with_an_independent_brute_force_library():
+    """Third-party cross-check of the checker (faiss itself is not installable here): scikit-learn's brute-force
+    NearestNeighbors under the cosine metric ranks unit-norm rows exactly as IndexFlatIP ranks them by inner product
+    (cosine distance = 1 - ip), and torch.topk over the full fp32 score matrix gives the same lists."""
+    neighbors = pytest.importorskip("sklearn.neighbors")
+    rng = np.random.default_rng(21)
+    cat = flat_ip.normalize_L2(rng.standard_normal((3000, 32)).astype(np.float32))
+    qry = flat_ip.normalize_L2(rng.standard_normal((40, 32)).astype(np.float32))
+    ix = flat_ip.IndexFlatIP(32, db_block=512)
+    ix.add(cat)
+    D, I = ix.search(qry, 25)
+    nn = neighbors.NearestNeighbors(n_neighbors=25, algorithm="brute", metric="cosine").fit(cat.astype(np.float64))
+    dist, ind = nn.kneighbors(qry.astype(np.float64))
+    assert np.allclose(1.0 - dist, D, atol=1e-6)
+    mism = I != ind                        # fp64 vs fp32 scores may swap neighbours closer than fp32 resolution
+    assert mism.mean() < 0.02 and (np.abs((1.0 - dist) - D)[mism] < 1e-6).all()
+    import torch
+    ts, ti = torch.topk(torch.from_numpy(qry) @ torch.from_numpy(cat).T, 25, dim=1)
+    m2 = I != ti.numpy()
+    assert np.allclose(D, ts.numpy(), atol=1e-6) and m2.mean() < 0.02
+
+
 def test_reservoir_baseline_search_equals_the_checker_including_ties():
     """oracle.flat_ip.search_reservoir (blocked sgemm + the C reservoir result handler of oracle/csrc/flat_select.c: what
     bench.py times as the CPU baseline) returns exactly the checker's lists, also when scores tie (duplicated rows: the
