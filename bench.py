@@ -268,14 +268,14 @@ def _cpu_sample(rows: int, queries: int):
 
 
 def run_reference(args, rank: int, world: int):
-    """CPU arm: W warm-up + EXACTLY K timed steps, each step one flat search of a bounded sample of config 3 (1024 of
-    the 4096 queries against 1 M of the 10 M rows, fp32, all host threads); QPS scaled linearly in the rows.  The
+    """CPU arm: W warm-up + EXACTLY K timed steps, each step one flat search of a bounded sample of config 3 (the whole
+    4096-query batch against 1 M of the 10 M rows, fp32, all host threads); QPS scaled linearly in the rows.  The
     sample shrinks (never the step count) if K steps of it would not end within a few minutes on this host."""
     if rank != 0:
         return
     search, what = _cpu_search()
     threads = host_threads()
-    rows, queries = 1_000_000, 1024
+    rows, queries = 1_000_000, N_QUERIES
     steps, warmup = max(args.steps, 1), max(args.warmup, 0)
     cat, qry = _cpu_sample(rows, queries)
     search(cat[: 1 << 17], qry[:64], TOPK, threads)   # start the thread pools
@@ -1002,7 +1002,7 @@ def main():
     cpu = None
     if want_cpu:
         threads = host_threads()
-        rows, queries = 1_000_000, 1024
+        rows, queries = 1_000_000, N_QUERIES
         try:
             v, dt, what = cpu_retrieval_baseline(rows, queries, threads)
             cpu = {"value": v, "unit": "queries/s", "cores": threads, "kind": "port",
