@@ -92,6 +92,32 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert "null" in _native.last_error()
 
 
+def test_every_entry_point_rejects_null_arguments_with_a_message():
+    """Error behaviour of the whole C-ABI, no GPU needed: called with null pointers and zero sizes every int-returning
+    entry point that takes a pointer returns non-zero and explains itself through b200rec_last_error() — no crash, no
+    launch, no exception across the ABI (the two pure shape predicates return 0 = "no")."""
+    import ctypes as C
+    from b200rec import _native
+    lib = _native.lib()
+    predicates = {"b200rec_topk_has_sample", "b200rec_inbatch_grad_supported"}
+    before = lib.b200rec_launch_count()
+    checked = 0
+    for name, (restype, argtypes) in _native.SIGNATURES.items():
+        if restype is not C.c_int or C.c_void_p not in argtypes and name not in predicates:
+            continue
+        args = [None if t is C.c_void_p else (0.0 if t in (C.c_float, C.c_double) else 0) for t in argtypes]
+        rc = getattr(lib, name)(*args)
+        if name in predicates:
+            assert rc == 0, name
+            continue
+        assert rc != 0, f"{name} accepted null pointers"
+        msg = _native.last_error()
+        assert msg and ("null" in msg or "empty" in msg or "must" in msg), f"{name}: unhelpful error {msg!r}"
+        checked += 1
+    assert checked >= 45
+    assert lib.b200rec_launch_count() == before
+
+
 def test_no_cpu_fallback():
     from b200rec.training_utils import create_two_tower_model_for_training
     m = create_two_tower_model_for_training(3, 20)
