@@ -118,6 +118,26 @@ def test_every_entry_point_rejects_null_arguments_with_a_message():
     assert lib.b200rec_launch_count() == before
 
 
+def test_header_is_plain_c_and_a_c_host_links(tmp_path):
+    """The boundary is a C ABI, not a Python extension: include/b200rec.h compiles as pedantic C99, a C program links
+    against libb200rec.so and gets its errors as return codes + b200rec_last_error() (tests/c_host/host.c)."""
+    import shutil
+    import subprocess
+    from b200rec import _native
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    libdir = os.path.dirname(_native.LIB_PATH)
+    exe = str(tmp_path / "host")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c_host", "host.c"), "-o", exe, "-L", libdir, "-lb200rec",
+                        f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "config-3 workspace" in r.stdout
+
+
 def test_no_cpu_fallback():
     from b200rec.training_utils import create_two_tower_model_for_training
     m = create_two_tower_model_for_training(3, 20)
