@@ -55,13 +55,19 @@ def primary_config(world: int) -> dict:
 
 
 def _peaks():
+    """Roofline denominators: the driver-measured copy bandwidth and bf16 throughput of this pool's B200s
+    (MEASURED_PEAKS.json), else the fallback B200_PROFILING.md states.  Never raises: the line being printed with the
+    fallback peaks beats losing a finished measurement to a malformed file."""
+    fallback = {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1650.0, "source": "fallback (B200_PROFILING.md)"}
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
+    try:
         with open(path) as fh:
             p = json.load(fh)
-        return {"hbm_gbs": float(p["hbm_gbs"]), "tflops": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
-                "tflops_burst": float(p["bf16_tflops"]), "source": "measured (MEASURED_PEAKS.json: sustained bf16, copy bandwidth)"}
-    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1650.0, "source": "fallback (B200_PROFILING.md)"}
+        burst = float(p["bf16_tflops"])
+        return {"hbm_gbs": float(p["hbm_gbs"]), "tflops": float(p.get("bf16_tflops_sustained") or burst),
+                "tflops_burst": burst, "source": "measured (MEASURED_PEAKS.json: sustained bf16, copy bandwidth)"}
+    except Exception:  # noqa: BLE001 - absent, unreadable or partial file
+        return fallback
 
 
 def host_threads() -> int:
