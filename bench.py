@@ -861,6 +861,24 @@ def run_serve_block(ctx: Ctx, steps: int, warmup: int):
 
 
 # ------------------------------------------------------------------------------------------------ main arm
+def run_block(extra: dict, world: int, key: str, fn, *a, **kw) -> None:
+    """One extra block of the line.  On a single GPU a failing block is recorded as {"error": ...} instead of costing
+    the headline (the retrieval numbers are already measured); under torchrun an exception stays fatal, because a rank
+    that skipped a block would leave its peers waiting inside that block's collectives."""
+    if world > 1:
+        extra[key] = fn(*a, **kw)
+        return
+    try:
+        extra[key] = fn(*a, **kw)
+    except Exception as exc:  # noqa: BLE001
+        import gc
+        extra[key] = {"error": repr(exc)[:300]}
+        del exc
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -984,20 +1002,7 @@ def main():
     bsteps = min(max(steps, 10), 30)
 
     def block(key, fn, *a, **kw):
-        """One extra block.  On a single GPU a failing block is recorded in the line instead of costing the headline
-        (the retrieval numbers above are already measured); under torchrun an exception stays fatal, because a rank that
-        skipped a block would leave its peers waiting inside that block's collectives."""
-        if world > 1:
-            extra[key] = fn(*a, **kw)
-            return
-        try:
-            extra[key] = fn(*a, **kw)
-        except Exception as exc:  # noqa: BLE001
-            import gc
-            extra[key] = {"error": repr(exc)[:300]}
-            del exc
-            gc.collect()
-            torch.cuda.empty_cache()
+        run_block(extra, world, key, fn, *a, **kw)
 
     if "train" in blocks:
         block("train", run_table_train_block, ctx, bsteps, warmup, want_cpu, name="config 2 (synthetic)", NU=1_000_000,

@@ -443,3 +443,27 @@ def test_flat_index_host_logic_without_a_gpu():
     ix._id_array = None
     assert ix.search(q, k=3)[0][0] == ["it4", "it5"]                                      # unmapped rows are skipped, not refilled
     assert eng.get_metrics()["total_queries"] == 1 and eng.get_metrics()["index_type"] == "b200"
+
+
+def test_bench_host_logic_without_a_gpu():
+    """bench.py pieces that need no GPU: both arms print the same `config`, a failing extra block is recorded inside the
+    single-GPU line but stays fatal under torchrun, the peaks loader never raises, the CPU arm picks the C reservoir."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.primary_config(8)["workload"].endswith("over 8 GPU(s)") and bench.primary_config(1)["seed"] == bench.SEED
+    extra = {}
+
+    def boom(x):
+        raise RuntimeError("no memory for " + x)
+
+    bench.run_block(extra, 1, "ok", lambda v: {"value": v}, 3)
+    bench.run_block(extra, 1, "bad", boom, "cfg4")
+    assert extra["ok"] == {"value": 3} and "no memory for cfg4" in extra["bad"]["error"]
+    with pytest.raises(RuntimeError):
+        bench.run_block(extra, 2, "bad2", boom, "serve")
+    peaks = bench._peaks()
+    assert peaks["tflops"] > 0 and peaks["hbm_gbs"] > 0 and peaks["tflops_burst"] >= peaks["tflops"]
+    search, what = bench._cpu_search()
+    assert search.__name__ == "search_reservoir" and "flat_select.c" in what
