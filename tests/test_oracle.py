@@ -394,3 +394,20 @@ def test_oracle_content_projection_branch_matches_reference(golden_dir):
         e = t.forward(g["numerical"], {"genre": g["genre"]}, training=training, content=g["content"],
                       update_running=training)
         assert np.abs(e - g[key]).max() <= 2e-6, key
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not mounted")
+def test_committed_goldens_regenerate_from_the_imported_reference(tmp_path):
+    """Provenance of tests/golden/*.npz: every generator script is re-run here (each imports the unmodified reference and
+    runs it on seeded inputs) and what it writes must equal the committed fixture — identical integer / string arrays,
+    floating-point arrays bit-identical at the generating thread count and within 1e-4 of the array's scale otherwise
+    (tests/golden/verify_goldens.py states the one exception, the chaotic 120-step trajectory)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("verify_goldens", os.path.join(os.path.dirname(__file__), "golden",
+                                                                                "verify_goldens.py"))
+    vg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vg)
+    vg.regenerate(str(tmp_path))
+    committed, problems, worst = vg.compare(str(tmp_path))
+    assert len(committed) >= 14
+    assert not problems, problems[:10]
