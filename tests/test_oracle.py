@@ -411,3 +411,94 @@ def test_committed_goldens_regenerate_from_the_imported_reference(tmp_path):
     committed, problems, worst = vg.compare(str(tmp_path))
     assert len(committed) >= 14
     assert not problems, problems[:10]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not mounted")
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_matches_the_live_reference_on_random_configurations(seed):
+    """Beyond the stored fixtures: the numpy restatement against the IMPORTED reference itself (torch-CPU autograd) on
+    configurations drawn at random — depth 1-3, every activation, ragged widths, 0-3 categorical fields per tower with
+    small and large cardinalities (row width min(50, (card+1)//2), padding id 0 present in the batch), batch sizes down
+    to 2, explicit / in-batch / mixed loss with random biases and temperature: embeddings, losses, every parameter
+    gradient (tables included) and the BatchNorm running statistics after the step."""
+    import sys
+    import torch
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    from src.models.two_tower import ItemTower, TwoTowerModel, UserTower
+    rng = np.random.default_rng(1000 + seed)
+    torch.manual_seed(1000 + seed)
+    act = ["relu", "gelu", "leaky_relu", "tanh", "sigmoid", "relu"][seed]
+    L = int(rng.integers(1, 4))
+    hidden = [int(rng.integers(3, 40)) for _ in range(L)]
+    E = int(rng.integers(2, 33))
+    B = int([2, 5, 33, 64, 17, 128][seed])
+    R = int(rng.integers(2, 6))               # neg_ratio 1 crashes in the reference (SURVEY section 7.8)
+    ud, idim = int(rng.integers(1, 12)), int(rng.integers(1, 24))
+    ucards = {f"uf{j}": int(rng.choice([1, 2, 7, 40, 300])) for j in range(int(rng.integers(0, 4)))}
+    icards = {f"if{j}": int(rng.choice([1, 3, 9, 120, 99])) for j in range(int(rng.integers(0, 4)))}
+    ut = UserTower(ud, E, hidden, 0.0, act, ucards or None)
+    it = ItemTower(idim, E, hidden, 0.0, act, icards or None, use_content_embedding=False)
+    T = float(rng.uniform(0.03, 0.5))
+    model = TwoTowerModel(ut, it, temperature=T, use_bias=True)
+    with torch.no_grad():
+        model.user_bias.fill_(float(rng.normal(0, 0.3)))
+        model.item_bias.fill_(float(rng.normal(0, 0.3)))
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.copy_(1.0 + 0.2 * torch.randn(m.weight.shape))
+                m.bias.copy_(0.1 * torch.randn(m.bias.shape))
+    model.train()
+    sd_u = {k: v.detach().numpy().copy() for k, v in ut.state_dict().items()}
+    sd_i = {k: v.detach().numpy().copy() for k, v in it.state_dict().items()}
+    uf = rng.standard_normal((B, ud)).astype(np.float32)
+    pf = rng.standard_normal((B, idim)).astype(np.float32)
+    nf = rng.standard_normal((B * R, idim)).astype(np.float32)
+    ucat = {k: rng.integers(0, c + 1, size=B) for k, c in ucards.items()}       # 0 = padding id
+    icat = {k: rng.integers(0, c + 1, size=B) for k, c in icards.items()}
+    ncat = {k: rng.integers(0, c + 1, size=B * R) for k, c in icards.items()}
+    t = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}
+    u = model.get_user_embeddings({"numerical": torch.from_numpy(uf), "categorical": t(ucat)})
+    p = model.get_item_embeddings({"numerical": torch.from_numpy(pf), "categorical": t(icat)})
+    n = model.get_item_embeddings({"numerical": torch.from_numpy(nf), "categorical": t(ncat)})
+    le_ref, li_ref = model.contrastive_loss(u, p, n), model.in_batch_negative_loss(u, p)
+    mode = seed % 3
+    loss_ref = [0.7 * le_ref + 0.3 * li_ref, li_ref, le_ref][mode]
+    loss_ref.backward()
+    # ---- the oracle on the same numbers
+    uo, po, no = tt.TowerOracle(sd_u, L, act), tt.TowerOracle(sd_i, L, act), tt.TowerOracle(sd_i, L, act)
+    ue, pe = uo.forward(uf, ucat), po.forward(pf, icat)
+    ne = no.forward(nf, ncat)
+    np.testing.assert_allclose(ue, u.detach().numpy(), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(pe, p.detach().numpy(), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(ne, n.detach().numpy(), rtol=2e-5, atol=2e-6)
+    ub, ib = float(model.user_bias.item()), float(model.item_bias.item())
+    le, du_e, dp_e, dn_e, db = tt.explicit_loss(ue, pe, ne, T, ub, ib, want_grad=True)
+    li, du_i, dp_i = tt.in_batch_loss(ue, pe, T, want_grad=True)
+    assert abs(le - le_ref.item()) <= 2e-5 * max(abs(le), 1e-3) and abs(li - li_ref.item()) <= 2e-5 * max(abs(li), 1e-3)
+    we, wi = [(0.7, 0.3), (0.0, 1.0), (1.0, 0.0)][mode]
+    gu, _ = uo.backward(we * du_e + wi * du_i)
+    gp, _ = po.backward(we * dp_e + wi * dp_i)
+    gn, _ = no.backward(we * dn_e)
+    if we:
+        assert abs(we * db - float(model.user_bias.grad)) <= 1e-4 * max(abs(we * db), 1e-4)
+    for tower, grads, extra in ((ut, gu, None), (it, gp, gn)):
+        named = dict(tower.named_parameters())
+        for k, v in grads.items():
+            ref = named[k].grad
+            ref = np.zeros_like(v) if ref is None else ref.numpy()
+            got = v + (extra[k] if extra is not None and we else 0)
+            # fp64 oracle vs the reference's fp32 autograd: 1e-4 of the gradient's scale, 5e-4 for the 2- and 5-sample
+            # batches (BatchNorm over a handful of rows divides by a variance that fp32 itself resolves poorly)
+            tol = 1e-4 if B >= 16 else 5e-4
+            assert np.abs(got - ref).max() <= tol * max(np.abs(ref).max(), 1e-5), (k, act, L)
+            if k.startswith("embeddings."):
+                assert np.abs(got[0]).max() == 0                     # padding row: no gradient
+    # BatchNorm running statistics after the three tower passes of the step (item tower: two updates)
+    uo.forward(uf, ucat, update_running=True)
+    po.forward(pf, icat, update_running=True)
+    po.forward(nf, ncat, update_running=True)
+    for tower, orc in ((ut, uo), (it, po)):
+        for k, v in tower.state_dict().items():
+            if "running" in k:
+                np.testing.assert_allclose(orc.p[k], v.numpy(), rtol=1e-4, atol=1e-6, err_msg=k)
