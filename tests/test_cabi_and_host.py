@@ -445,6 +445,75 @@ def test_flat_index_host_logic_without_a_gpu():
     assert eng.get_metrics()["total_queries"] == 1 and eng.get_metrics()["index_type"] == "b200"
 
 
+class _OracleDeviceIndex:
+    """CPU stand-in for b200rec.retrieval.FlatIPDeviceIndex in HOST-LOGIC tests only (tests may use the oracle; the
+    product never does): same surface (`add(x, normalize)`, `search(q, k, normalize)`, `ntotal`, `reconstruct_n`)."""
+
+    def __init__(self, d, storage="fp32", device=None, row_offset=0):
+        from oracle.flat_ip import IndexFlatIP
+        self.d, self._ix = d, IndexFlatIP(d)
+
+    ntotal = property(lambda self: self._ix.ntotal)
+
+    def add(self, x, normalize=False):
+        from oracle.flat_ip import normalize_L2
+        x = np.array(x, dtype=np.float32)
+        self._ix.add(normalize_L2(x) if normalize else x)
+
+    def search(self, q, k, normalize=False):
+        from oracle.flat_ip import normalize_L2
+        q = np.array(q, dtype=np.float32).reshape(-1, self.d)
+        return self._ix.search(normalize_L2(q) if normalize else q, k)
+
+    def reconstruct_n(self, i0=0, n=None):
+        return self._ix.xb[i0:(None if n is None else i0 + n)].copy()
+
+
+@pytest.mark.parametrize("metric", ["cosine", "ip"])
+def test_drop_in_index_host_logic_matches_the_reference_wrapper_goldens(monkeypatch, tmp_path, metric):
+    """The HOST side of B200FlatIndex / RetrievalEngine (casts, 1-D promotion, vectorised row -> id map, the filter_ids
+    post-pass with k_search = min(2k, N), add, save / load through the IxFI file) against wrapper_small.npz — outputs of
+    the REFERENCE's own FaissIndex / RetrievalEngine code — with the device index swapped for an oracle-backed stand-in,
+    so this half of the drop-in boundary is pinned on CPU too (tests/test_gpu_index.py runs the real thing)."""
+    import json
+    from b200rec import retrieval
+    monkeypatch.setattr(retrieval, "FlatIPDeviceIndex", _OracleDeviceIndex)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "wrapper_small.npz"))
+    cases, allowed = json.loads(str(g["cases_json"])), json.loads(str(g["allowed_json"]))
+    emb, extra, qry, N, D = g["emb"], g["extra"], g["qry"], int(g["N"]), int(g["D"])
+
+    def same(got, want):
+        assert got[0] == want[0], "item ids differ"
+        for a, b in zip(got[1], want[1]):
+            assert len(a) == len(b) and np.allclose(a, b, rtol=1e-6, atol=2e-6)
+
+    ix = retrieval.B200FlatIndex({"dimension": D, "index_factory": "IVF1024,Flat", "metric": metric})
+    with pytest.raises(ValueError, match="Index not built yet"):
+        ix.search(qry, k=3)
+    with pytest.raises(ValueError, match="No index to save"):
+        ix.save(str(tmp_path / "never"))
+    ix.build(emb.copy(), [f"item_{i}" for i in range(N)])
+    same(ix.search(qry.copy(), k=10), cases[f"{metric}_k10"])
+    same(ix.search(qry[0].copy(), k=5), cases[f"{metric}_1d_k5"])
+    same(ix.search(qry.astype(np.float64), k=7, filter_ids=allowed), cases[f"{metric}_filter_k7"])
+    assert ix.search(qry[:2].copy(), k=4, filter_ids=[]) == ([[], []], [[], []])
+    ix.save(str(tmp_path / "idx"))                       # IxFI + pkl round trip keeps rows, ids and answers
+    ix2 = retrieval.B200FlatIndex({"dimension": D, "metric": metric})
+    ix2.load(str(tmp_path / "idx"))
+    assert ix2.current_size == N and ix2.id_map[3] == "item_3"
+    same(ix2.search(qry.copy(), k=10), cases[f"{metric}_k10"])
+    ix.add(extra.copy(), [f"new_{i}" for i in range(len(extra))])
+    same(ix.search(qry.copy(), k=10), cases[f"{metric}_after_add_k10"])
+    assert ix.current_size == cases[f"{metric}_size"]
+    if metric == "cosine":
+        eng = retrieval.RetrievalEngine({"index_type": "faiss", "embedding_dim": D,
+                                         "faiss": {"index_factory": "Flat", "metric": "cosine"}})
+        eng.build_index(emb.copy(), [f"item_{i}" for i in range(N)])
+        ids, scores, metrics = eng.retrieve(qry[:2].copy(), k=6)
+        same((ids, scores), cases["engine_retrieve_k6"])
+        assert sorted(metrics.keys()) == cases["engine_metrics_keys"] and metrics["num_results"] == 12
+
+
 def test_bench_host_logic_without_a_gpu():
     """bench.py pieces that need no GPU: both arms print the same `config`, a failing extra block is recorded inside the
     single-GPU line but stays fatal under torchrun, the peaks loader never raises, the CPU arm picks the C reservoir."""
