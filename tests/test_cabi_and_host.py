@@ -198,6 +198,46 @@ def test_same_init_and_keys_as_the_imported_reference():
     assert ours.temperature == ref.temperature
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not mounted")
+def test_checkpoints_are_interchangeable_with_the_reference(tmp_path):
+    """save_model / load_model in both directions (reference two_tower.py:516-546): a checkpoint written by b200rec loads
+    into the reference model and vice versa — same file keys, same state-dict keys and layouts, biases, temperature."""
+    sys.path.insert(0, "/root/reference")
+    try:
+        from src.models.two_tower import create_two_tower_model as ref_create
+    finally:
+        sys.path.pop(0)
+    from b200rec.two_tower import create_two_tower_model
+    cfg = {"embedding_dim": 16, "temperature": 0.09,
+           "user_tower": {"input_dim": 5, "hidden_layers": [24, 16], "categorical_features": {"a": 12}},
+           "item_tower": {"input_dim": 6, "hidden_layers": [24, 16], "categorical_features": {"g": 40, "h": 3},
+                          "use_content_embedding": True}}
+    for writer_is_ours in (True, False):
+        torch.manual_seed(5 + writer_is_ours)
+        src = (create_two_tower_model if writer_is_ours else ref_create)(cfg)
+        with torch.no_grad():
+            src.user_bias.fill_(0.25)
+            src.item_bias.fill_(-0.5)
+            for m in src.modules():
+                if isinstance(m, torch.nn.BatchNorm1d):
+                    m.running_mean.normal_()
+                    m.running_var.uniform_(0.5, 2.0)
+        src.temperature = 0.123
+        path = str(tmp_path / f"ckpt_{writer_is_ours}.pth")
+        src.save_model(path)
+        ck = torch.load(path, map_location="cpu", weights_only=False)
+        assert sorted(ck.keys()) == ["item_bias", "item_tower_state", "temperature", "user_bias", "user_tower_state"]
+        torch.manual_seed(99)
+        dst = (ref_create if writer_is_ours else create_two_tower_model)(cfg)
+        dst.load_model(path)
+        a, b = src.state_dict(), dst.state_dict()
+        assert list(a.keys()) == list(b.keys())
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+        assert dst.temperature == 0.123
+        assert dst.user_bias.item() == 0.25 and dst.item_bias.item() == -0.5
+
+
 def test_shard_bounds_cover_the_catalogue():
     from b200rec.dist import shard_bounds
     for n, w in ((10_000_000, 8), (1001, 4), (7, 8), (5, 1)):
