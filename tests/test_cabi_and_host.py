@@ -238,6 +238,34 @@ def test_checkpoints_are_interchangeable_with_the_reference(tmp_path):
         assert dst.user_bias.item() == 0.25 and dst.item_bias.item() == -0.5
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not mounted")
+@pytest.mark.parametrize("config", [None, {}, {"embedding_dim": 64, "hidden_layers": [128, 64], "dropout_rate": 0.3,
+                                               "temperature": 0.1, "activation": "gelu"}])
+def test_training_factory_matches_the_reference(config):
+    """create_two_tower_model_for_training (reference src/training/utils.py:14-71): same defaults, same RNG consumption
+    (bit-identical initial weights), same temperature / dropout / activation wiring, same parameter count helper."""
+    sys.path.insert(0, "/root/reference")
+    try:
+        from src.training.utils import count_parameters as ref_count, create_two_tower_model_for_training as ref_create
+    finally:
+        sys.path.pop(0)
+    from b200rec.training_utils import count_parameters, create_two_tower_model_for_training
+    args = (3, 20) if config is None else (3, 20, config)
+    torch.manual_seed(7)
+    ref = ref_create(*args)
+    torch.manual_seed(7)
+    ours = create_two_tower_model_for_training(*args)
+    rsd, osd = ref.state_dict(), ours.state_dict()
+    assert list(rsd.keys()) == list(osd.keys())
+    for k in rsd:
+        assert torch.equal(rsd[k], osd[k]), k
+    assert ours.temperature == ref.temperature and count_parameters(ours) == ref_count(ref)
+    drops = lambda m: [x.p for x in m.modules() if isinstance(x, torch.nn.Dropout)]
+    assert drops(ours.user_tower) == drops(ref.user_tower) and drops(ours.item_tower) == drops(ref.item_tower)
+    kinds = lambda m: [type(x).__name__ for x in m.mlp]
+    assert kinds(ours.user_tower) == kinds(ref.user_tower) and kinds(ours.item_tower) == kinds(ref.item_tower)
+
+
 def test_shard_bounds_cover_the_catalogue():
     from b200rec.dist import shard_bounds
     for n, w in ((10_000_000, 8), (1001, 4), (7, 8), (5, 1)):
