@@ -87,12 +87,15 @@ class TowerOracle:
                 if key in self.p:
                     embs.append(self.p[key][np.asarray(idx)])
                     fields.append((name, np.asarray(idx), self.p[key].shape[1]))
+        self.content_cache = None
         if content is not None and "content_projection.0.weight" in self.p:
             # ItemTower content branch (two_tower.py:184-191 Linear -> ReLU -> Dropout -> Linear, appended after the
-            # categorical embeddings :264-266); forward only, dropout 0 / eval
+            # categorical embeddings :264-266); dropout 0 / eval
             c = np.asarray(content, dtype=self.dtype)
-            h = np.maximum(c @ self.p["content_projection.0.weight"].T + self.p["content_projection.0.bias"], 0)
+            zc = c @ self.p["content_projection.0.weight"].T + self.p["content_projection.0.bias"]
+            h = np.maximum(zc, 0)
             embs.append(h @ self.p["content_projection.3.weight"].T + self.p["content_projection.3.bias"])
+            self.content_cache = (c, zc, h)
         if embs:
             x = np.concatenate([x] + embs, axis=-1)
         layers = []
@@ -164,6 +167,15 @@ class TowerOracle:
             gt[0] = 0
             grads[key] = gt
             off += width
+        if self.content_cache is not None:       # content branch: the last slice of the concatenated input
+            c, zc, h = self.content_cache
+            W3 = self.p["content_projection.3.weight"]
+            dproj = dx[:, off:off + W3.shape[0]]
+            grads["content_projection.3.weight"] = dproj.T @ h
+            grads["content_projection.3.bias"] = dproj.sum(0)
+            dzc = (dproj @ W3) * (zc > 0)
+            grads["content_projection.0.weight"] = dzc.T @ c
+            grads["content_projection.0.bias"] = dzc.sum(0)
         return grads, dx[:, :num_dim]
 
 

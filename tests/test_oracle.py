@@ -383,7 +383,8 @@ def test_round2_goldens_are_consistent(golden_dir):
 
 def test_oracle_content_projection_branch_matches_reference(golden_dir):
     """oracle.TowerOracle with the ItemTower content branch (two_tower.py:184-191,264-266) against the golden generated
-    from the imported reference: train-mode (batch statistics) and eval-mode embeddings."""
+    from the imported reference: train-mode (batch statistics) and eval-mode embeddings, and the gradient of
+    sum(emb * w) with respect to every parameter."""
     import os
     import numpy as np
     from oracle.two_tower import TowerOracle
@@ -394,6 +395,13 @@ def test_oracle_content_projection_branch_matches_reference(golden_dir):
         e = t.forward(g["numerical"], {"genre": g["genre"]}, training=training, content=g["content"],
                       update_running=training)
         assert np.abs(e - g[key]).max() <= 2e-6, key
+        if training:
+            # gradient of sum(emb * w) w.r.t. every parameter, the content_projection Linears and the table included
+            grads, _ = t.backward(g["w"])
+            want = {k[5:]: g[k] for k in g.files if k.startswith("grad.")}
+            assert set(grads) == set(want)
+            for k, ref in want.items():
+                assert np.abs(grads[k] - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1e-6), k
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not mounted")
