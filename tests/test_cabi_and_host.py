@@ -604,3 +604,5 @@ def test_bench_host_logic_without_a_gpu():
     assert peaks["tflops"] > 0 and peaks["hbm_gbs"] > 0 and peaks["tflops_burst"] >= peaks["tflops"]
     search, what = bench._cpu_search()
     assert search.__name__ == "search_reservoir" and "flat_select.c" in what
+    qps, dt, what2 = bench.cpu_retrieval_baseline(1 << 17, 64, 2)          # the GPU arm's cpu_baseline leg, tiny sample
+    assert qps > 0 and dt > 0 and what2 == what
